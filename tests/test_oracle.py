@@ -1,0 +1,138 @@
+"""CPU: pin the oracle restatement against the fixtures generated from the unmodified reference
+(tests/golden/make_golden.py) and, where /root/reference is mounted, against the live reference."""
+import math
+import os
+
+import pytest
+import torch
+
+import oracle
+from oracle import ViTConfig
+from oracle.ref_shim import reference_available, import_reference
+
+FULL = ["tiny65", "tiny17c100", "nocls_nomlp"]
+SUMMARY = ["full65", "full17c100"]
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+
+
+def _run_oracle(g, steps=3):
+    torch.set_num_threads(1)
+    cfg = ViTConfig(**g["cfg"])
+    params = oracle.init_params(cfg, seed=0)
+    x, y = oracle.hash_inputs(cfg, g["batch"], seed=1)
+    logits, loss, grads = oracle.train_step(params, x, y, cfg, g["smoothing"])
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    a = g["adam"]
+    losses = [loss.item()]
+    g_step = grads
+    for t in range(1, steps + 1):
+        oracle.adam_step(params, g_step, m, v, t, a["lr"], a["betas"], a["eps"], a["weight_decay"])
+        if t < steps:
+            _, l2, g_step = oracle.train_step(params, x, y, cfg, g["smoothing"])
+            losses.append(l2.item())
+    return cfg, logits, losses, grads, params
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_oracle_matches_reference_golden_full(golden_dir, name):
+    g = _load(golden_dir, name)
+    cfg, logits, losses, grads, params3 = _run_oracle(g)
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-5, atol=1e-6)
+    assert losses == pytest.approx(g["losses"], rel=1e-5)
+    for k, ref in g["grads"].items():
+        got = grads[k] if grads[k] is not None else torch.zeros_like(ref)
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"grad {k}: {m}")
+    for k, ref in g["params3"].items():
+        torch.testing.assert_close(params3[k], ref, rtol=1e-5, atol=2e-6, msg=lambda m, k=k: f"param {k}: {m}")
+    # attention maps (save_attn_map protocol, layers.py:99-100)
+    x, _ = oracle.hash_inputs(cfg, g["batch"], seed=1)
+    _, attn = oracle.vit_forward(oracle.init_params(cfg, 0), x, cfg, return_attn=True)
+    torch.testing.assert_close(attn, g["attn"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", SUMMARY)
+def test_oracle_matches_reference_golden_summary(golden_dir, name):
+    g = _load(golden_dir, name)
+    cfg, logits, losses, grads, params3 = _run_oracle(g)
+    torch.testing.assert_close(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    assert losses == pytest.approx(g["losses"], rel=1e-4)
+    for k, ref in g["grads"].items():
+        assert grads[k].double().norm().item() == pytest.approx(ref["norm"], rel=1e-4, abs=1e-9), k
+        torch.testing.assert_close(grads[k].flatten()[:16], ref["head"], rtol=1e-3, atol=1e-6)
+    for k, ref in g["params3"].items():
+        assert params3[k].double().norm().item() == pytest.approx(ref["norm"], rel=1e-5), k
+        torch.testing.assert_close(params3[k].flatten()[:16], ref["head"], rtol=1e-4, atol=1e-5)
+
+
+def test_param_count_matches_reference_readme():
+    # README.md:37 "6.3 M"; exact count probed from the reference
+    cfg = ViTConfig(num_classes=10, img_size=32, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+    shapes = cfg.param_shapes()
+    assert len(shapes) == 120
+    assert sum(math.prod(s) for s in shapes.values()) == 6_268_810
+    cfg = ViTConfig(num_classes=100, img_size=32, patch=4, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+    assert sum(math.prod(s) for s in cfg.param_shapes().values()) == 6_340_324
+
+
+def test_patch_layout_identity():
+    # words[b, ph*P+pw, (kh*ps+kw)*3+c] == x[b, c, ph*ps+kh, pw*ps+kw]   (vit.py:83-88)
+    cfg = ViTConfig(patch=4)
+    x, _ = oracle.hash_inputs(cfg, 2)
+    w = oracle.to_words(x, cfg)
+    ps, P = cfg.patch_size, cfg.patch
+    for (b, ph, pw, kh, kw, c) in [(0, 0, 0, 0, 0, 0), (1, 3, 2, 7, 5, 2), (0, 1, 3, 4, 0, 1)]:
+        assert w[b, ph * P + pw, (kh * ps + kw) * 3 + c] == x[b, c, ph * ps + kh, pw * ps + kw]
+
+
+def test_ls_ce_closed_form_gradient():
+    torch.manual_seed(0)
+    z = torch.randn(5, 10, requires_grad=True)
+    y = torch.randint(0, 10, (5,))
+    loss = oracle.ls_ce_loss(z, y, 10, 0.1)
+    loss.backward()
+    torch.testing.assert_close(z.grad, oracle.ls_ce_dlogits(z.detach(), y, 10, 0.1), rtol=1e-5, atol=1e-7)
+
+
+def test_adam_restatement_matches_torch_adam():
+    torch.manual_seed(0)
+    p0 = {"a": torch.randn(7, 5), "b": torch.randn(11)}
+    ours = {k: v.clone() for k, v in p0.items()}
+    theirs = [torch.nn.Parameter(v.clone()) for v in p0.values()]
+    opt = torch.optim.Adam(theirs, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
+    m = {k: torch.zeros_like(v) for k, v in p0.items()}
+    v = {k: torch.zeros_like(x) for k, x in p0.items()}
+    for t in range(1, 6):
+        g = {k: torch.randn_like(x) for k, x in p0.items()}
+        for p, gg in zip(theirs, g.values()):
+            p.grad = gg.clone()
+        opt.step()
+        oracle.adam_step(ours, g, m, v, t)
+    for p, k in zip(theirs, ours):
+        torch.testing.assert_close(ours[k], p.detach(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("kw", [
+    dict(num_classes=10, img_size=32, patch=8, num_layers=2, hidden=64, mlp_hidden=96, head=4),
+    dict(num_classes=100, img_size=32, patch=4, num_layers=1, hidden=64, mlp_hidden=64, head=2, is_cls_token=False),
+])
+def test_oracle_matches_live_reference(kw):
+    ref_vit, _, ref_crit = import_reference()
+    cfg = ViTConfig(**kw)
+    torch.manual_seed(2045)  # main.py:150
+    model = ref_vit.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, num_layers=cfg.num_layers,
+                        hidden=cfg.hidden, mlp_hidden=cfg.mlp_hidden, head=cfg.head, is_cls_token=cfg.is_cls_token)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}  # reference's own init
+    x = torch.randn(3, 3, 32, 32)
+    y = torch.randint(0, cfg.num_classes, (3,))
+    loss_ref = ref_crit.LabelSmoothingCrossEntropyLoss(cfg.num_classes, 0.1)(model(x), y)
+    loss_ref.backward()
+    logits, loss, grads = oracle.train_step(params, x, y, cfg, 0.1)
+    torch.testing.assert_close(logits, model(x).detach(), rtol=1e-5, atol=1e-6)
+    assert loss.item() == pytest.approx(loss_ref.item(), rel=1e-6)
+    for k, p in model.named_parameters():
+        torch.testing.assert_close(grads[k], p.grad, rtol=1e-4, atol=1e-6)
