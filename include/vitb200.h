@@ -1,0 +1,143 @@
+/*
+ * vitb200.h — C ABI of libvitb200.so: hand-written sm_100a kernels for the training hot path of
+ * mahbodnr/ViT-CIFAR (vit.ViT + layers.TransformerEncoder / MultiHeadSelfAttention + label-smoothing
+ * cross-entropy + Adam).
+ *
+ * The reference has no native layer: every entry point below replaces a run of
+ * PyTorch/ATen calls in the reference's Python, cited as `file:line` into the reference repository.
+ * The Python host (vit-cifar_b200/) binds these with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller, alive until `stream` has passed the call.
+ *  - Nothing allocates, nothing synchronises the host; every kernel runs on the `stream` argument
+ *    (a cudaStream_t passed as void*), so calls can be captured into a CUDA graph.
+ *  - Return value: 0 = ok; < 0 = bad argument (vitb_last_error() has the text); > 0 = cudaError_t.
+ *  - `dt` selects the ACTIVATION storage type: VITB_F32 (check mode: fp32 storage, SIMT fp32 math)
+ *    or VITB_BF16 (bf16 storage, fp32 accumulation; tcgen05 tensor-core GEMMs, mma.sync attention).
+ *    Parameters, gradients and optimiser state are always fp32; `w_act` arguments are the weight
+ *    in the activation type (the bf16 shadow written by vitb_adam_multi / vitb_cast_f32_to_bf16,
+ *    or the fp32 master itself in check mode).
+ *  - Row-major everywhere. "rows" is B*T (tokens of the whole batch).
+ */
+#ifndef VITB200_H_
+#define VITB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITB_F32 0
+#define VITB_BF16 1
+
+#define VITB_ABI_VERSION 1
+
+/* ABI version of the loaded library (== VITB_ABI_VERSION). */
+int vitb_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* vitb_last_error(void);
+/* 1 if the current device is compute capability 10.x, else 0 (the kernels are sm_100a only). */
+int vitb_device_supported(void);
+
+/* fp32 -> bf16 copy of a flat buffer (weight shadow refresh after an external optimiser step). */
+int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- patch embedding: vit.py:79-89 (_to_words), vit.py:67 (emb), vit.py:68-70 (cls cat + pos_emb) ----
+ * img   fp32 (B,3,S,S) NCHW;   w fp32 (H, K) with K = (S/P)^2*3, feature index (kh*ps+kw)*3+c
+ * bias  fp32 (H);  cls fp32 (H) or NULL when has_cls == 0;  pos fp32 (T,H), T = P*P + has_cls
+ * out   act  (B,T,H):  out[b,0] = cls+pos[0];  out[b,has_cls+n] = words[b,n]·wᵀ + bias + pos[has_cls+n]
+ * P is the number of patches per side (the reference's `patch`, vit.py:37). */
+int vitb_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* cls,
+                         const float* pos, void* out, int B, int S, int P, int H, int has_cls,
+                         int dt, void* stream);
+/* Backward of the above (autograd of vit.py:66-70). dout act (B,T,H).  Writes (overwrites)
+ * dw (H,K), dbias (H), dcls (H) (may be NULL), dpos (T,H).  ws: vitb_patch_embed_bwd_ws_bytes(). */
+size_t vitb_patch_embed_bwd_ws_bytes(int B, int S, int P, int H, int has_cls);
+int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* dbias, float* dcls,
+                         float* dpos, void* ws, size_t ws_bytes, int B, int S, int P, int H,
+                         int has_cls, int dt, void* stream);
+
+/* ---- LayerNorm: layers.py:26,30,45,47 (la1/la2), vit.py:62 (fc[0]); eps 1e-5, affine ----
+ * x act, row r at x + r*x_row_stride elements (lets the head read out[:,0], vit.py:73); y act (rows,H)
+ * mean/rstd fp32 (rows) saved for backward. */
+int vitb_layernorm_fwd(const void* x, int64_t x_row_stride, const float* gamma, const float* beta,
+                       void* y, float* mean, float* rstd, int rows, int H, float eps, int dt,
+                       void* stream);
+/* dx = LN'(dy) (+ dres if dres != NULL: the residual branch of layers.py:45/47).
+ * dx row r at dx + r*dx_row_stride.  dgamma/dbeta fp32 (H) overwritten.  If dx_colsum != NULL it
+ * receives sum over rows of dx (H) = bias gradient of the Linear that produced the LN input.
+ * ws: vitb_layernorm_bwd_ws_bytes(rows, H). */
+size_t vitb_layernorm_bwd_ws_bytes(int rows, int H);
+int vitb_layernorm_bwd(const void* dy, const void* x, int64_t x_row_stride, const float* gamma,
+                       const float* mean, const float* rstd, const void* dres, void* dx,
+                       int64_t dx_row_stride, float* dgamma, float* dbeta, float* dx_colsum,
+                       void* ws, size_t ws_bytes, int rows, int H, int dt, void* stream);
+
+/* ---- Linear layers: layers.py:81-85,92-94,102 (Wq/Wk/Wv/out_project), layers.py:33-37 (mlp),
+ *      vit.py:63,76 (fc[1]).  GELU is exact/erf (nn.GELU default).
+ * C[M,N] = act(A[M,K] · W[N,K]ᵀ + bias[N]) (+ residual[M,N]);  if preact != NULL the value before
+ * GELU is stored there (needed by backward).  flags: VITB_GEMM_GELU.  A,W,residual,C,preact: act type.
+ * bf16: tcgen05 path, needs N % 128 == 0 and K % 64 == 0 (else falls to the SIMT kernel). */
+#define VITB_GEMM_GELU 1
+#define VITB_GEMM_OUT_F32 2 /* C is fp32 regardless of dt (head logits) */
+int vitb_gemm_bias_act_fwd(const void* a, const void* w_act, const float* bias, const void* residual,
+                           void* c, void* preact, int M, int N, int K, int flags, int dt, void* stream);
+/* dX[M,K] = dY[M,N] · W[N,K]  (* gelu'(z[M,K]) if z != NULL: fuses the GELU backward of the layer
+ * that produced this Linear's input, layers.py:34/37). */
+int vitb_gemm_dgrad(const void* dy, const void* w_act, const void* z, void* dx, int M, int N, int K,
+                    int flags, int dt, void* stream);
+/* dW[N,K] (fp32) = dY[M,N]ᵀ · X[M,K];  dbias[N] (fp32) = column sums of dY (if dbias != NULL).
+ * Overwrites.  Split over M with a fixed-order second pass (deterministic).
+ * flags: VITB_GEMM_DY_F32: dY is fp32 regardless of dt (head dlogits). */
+#define VITB_GEMM_DY_F32 4
+size_t vitb_gemm_wgrad_ws_bytes(int M, int N, int K, int dt);
+int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias, void* ws,
+                          size_t ws_bytes, int M, int N, int K, int flags, int dt, void* stream);
+
+/* ---- attention core: layers.py:92-101.  qkv act (B,T,3H) = [Q | K | V] per token, head h owns
+ * columns h*d..h*d+d-1 of each third;  o act (B,T,H) (= attn.flatten(2), layers.py:102)
+ * lse fp32 (B,heads,T): log-sum-exp of the scaled scores (saved instead of the (B,h,T,T) map).
+ * attn_map fp32 (B,heads,T,T) or NULL: the softmax map itself (save_attn_map, layers.py:99-100).
+ * scale = 1/sqrt(features) (layers.py:79,97).  d in {32,64}, T <= 128. */
+int vitb_attn_fwd(const void* qkv, void* o, float* lse, float* attn_map, int B, int T, int heads,
+                  int d, float scale, int dt, void* stream);
+/* dqkv act (B,T,3H) from do act (B,T,H): dP = dO·Vᵀ; dS = P∘(dP − rowsum(P∘dP)); dQ = dS·K·scale;
+ * dK = dSᵀ·Q·scale; dV = Pᵀ·dO (autograd of layers.py:96-101). P is recomputed from lse. */
+int vitb_attn_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int T,
+                  int heads, int d, float scale, int dt, void* stream);
+
+/* ---- GELU backward + column sums: dz = dy * gelu'(z); colsum fp32 (cols) = sum over rows of dz
+ * (bias gradient of the Linear before the GELU, layers.py:36-37) if colsum != NULL. ---- */
+size_t vitb_colsum_ws_bytes(int rows, int cols);
+int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum, void* ws,
+                         size_t ws_bytes, int rows, int cols, int dt, void* stream);
+/* colsum fp32 (cols) = sum over rows of x act (rows, cols). */
+int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int rows, int cols, int dt,
+                void* stream);
+
+/* ---- token pooling for the head: vit.py:72-75.  mode 0: y[b] = x[b,0] (cls); mode 1: mean over T.
+ * bwd: dx (B,T,H) fully written (zeros where no gradient flows). */
+int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream);
+int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int dt, void* stream);
+
+/* ---- label-smoothing cross-entropy: criterions.py:13-19.  logits fp32 (B,C), labels int64 (B).
+ * loss (1 float) = mean_i sum_j -q_ij log_softmax(z_i)_j, q_iy = 1-s, q_ij = s/(C-1) otherwise.
+ * dlogits fp32 (B,C) = (softmax(z) - q) * (grad_scale / B)  (may be NULL: forward only). ---- */
+int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, float* dlogits,
+                       int B, int C, float smoothing, float grad_scale, void* stream);
+
+/* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77
+ * (lr main.py:48, betas :51-52, weight_decay :56, eps 1e-8).  g is multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce).  hyper: HOST values {step_size = lr/(1-b1^t),
+ * bc2_sqrt = sqrt(1-b2^t), beta1, beta2, eps, weight_decay, grad_scale, 0}.  If hyper_dev != NULL
+ * the 8 floats are read from device memory instead (so a captured CUDA graph sees new values).
+ * w_shadow (bf16, n) may be NULL; else it receives the updated parameters rounded to bf16. ---- */
+int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow, int64_t n,
+                    const float* hyper_host, const float* hyper_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H_ */

@@ -1,0 +1,81 @@
+"""Build libvitb200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+    python vit-cifar_b200/build.py [--force]
+
+The library is compiled for sm_100a only (`-gencode arch=compute_100a,code=sm_100a -lineinfo`); nvcc
+cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the repo
+snapshot, so nothing is JIT-compiled at run time.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB_PATH = os.path.join(HERE, "libvitb200.so")
+
+SOURCES = ["elementwise.cu", "loss_adam.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu"]
+HEADERS = ["common.cuh", "gemm_internal.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; libvitb200.so cannot be built")
+    return cand
+
+
+def _newest_input() -> float:
+    paths = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(INCLUDE, "vitb200.h"), __file__]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def needs_build() -> bool:
+    return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _newest_input()
+
+
+def _compile(src: str) -> str:
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(OBJ_DIR, src.replace(".cu", ".ptxas.log"))
+    with open(log, "w") as f:
+        f.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with cf.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(_compile, SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(f"built {LIB_PATH}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    build_library(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,158 @@
+// common.cuh — shared device/host helpers for libvitb200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vitb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvitb200 is written for sm_100a (B200) only"
+#endif
+
+namespace vitb {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define VITB_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::vitb::set_error(__VA_ARGS__);      \
+      return -1;                           \
+    }                                      \
+  } while (0)
+
+#define VITB_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::vitb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+// after a kernel launch
+#define VITB_LAUNCH_OK() VITB_CUDA_OK(cudaPeekAtLastError())
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// activation storage types
+// ---------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct Act;
+template <> struct Act<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Act<bf16> {
+  static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 4 consecutive activations <-> float4 (8-byte access for bf16, 16-byte for fp32)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// math
+// ---------------------------------------------------------------------------------------------
+// exact (erf) GELU, nn.GELU() default (layers.py:34,37)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx [x Phi(x)] = Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-order reduction of per-block partials: out_k[c] = sum_p ws[k][p][c]   (k = blockIdx.y < 3)
+// (template so that every translation unit can instantiate it without relocatable device code)
+// ---------------------------------------------------------------------------------------------
+template <int kUnused = 0>
+__global__ void partials_finalize_kernel(const float* __restrict__ ws, int nparts, int64_t cols,
+                                         float* out0, float* out1, float* out2) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+  if (c >= cols || out == nullptr) return;
+  const float* p = ws + (size_t)k * nparts * cols + c;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = 0;
+  for (; i + 4 <= nparts; i += 4) {
+    s0 += p[(size_t)(i + 0) * cols];
+    s1 += p[(size_t)(i + 1) * cols];
+    s2 += p[(size_t)(i + 2) * cols];
+    s3 += p[(size_t)(i + 3) * cols];
+  }
+  for (; i < nparts; ++i) s0 += p[(size_t)i * cols];
+  out[c] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM epilogue description shared by the SIMT (fp32 check mode / small shapes) and tcgen05 paths
+// ---------------------------------------------------------------------------------------------
+enum EpiMode { EPI_FWD = 0, EPI_DGRAD = 1, EPI_RAW_F32 = 2 };
+
+struct EpiParams {
+  int mode;              // EpiMode
+  int gelu;              // EPI_FWD: apply exact GELU after bias
+  int out_f32;           // EPI_FWD: `out` is fp32 regardless of the activation type
+  const float* bias;     // [N] or null
+  const void* residual;  // [M,N] act or null (added after GELU)
+  void* out;             // [M,N] act (or fp32 for RAW/out_f32)
+  void* preact;          // [M,N] act or null: value before GELU
+  const void* aux;       // EPI_DGRAD: z [M,N] act or null -> multiply by gelu'(z)
+  int64_t ldc;           // row pitch of out/residual/preact/aux in elements
+  // output row remap (patch embedding writes token rows of a (B,T,H) tensor and adds pos_emb):
+  // phys_row = (m / rm_group) * rm_stride + rm_offset + m % rm_group ; pos row = phys_row % rm_stride
+  int rm_group, rm_stride, rm_offset;
+  const float* pos;      // [rm_stride, N] fp32 or null
+};
+
+}  // namespace vitb

@@ -1,0 +1,416 @@
+// elementwise.cu — HBM-bound kernels: LayerNorm fwd/bwd (+residual grad, +column sums), GELU backward
+// with fused bias-gradient column sums, column sums, token pooling, fp32->bf16 shadow cast.
+// All are one-pass, 8/16-byte vectorised, warp-shuffle reductions, fp32 math on bf16/fp32 storage.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vitb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cast
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    st4(dst + i * 4, ld4(src + i * 4));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, VEC float4-groups per lane (H = 128*VEC)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, int64_t xs,
+                                                     const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd,
+                                                     int rows, float eps) {
+  constexpr int H = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + (int64_t)row * xs;
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = ld4(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rs = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+  T* yr = y + (int64_t)row * H;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = ld4(gamma + c), b = ld4(beta + c);
+    float4 o;
+    o.x = (v[i].x - mu) * rs * g.x + b.x;
+    o.y = (v[i].y - mu) * rs * g.y + b.y;
+    o.z = (v[i].z - mu) * rs * g.z + b.z;
+    o.w = (v[i].w - mu) * rs * g.w + b.w;
+    st4(yr + c, o);
+  }
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward (+ residual gradient add, + dgamma/dbeta/colsum(dx) partials)
+// grid-stride over rows, one warp per row; per-block partials -> ws[3][gridDim.x][H]
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnBwdWarps = 8;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kLnBwdWarps * 32)
+    ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t xs,
+                  const float* __restrict__ gamma, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
+                  int64_t dxs, float* __restrict__ ws, int want_colsum, int rows) {
+  constexpr int H = VEC * 128;
+  __shared__ float red[kLnBwdWarps][H];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 gam[VEC], dg[VEC], db[VEC], dc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    gam[i] = ld4(gamma + (i * 32 + lane) * 4);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = dg[i];
+    dc[i] = dg[i];
+  }
+  for (int row = blockIdx.x * kLnBwdWarps + warp; row < rows; row += gridDim.x * kLnBwdWarps) {
+    const T* xr = x + (int64_t)row * xs;
+    const T* dyr = dy + (int64_t)row * H;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[VEC], d[VEC];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 xv = ld4(xr + c);
+      d[i] = ld4(dyr + c);
+      xh[i].x = (xv.x - mu) * rs;
+      xh[i].y = (xv.y - mu) * rs;
+      xh[i].z = (xv.z - mu) * rs;
+      xh[i].w = (xv.w - mu) * rs;
+      // parameter gradients use dy, the input gradient uses g = dy * gamma
+      dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y;
+      dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
+      db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+      d[i].x *= gam[i].x; d[i].y *= gam[i].y; d[i].z *= gam[i].z; d[i].w *= gam[i].w;
+      c1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      c2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    c1 = warp_sum(c1) * (1.0f / H);
+    c2 = warp_sum(c2) * (1.0f / H);
+    T* dxr = dx + (int64_t)row * dxs;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rs * (d[i].x - c1 - xh[i].x * c2);
+      o.y = rs * (d[i].y - c1 - xh[i].y * c2);
+      o.z = rs * (d[i].z - c1 - xh[i].z * c2);
+      o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+      if (dres != nullptr) {
+        const float4 r = ld4(dres + (int64_t)row * H + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      st4(dxr + c, o);
+      dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w;
+    }
+  }
+  // block reduction of the three partial vectors, one at a time through the same smem
+  const int nparts = gridDim.x;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    if (k == 2 && !want_colsum) break;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 v = k == 0 ? dg[i] : (k == 1 ? db[i] : dc[i]);
+      *reinterpret_cast<float4*>(&red[warp][(i * 32 + lane) * 4]) = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnBwdWarps; ++w) s += red[w][c];
+      ws[((size_t)k * nparts + blockIdx.x) * H + c] = s;
+    }
+  }
+}
+
+static int ln_bwd_blocks(int rows) {
+  int b = ceil_div(rows, kLnBwdWarps);
+  return b < 2 * kNumSMs ? (b < 1 ? 1 : b) : 2 * kNumSMs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-streaming kernels with per-column partial sums: GELU backward, plain column sums
+// block = (TX column groups of 4) x (TY rows); grid = (row parts, column chunks)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool GELU_BWD>
+__global__ void __launch_bounds__(256)
+    rows_colsum_kernel(const T* __restrict__ a, const T* __restrict__ z, T* __restrict__ out,
+                       float* __restrict__ ws, int rows, int cols) {
+  __shared__ float4 red[256];
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int c = (blockIdx.y * TX + tx) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x * TY + ty; r < rows; r += gridDim.x * TY) {
+    const size_t off = (size_t)r * cols + c;
+    float4 v = ld4(a + off);
+    if (GELU_BWD) {
+      const float4 zz = ld4(z + off);
+      v.x *= gelu_grad_f(zz.x);
+      v.y *= gelu_grad_f(zz.y);
+      v.z *= gelu_grad_f(zz.z);
+      v.w *= gelu_grad_f(zz.w);
+      st4(out + off, v);
+    }
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (ws == nullptr) return;
+  red[ty * TX + tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < TY; ++j) {
+      const float4 o = red[j * TX + tx];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *reinterpret_cast<float4*>(ws + (size_t)blockIdx.x * cols + c) = acc;
+  }
+}
+
+struct RowsGeom {
+  int tx, ty, gx, gy;
+};
+static bool rows_geom(int rows, int cols, RowsGeom* g) {
+  if (cols % 128 != 0) return false;
+  const int cg = cols / 4;
+  int tx = 32;
+  for (int cand : {128, 96, 64, 32})
+    if (cg % cand == 0) { tx = cand; break; }
+  g->tx = tx;
+  g->ty = 256 / tx;
+  g->gy = cg / tx;
+  int gx = ceil_div(rows, g->ty * 4);
+  const int cap = (4 * kNumSMs + g->gy - 1) / g->gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  g->gx = gx;
+  return true;
+}
+
+template <typename T>
+static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out, float* colsum,
+                              void* ws, size_t ws_bytes, int rows, int cols, cudaStream_t st) {
+  RowsGeom g;
+  VITB_REQUIRE(rows_geom(rows, cols, &g), "colsum: cols=%d must be a multiple of 128", cols);
+  float* wsf = nullptr;
+  if (colsum != nullptr) {
+    VITB_REQUIRE(ws != nullptr && ws_bytes >= (size_t)g.gx * cols * sizeof(float),
+                 "colsum: workspace too small (%zu < %zu)", ws_bytes, (size_t)g.gx * cols * sizeof(float));
+    wsf = (float*)ws;
+  }
+  dim3 grid(g.gx, g.gy), block(g.tx, g.ty);
+  if (gelu)
+    rows_colsum_kernel<T, true><<<grid, block, 0, st>>>((const T*)a, (const T*)z, (T*)out, wsf, rows, cols);
+  else
+    rows_colsum_kernel<T, false><<<grid, block, 0, st>>>((const T*)a, nullptr, nullptr, wsf, rows, cols);
+  VITB_LAUNCH_OK();
+  if (colsum != nullptr) {
+    partials_finalize_kernel<0><<<dim3(ceil_div(cols, 256), 1), 256, 0, st>>>(wsf, g.gx, cols, colsum, nullptr, nullptr);
+    VITB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling (vit.py:72-75)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn, int H, int mode) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    float4 acc = ld4(x + ((size_t)b * Tn) * H + c);
+    if (mode == 1) {
+      for (int t = 1; t < Tn; ++t) {
+        const float4 v = ld4(x + ((size_t)b * Tn + t) * H + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const float inv = 1.0f / Tn;
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    st4(y + (size_t)b * H + c, acc);
+  }
+}
+
+template <typename T>
+__global__ void pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Tn, int H, int mode) {
+  const size_t total4 = (size_t)B * Tn * H / 4;
+  const float inv = 1.0f / Tn;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int c = (int)(e % H);
+    const size_t bt = e / H;
+    const int t = (int)(bt % Tn);
+    const size_t b = bt / Tn;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == 1) {
+      v = ld4(dy + b * H + c);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    } else if (t == 0) {
+      v = ld4(dy + b * H + c);
+    }
+    st4(dx + e, v);
+  }
+}
+
+}  // namespace vitb
+
+using namespace vitb;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int vitb_version(void) { return VITB_ABI_VERSION; }
+const char* vitb_last_error(void) { return g_err; }
+
+int vitb_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  VITB_REQUIRE(src && dst && n >= 0, "cast: null pointer");
+  if (n == 0) return 0;
+  VITB_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "cast: buffers must be 16/8-byte aligned");
+  int blocks = (int)ceil_div64(n / 4 + 1, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+#define VITB_DISPATCH_VEC(H, ...)                                                     \
+  switch ((H) / 128) {                                                                \
+    case 1: { constexpr int VEC = 1; __VA_ARGS__; } break;                            \
+    case 2: { constexpr int VEC = 2; __VA_ARGS__; } break;                            \
+    case 3: { constexpr int VEC = 3; __VA_ARGS__; } break;                            \
+    case 4: { constexpr int VEC = 4; __VA_ARGS__; } break;                            \
+    case 6: { constexpr int VEC = 6; __VA_ARGS__; } break;                            \
+    case 8: { constexpr int VEC = 8; __VA_ARGS__; } break;                            \
+    default: ::vitb::set_error("layernorm: H=%d unsupported (128*{1,2,3,4,6,8})", H); return -1; \
+  }
+
+int vitb_layernorm_fwd(const void* x, int64_t xs, const float* gamma, const float* beta, void* y,
+                       float* mean, float* rstd, int rows, int H, float eps, int dt, void* stream) {
+  VITB_REQUIRE(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  VITB_REQUIRE(rows >= 0 && H % 128 == 0 && xs % 4 == 0, "layernorm_fwd: bad shape rows=%d H=%d stride=%lld", rows, H, (long long)xs);
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ceil_div(rows, 8);
+  if (dt == VITB_BF16) {
+    VITB_DISPATCH_VEC(H, (ln_fwd_kernel<bf16, VEC><<<blocks, 256, 0, st>>>((const bf16*)x, xs, gamma, beta, (bf16*)y, mean, rstd, rows, eps)));
+  } else {
+    VITB_DISPATCH_VEC(H, (ln_fwd_kernel<float, VEC><<<blocks, 256, 0, st>>>((const float*)x, xs, gamma, beta, (float*)y, mean, rstd, rows, eps)));
+  }
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+size_t vitb_layernorm_bwd_ws_bytes(int rows, int H) {
+  return (size_t)3 * ln_bwd_blocks(rows) * H * sizeof(float);
+}
+
+int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* gamma, const float* mean,
+                       const float* rstd, const void* dres, void* dx, int64_t dxs, float* dgamma,
+                       float* dbeta, float* dx_colsum, void* ws, size_t ws_bytes, int rows, int H, int dt,
+                       void* stream) {
+  VITB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && ws, "layernorm_bwd: null pointer");
+  VITB_REQUIRE(rows > 0 && H % 128 == 0 && xs % 4 == 0 && dxs % 4 == 0, "layernorm_bwd: bad shape");
+  VITB_REQUIRE(ws_bytes >= vitb_layernorm_bwd_ws_bytes(rows, H), "layernorm_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ln_bwd_blocks(rows);
+  const int want = dx_colsum != nullptr;
+  if (dt == VITB_BF16) {
+    VITB_DISPATCH_VEC(H, (ln_bwd_kernel<bf16, VEC><<<blocks, kLnBwdWarps * 32, 0, st>>>(
+                             (const bf16*)dy, (const bf16*)x, xs, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dxs, (float*)ws, want, rows)));
+  } else {
+    VITB_DISPATCH_VEC(H, (ln_bwd_kernel<float, VEC><<<blocks, kLnBwdWarps * 32, 0, st>>>(
+                             (const float*)dy, (const float*)x, xs, gamma, mean, rstd, (const float*)dres, (float*)dx, dxs, (float*)ws, want, rows)));
+  }
+  VITB_LAUNCH_OK();
+  partials_finalize_kernel<0><<<dim3(ceil_div(H, 256), 3), 256, 0, st>>>((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+size_t vitb_colsum_ws_bytes(int rows, int cols) {
+  RowsGeom g;
+  if (!rows_geom(rows, cols, &g)) return 0;
+  return (size_t)g.gx * cols * sizeof(float);
+}
+
+int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes,
+                         int rows, int cols, int dt, void* stream) {
+  VITB_REQUIRE(dy && z && dz && rows > 0, "gelu_bwd: null pointer / empty");
+  if (dt == VITB_BF16) return launch_rows_colsum<bf16>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+  return launch_rows_colsum<float>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+}
+
+int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int rows, int cols, int dt, void* stream) {
+  VITB_REQUIRE(x && colsum && rows > 0, "colsum: null pointer / empty");
+  if (dt == VITB_BF16) return launch_rows_colsum<bf16>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+  return launch_rows_colsum<float>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+}
+
+int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream) {
+  VITB_REQUIRE(x && y && B > 0 && T > 0 && H % 4 == 0 && (mode == 0 || mode == 1), "pool_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == VITB_BF16) pool_fwd_kernel<bf16><<<B, 128, 0, st>>>((const bf16*)x, (bf16*)y, B, T, H, mode);
+  else pool_fwd_kernel<float><<<B, 128, 0, st>>>((const float*)x, (float*)y, B, T, H, mode);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int dt, void* stream) {
+  VITB_REQUIRE(dy && dx && B > 0 && T > 0 && H % 4 == 0 && (mode == 0 || mode == 1), "pool_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)ceil_div64((int64_t)B * T * H / 4, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (dt == VITB_BF16) pool_bwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dy, (bf16*)dx, B, T, H, mode);
+  else pool_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (float*)dx, B, T, H, mode);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

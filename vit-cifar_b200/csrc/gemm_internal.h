@@ -1,0 +1,30 @@
+// gemm_internal.h — host-side interfaces shared between gemm_simt.cu and gemm_tc.cu (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace vitb {
+
+// C[M,N] = sum_k A(m,k) * B(k,n), generic strides (elements).
+//   A(m,k) = a[m*a_sm + kmap(k)],  kmap(k) = k*a_sk, or with a_kgroup > 0:
+//            (k / a_kgroup) * a_kgroup_stride + (k % a_kgroup) * a_sk + a_koff
+//   B(k,n) = b[k*b_sk + n*b_sn]
+//   gather: operand is the patch matrix of an NCHW fp32 image (vit.py:79-89):
+//            words(m, f) = img[b][c][ph*ps+kh][pw*ps+kw], m = (b*P+ph)*P+pw, f = (kh*ps+kw)*3+c
+//            a_gather: A(m,k) = words(m,k);  b_gather: B(k,n) = words(k,n)
+struct SimtGemmArgs {
+  const void* a;
+  const void* b;
+  int M, N, K;
+  int64_t a_sm, a_sk;
+  int a_kgroup;
+  int64_t a_kgroup_stride, a_koff;
+  int64_t b_sk, b_sn;
+  int a_gather, b_gather, gather_S, gather_P;
+  EpiParams e;
+};
+
+int simt_gemm_launch(const SimtGemmArgs& g, int a_dt, int b_dt, int o_dt, int splits, cudaStream_t st);
+int simt_pick_splits(int tiles, int K);
+int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t ld, int x_dt, cudaStream_t st);
+
+}  // namespace vitb

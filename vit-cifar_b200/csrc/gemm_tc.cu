@@ -1,0 +1,544 @@
+// gemm_tc.cu — bf16 tensor-core GEMM for sm_100a: TMA (128B swizzle) -> shared-memory ring ->
+// tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue with fused
+// bias / GELU / residual / pre-activation save / GELU-backward, or fp32 split-K partials.
+//
+// One persistent kernel, three roles (warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
+// warps 2-5: epilogue), two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Operand layouts are chosen per GEMM so no tensor is ever transposed in memory:
+//   fwd   C[M,N]  = A[M,K]   · W[N,K]ᵀ : A K-major,  B K-major
+//   dgrad dX[M,K] = dY[M,N]  · W[N,K]  : A K-major,  B MN-major (reduction runs over W's rows)
+//   wgrad dW[N,K] = dY[M,N]ᵀ · X[M,K]  : A MN-major, B MN-major (reduction runs over the rows of both)
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_internal.h"
+
+namespace vitb {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 along the contiguous dimension
+constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
+constexpr int kTcThreads = 192;  // 6 warps
+
+struct TcArgs {
+  int M;             // valid output rows (C rows; for wgrad: N_out)
+  int N;             // output columns (multiple of BN)
+  int num_m_blocks, num_n_blocks, splits;
+  int kblocks_total, kblocks_per_split;
+  EpiParams e;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Wait with a wall-clock bound: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("vitb gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+constexpr uint32_t tmem_cols() {
+  return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr uint32_t kABytes = BM * BK * 2;
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBarOff = STAGES * kStageBytes;
+  static constexpr uint32_t kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers: one thread = one output row, 32 consecutive columns per call
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row32_bf16(const bf16* p, float (&f)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = q[i];
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[i * 8 + 0] = a.x; f[i * 8 + 1] = a.y; f[i * 8 + 2] = b.x; f[i * 8 + 3] = b.y;
+    f[i * 8 + 4] = c.x; f[i * 8 + 5] = c.y; f[i * 8 + 6] = d.x; f[i * 8 + 7] = d.y;
+  }
+}
+__device__ __forceinline__ void store_row32_bf16(bf16* p, const float (&f)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+    u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+    u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    q[i] = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcArgs p) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  auto a_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes; };
+  auto b_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes + S::kABytes; };
+  const uint32_t bar_base = smem_base + S::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (uint32_t)(STAGES + s) * 8; };
+  auto tfull_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + a) * 8; };
+  auto tempty_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + 2 + a) * 8; };
+  const uint32_t tmem_slot = bar_base + (2 * STAGES + 4) * 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOff + (2 * STAGES + 4) * 8);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols<BN>()) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int tiles_per_split = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = tiles_per_split * p.splits;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_per_split;
+        const int rem = tile - split * tiles_per_split;
+        const int m0 = (rem / p.num_n_blocks) * BM;
+        const int n0 = (rem % p.num_n_blocks) * BN;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_stage(stage) + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_per_split;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; ++kk) {
+            // K-major: advance 16 elements (32 B) inside the swizzle atom; SBO = 8 rows * 128 B.
+            // MN-major: advance 16 k-rows (2048 B); SBO = 8 k-rows * 128 B, LBO = next 64-wide MN atom.
+            const uint64_t adesc = A_MN ? make_smem_desc(a_stage(stage) + kk * (UK * 128), BK * 128, 1024)
+                                        : make_smem_desc(a_stage(stage) + kk * (UK * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_stage(stage) + kk * (UK * 128), BK * 128, 1024)
+                                        : make_smem_desc(b_stage(stage) + kk * (UK * 2), 16, 1024);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const EpiParams& e = p.e;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_per_split;
+      const int rem = tile - split * tiles_per_split;
+      const int m0 = (rem / p.num_n_blocks) * BM;
+      const int n0 = (rem % p.num_n_blocks) * BN;
+      const int grow = m0 + row_in_tile;
+      const bool valid = grow < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        tc_ld32(taddr + (uint32_t)c0, raw);
+        tc_wait_ld();
+        if (c0 + 32 >= BN) {  // accumulator fully drained into registers: hand the stage back
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (!valid) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        const int col = n0 + c0;
+        if (e.mode == EPI_RAW_F32) {
+          float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + col;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          continue;
+        }
+        const size_t off = (size_t)grow * e.ldc + col;
+        if (e.mode == EPI_FWD) {
+          if (e.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (e.preact != nullptr) store_row32_bf16((bf16*)e.preact + off, v);
+          if (e.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+          }
+          if (e.residual != nullptr) {
+            float r[32];
+            load_row32_bf16((const bf16*)e.residual + off, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+        } else {  // EPI_DGRAD
+          if (e.aux != nullptr) {
+            float z[32];
+            load_row32_bf16((const bf16*)e.aux + off, z);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_f(z[j]);
+          }
+        }
+        store_row32_bf16((bf16*)e.out + off, v);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // teardown: everyone done with TMEM before the owning warp frees it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols<BN>()) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] (inner contiguous), box = 64 x box_outer, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  VITB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  VITB_REQUIRE(((uintptr_t)ptr % 16 == 0) && (pitch_elems * 2) % 16 == 0, "gemm_tc: operand must be 16-byte aligned with a 16-byte multiple pitch");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VITB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu pitch=%llu box=%u)", (int)r,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_outer);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
+    configured = true;
+  }
+  const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kern<<<grid, kTcThreads, S::kDynBytes, st>>>(ma, mb, args);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+constexpr int kBN = 128;
+constexpr int kStages = 6;
+
+static bool tc_shape_ok(int N, int K) { return N % kBN == 0 && K % BK == 0; }
+
+static int check_dt(int dt) {
+  VITB_REQUIRE(dt == VITB_F32 || dt == VITB_BF16, "dt must be VITB_F32 or VITB_BF16 (got %d)", dt);
+  return 0;
+}
+
+}  // namespace vitb
+
+using namespace vitb;
+
+extern "C" {
+
+int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, const void* residual, void* c, void* preact,
+                           int M, int N, int K, int flags, int dt, void* stream) {
+  VITB_REQUIRE(a && w && c, "gemm_fwd: null pointer");
+  VITB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_fwd: bad shape M=%d N=%d K=%d", M, N, K);
+  if (check_dt(dt)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiParams e = {};
+  e.mode = EPI_FWD; e.gelu = (flags & VITB_GEMM_GELU) ? 1 : 0; e.out_f32 = (flags & VITB_GEMM_OUT_F32) ? 1 : 0;
+  e.bias = bias; e.residual = residual; e.out = c; e.preact = preact; e.ldc = N;
+  if (dt == VITB_BF16 && tc_shape_ok(N, K) && !e.out_f32) {
+    CUtensorMap ma, mb;
+    if (make_map(&ma, a, K, M, K, BM)) return -1;
+    if (make_map(&mb, w, K, N, K, kBN)) return -1;
+    TcArgs t = {};
+    t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
+    t.kblocks_total = K / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
+    return launch_tc<kBN, false, false, kStages>(ma, mb, t, st);
+  }
+  SimtGemmArgs g = {};
+  g.a = a; g.b = w; g.M = M; g.N = N; g.K = K;
+  g.a_sm = K; g.a_sk = 1; g.b_sk = 1; g.b_sn = K; g.e = e;
+  return simt_gemm_launch(g, dt, dt, dt, 1, st);
+}
+
+int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int M, int N, int K, int flags, int dt, void* stream) {
+  VITB_REQUIRE(dy && w && dx, "gemm_dgrad: null pointer");
+  VITB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_dgrad: bad shape M=%d N=%d K=%d", M, N, K);
+  if (check_dt(dt)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dy_f32 = (flags & VITB_GEMM_DY_F32) ? 1 : 0;
+  EpiParams e = {};
+  e.mode = EPI_DGRAD; e.out = dx; e.aux = z; e.ldc = K;
+  // GEMM view: C[M, K] = dY[M, N] (K-major, reduction N) x W[N, K] (MN-major: reduction over rows)
+  if (dt == VITB_BF16 && !dy_f32 && K % kBN == 0 && N % BK == 0) {
+    CUtensorMap ma, mb;
+    if (make_map(&ma, dy, N, M, N, BM)) return -1;
+    if (make_map(&mb, w, K, N, K, 64)) return -1;  // box: 64 output columns x 64 reduction rows
+    TcArgs t = {};
+    t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
+    t.kblocks_total = N / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
+    return launch_tc<kBN, false, true, kStages>(ma, mb, t, st);
+  }
+  SimtGemmArgs g = {};
+  g.a = dy; g.b = w; g.M = M; g.N = K; g.K = N;
+  g.a_sm = N; g.a_sk = 1; g.b_sk = K; g.b_sn = 1; g.e = e;
+  return simt_gemm_launch(g, dy_f32 ? VITB_F32 : dt, dt, dt, 1, st);
+}
+
+// split plan for wgrad on the tensor-core path
+static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* kb_per) {
+  const int tiles = (N / BM) * (K / kBN);
+  const int total = ceil_div(M, BK);
+  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > total) s = total;
+  const int per = ceil_div(total, s);
+  *splits = ceil_div(total, per);
+  *kb_total = total;
+  *kb_per = per;
+}
+
+static bool wgrad_tc_ok(int N, int K, int flags, int dt) {
+  return dt == VITB_BF16 && !(flags & VITB_GEMM_DY_F32) && N % BM == 0 && K % kBN == 0;
+}
+
+static int wgrad_simt_splits(int M, int N, int K) { return simt_pick_splits(ceil_div(N, 64) * ceil_div(K, 64), M); }
+
+size_t vitb_gemm_wgrad_ws_bytes(int M, int N, int K, int dt) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int splits;
+  if (wgrad_tc_ok(N, K, 0, dt)) {
+    int a, b;
+    wgrad_tc_plan(M, N, K, &splits, &a, &b);
+  } else {
+    splits = wgrad_simt_splits(M, N, K);
+  }
+  const size_t part = align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
+  return part + align_up(vitb_colsum_ws_bytes(M, N), 256) + 256;
+}
+
+int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias, void* ws, size_t ws_bytes, int M, int N, int K,
+                          int flags, int dt, void* stream) {
+  VITB_REQUIRE(dy && x && dw, "gemm_wgrad: null pointer");
+  VITB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_wgrad: bad shape M=%d N=%d K=%d", M, N, K);
+  if (check_dt(dt)) return -1;
+  VITB_REQUIRE(ws_bytes >= vitb_gemm_wgrad_ws_bytes(M, N, K, dt) && (ws != nullptr), "gemm_wgrad: workspace too small (%zu < %zu)", ws_bytes,
+               vitb_gemm_wgrad_ws_bytes(M, N, K, dt));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dy_dt = (flags & VITB_GEMM_DY_F32) ? VITB_F32 : dt;
+  int splits;
+  float* part = (float*)ws;
+  if (wgrad_tc_ok(N, K, flags, dt)) {
+    int kb_total, kb_per;
+    wgrad_tc_plan(M, N, K, &splits, &kb_total, &kb_per);
+    // GEMM view: C[N, K] = dYᵀ (A MN-major: [M rows][N contiguous]) x X (B MN-major: [M rows][K contiguous]), reduction M
+    CUtensorMap ma, mb;
+    if (make_map(&ma, dy, N, M, N, 64)) return -1;
+    if (make_map(&mb, x, K, M, K, 64)) return -1;
+    TcArgs t = {};
+    t.M = N; t.N = K; t.num_m_blocks = N / BM; t.num_n_blocks = K / kBN; t.splits = splits;
+    t.kblocks_total = kb_total; t.kblocks_per_split = kb_per;
+    t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = splits > 1 ? part : dw;
+    int rc = launch_tc<kBN, true, true, kStages>(ma, mb, t, st);
+    if (rc) return rc;
+  } else {
+    splits = wgrad_simt_splits(M, N, K);
+    SimtGemmArgs g = {};
+    g.a = dy; g.b = x; g.M = N; g.N = K; g.K = M;
+    g.a_sm = 1; g.a_sk = N; g.b_sk = K; g.b_sn = 1;
+    g.e.mode = EPI_RAW_F32; g.e.ldc = K; g.e.out = splits > 1 ? part : dw;
+    int rc = simt_gemm_launch(g, dy_dt, dt, VITB_F32, splits, st);
+    if (rc) return rc;
+  }
+  if (splits > 1) {
+    const int64_t n = (int64_t)N * K;
+    partials_finalize_kernel<0><<<dim3((unsigned)ceil_div64(n, 256), 1), 256, 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+    VITB_LAUNCH_OK();
+  }
+  if (dbias != nullptr) {
+    if (N % 128 == 0) {
+      char* cws = (char*)ws + align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
+      return vitb_colsum(dy, dbias, cws, vitb_colsum_ws_bytes(M, N), M, N, dy_dt, stream);
+    }
+    return colsum_small_launch(dy, dbias, M, N, N, dy_dt, st);
+  }
+  return 0;
+}
+
+}  // extern "C"

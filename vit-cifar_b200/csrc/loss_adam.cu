@@ -1,0 +1,133 @@
+// loss_adam.cu — fused label-smoothing cross-entropy (fwd+bwd in one pass) and flat-buffer Adam.
+#include "common.cuh"
+
+namespace vitb {
+
+// ---------------------------------------------------------------------------------------------
+// LS-CE: criterions.py:13-19.  One CTA; each warp walks rows w, w+32, ...; fixed-order reduction.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+    ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss,
+                 float* __restrict__ dlogits, int B, int C, float smoothing, float grad_scale) {
+  __shared__ float part[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float off = smoothing / (float)(C - 1);
+  const float conf = 1.0f - smoothing;
+  const float gs = grad_scale / (float)B;
+  float acc = 0.f;
+  for (int r = warp; r < B; r += nwarps) {
+    const float* z = logits + (size_t)r * C;
+    const int y = (int)labels[r];
+    float mx = -INFINITY, sz = 0.f;
+    for (int j = lane; j < C; j += 32) {
+      const float v = z[j];
+      mx = fmaxf(mx, v);
+      sz += v;
+    }
+    mx = warp_max(mx);
+    sz = warp_sum(sz);
+    float se = 0.f;
+    for (int j = lane; j < C; j += 32) se += expf(z[j] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    const float zy = z[y];
+    // sum_j -q_j (z_j - lse)
+    const float li = -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
+    acc += li;
+    if (dlogits != nullptr) {
+      float* d = dlogits + (size_t)r * C;
+      for (int j = lane; j < C; j += 32) {
+        const float p = expf(z[j] - lse);
+        d[j] = (p - (j == y ? conf : off)) * gs;
+      }
+    }
+  }
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += part[w];
+    *loss = s / (float)B;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (coupled L2), torch.optim.Adam single-tensor arithmetic, over one flat buffer
+// ---------------------------------------------------------------------------------------------
+struct AdamHyper {
+  float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale, pad;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
+  g = g * h.grad_scale + h.wd * p;
+  m = m + (g - m) * (1.0f - h.beta1);
+  v = v * h.beta2 + (1.0f - h.beta2) * g * g;
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+  p = p - h.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256)
+    adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                bf16* __restrict__ shadow, int64_t n, AdamHyper hv, const float* __restrict__ hyper_dev) {
+  AdamHyper h = hv;
+  if (hyper_dev != nullptr) {
+    h.step_size = hyper_dev[0]; h.bc2_sqrt = hyper_dev[1]; h.beta1 = hyper_dev[2]; h.beta2 = hyper_dev[3];
+    h.eps = hyper_dev[4]; h.wd = hyper_dev[5]; h.grad_scale = hyper_dev[6];
+  }
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), mm = ld4(m + i * 4), vv = ld4(v + i * 4);
+    adam_one(pp.x, gg.x, mm.x, vv.x, h);
+    adam_one(pp.y, gg.y, mm.y, vv.y, h);
+    adam_one(pp.z, gg.z, mm.z, vv.z, h);
+    adam_one(pp.w, gg.w, mm.w, vv.w, h);
+    st4(p + i * 4, pp);
+    st4(m + i * 4, mm);
+    st4(v + i * 4, vv);
+    if (shadow != nullptr) st4(shadow + i * 4, pp);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp, g[i], mm, vv, h);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pp);
+  }
+}
+
+}  // namespace vitb
+
+using namespace vitb;
+
+extern "C" {
+
+int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, float* dlogits, int B, int C,
+                       float smoothing, float grad_scale, void* stream) {
+  VITB_REQUIRE(logits && labels && loss, "ls_ce: null pointer");
+  VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
+  ls_ce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, B, C, smoothing, grad_scale);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow, int64_t n,
+                    const float* hyper_host, const float* hyper_dev, void* stream) {
+  VITB_REQUIRE(p && g && m && v, "adam: null pointer");
+  VITB_REQUIRE(hyper_host || hyper_dev, "adam: need hyper_host or hyper_dev");
+  VITB_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "adam: buffers must be 16-byte aligned");
+  VITB_REQUIRE(w_shadow == nullptr || (uintptr_t)w_shadow % 8 == 0, "adam: shadow must be 8-byte aligned");
+  if (n == 0) return 0;
+  AdamHyper h = {};
+  if (hyper_host) {
+    h.step_size = hyper_host[0]; h.bc2_sqrt = hyper_host[1]; h.beta1 = hyper_host[2]; h.beta2 = hyper_host[3];
+    h.eps = hyper_host[4]; h.wd = hyper_host[5]; h.grad_scale = hyper_host[6];
+  }
+  int blocks = (int)ceil_div64(n / 4 + 1, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)w_shadow, n, h, hyper_dev);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"
