@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — train images/s (forward + LS-CE + backward + Adam) of the ViT-CIFAR hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]/[2]): ViT 7 layers / hidden 384 / 12 heads / MLP 384, `patch=8` patches per side
+(T = 65 tokens, patch vector K = 48), 10 classes, label smoothing 0.1, Adam(lr 1e-3, wd 5e-5), bf16 storage with
+fp32 accumulation, per-GPU batch 1024 (weak scaling: global batch = 1024 * N; 8192 at N = 8), synthetic
+32x32x3 data.  One "step" = one optimisation step over one batch.
+
+Prints ONE JSON line (rank 0).  `value` = steady-state img/s with the batch resident in HBM; `e2e` = the same
+through the public API from pinned HOST buffers (H2D of every batch and D2H of every loss inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, "port": /root/reference is not on the GPU
+box) on the host cores over a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = dict(num_classes=10, img_size=32, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+PER_GPU_BATCH = 1024
+ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
+SMOOTHING = 0.1
+METRIC = "train images/s (fwd+bwd+Adam)"
+UNIT = "img/s"
+
+
+def train_flops_per_image(T=65, K=48, H=384, M=384, L=7, C=10):
+    fwd = 2 * (T - 1) * K * H + L * (2 * T * H * (4 * H + 2 * M) + 4 * T * T * H) + 2 * H * C
+    return 3 * fwd
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (same arithmetic as the reference, torch fp32 on host cores)
+# ---------------------------------------------------------------------------------------------
+def cpu_port_images_per_s(batch: int, steps: int, warmup: int):
+    import torch
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = oracle.ViTConfig(**MODEL)
+    model = oracle.OracleViT(cfg, seed=0)
+    opt = torch.optim.Adam(model.parameters(), **ADAM)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    y = torch.randint(0, cfg.num_classes, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = oracle.ls_ce_loss(model(x), y, cfg.num_classes, SMOOTHING)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, cores, 1e3 * total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch = 128  # bounded sample of the 1024-image step: the CPU path is ~1e3x slower
+    v, cores, ms = cpu_port_images_per_s(batch, max(1, args.steps), max(1, min(args.warmup, 2)))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": f"{batch}-image steps on CPU"},
+        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {batch} (oracle port of the reference, torch fp32, {cores} threads)"},
+        "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_name(n):
+    return (f"ViT-CIFAR 7L/384h/12heads/MLP384 patch=8 (T=65,K=48) C=10, per-GPU batch {PER_GPU_BATCH} "
+            f"(global {PER_GPU_BATCH * n}), LS 0.1, Adam, bf16")
+
+
+# ---------------------------------------------------------------------------------------------
+# per-kernel probe: CUDA-event time of every C-ABI call of an eager step, grouped by (op, shape)
+# ---------------------------------------------------------------------------------------------
+def probe_kernels(eng, steps=3):
+    import torch
+    from vit_cifar_b200 import ops
+    names = ["patch_embed_fwd", "patch_embed_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_fwd", "gemm_dgrad", "gemm_wgrad",
+             "attn_fwd", "attn_bwd", "gelu_bwd_colsum", "colsum", "pool_fwd", "pool_bwd", "ls_ce", "adam"]
+    rec = []
+    orig = {}
+
+    def wrap(name, fn):
+        def inner(*a, **k):
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            shape = tuple(x for x in a if isinstance(x, int))
+            flags = tuple(sorted((kk, vv) for kk, vv in k.items() if isinstance(vv, bool) and vv))
+            extra = ("res",) if name == "gemm_fwd" and a[3] is not None else ()
+            extra += ("z",) if name == "gemm_dgrad" and a[2] is not None else ()
+            rec.append((name, shape, flags + extra, s, e))
+            return r
+        return inner
+
+    for n in names:
+        orig[n] = getattr(ops, n)
+        setattr(ops, n, wrap(n, orig[n]))
+    try:
+        saved_graph, eng.use_graph = eng.use_graph, False
+        for _ in range(steps):
+            eng.step()
+        torch.cuda.synchronize()
+        eng.use_graph = saved_graph
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    agg = {}
+    for name, shape, flags, s, e in rec:
+        key = (name, shape, flags)
+        d = agg.setdefault(key, [0.0, 0])
+        d[0] += s.elapsed_time(e)
+        d[1] += 1
+    table = []
+    for (name, shape, flags), (ms, cnt) in agg.items():
+        table.append({"op": name, "shape": list(shape), "flags": [str(f) for f in flags], "calls_per_step": cnt // steps,
+                      "ms_per_call": ms / cnt, "ms_per_step": ms / steps})
+    table.sort(key=lambda r: -r["ms_per_step"])
+    return table
+
+
+def kernel_roofline(row, pk, B, T, H):
+    """Algorithmic FLOPs / bytes of one call against the measured peaks."""
+    op, sh = row["op"], row["shape"]
+    sec = row["ms_per_call"] * 1e-3
+    E = 2  # bytes per bf16 activation element
+    if op in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"):
+        M, N, K = sh[:3]
+        fl = 2.0 * M * N * K
+        return {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["tf_sust"],
+                "traffic": None, "kernel": f"{op} M={M} N={N} K={K} {' '.join(row['flags'])}".strip(), "peak_kind": f"{pk['src']} sustained bf16"}
+    rows = B * T
+    by = {
+        "layernorm_fwd": 2 * rows * H * E, "layernorm_bwd": 4 * rows * H * E, "attn_fwd": 4 * rows * H * E, "attn_bwd": 8 * rows * H * E,
+        "gelu_bwd_colsum": 3 * rows * H * E, "colsum": (sh[0] * sh[1] * E) if len(sh) >= 2 else 0,
+        "patch_embed_fwd": B * 12288 + rows * H * E, "patch_embed_bwd": B * 12288 + rows * H * E,
+    }.get(op)
+    if op == "adam":
+        by = 30 * eng_numel  # 28 B/param fp32 state + 2 B bf16 shadow
+    if not by:
+        return None
+    return {"bound": "hbm", "achieved": by / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": by / sec / 1e9 / pk["hbm"], "traffic": None,
+            "kernel": f"{op} {sh}", "peak_kind": f"{pk['src']} copy bandwidth"}
+
+
+eng_numel = 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    global eng_numel
+    import torch
+    import torch.distributed as dist
+    import vit_cifar_b200 as vb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE=1 here)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    vb.set_precision("bf16")
+    torch.manual_seed(2045)  # main.py:150
+    model = vb.ViT(3, MODEL["num_classes"], img_size=32, patch=MODEL["patch"], dropout=0.0, num_layers=MODEL["num_layers"],
+                   hidden=MODEL["hidden"], mlp_hidden=MODEL["mlp_hidden"], head=MODEL["head"]).to(dev)
+    B = args.batch
+    eng = vb.TrainEngine(model, B, smoothing=SMOOTHING, process_group=pg, use_graph=not args.no_graph, **ADAM)
+    eng_numel = eng.n
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 4  # rotating pinned host batches (different data every step)
+    host_x = [torch.randn(B, 3, 32, 32, generator=g).pin_memory() for _ in range(nbuf)]
+    host_y = [torch.randint(0, MODEL["num_classes"], (B,), generator=g).pin_memory() for _ in range(nbuf)]
+    loss_host = torch.zeros(args.steps + args.warmup + 8, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident arm: the batch is already in HBM -------------------------------------
+    eng.load_batch(host_x[0], host_y[0])
+    W = max(3, args.warmup)
+    sampler = ClockSampler(local)
+    for i in range(2):  # eager warm-up + graph capture happen here, outside any timed region
+        eng.step()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(lambda i: eng.step(), args.steps, W)
+    # ---- end-to-end arm: pinned host -> device every step, loss read back every step ----------
+    def e2e_step(i):
+        loss = eng.step(host_x[i % nbuf], host_y[i % nbuf])
+        loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)
+    ms_e2e = timed(e2e_step, args.steps, W)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_host[(W + args.steps - 1) % loss_host.numel()])
+
+    imgs = B * world * args.steps
+    value = imgs / (ms_dev * 1e-3)
+    e2e = imgs / (ms_e2e * 1e-3)
+    pk = peaks()
+    fl = train_flops_per_image()
+
+    # ---- per-kernel probe + roofline of the dominant kernel (rank 0, after the timed regions) ----
+    table = probe_kernels(eng, steps=3)
+    roof = None
+    for row in table:
+        roof = kernel_roofline(row, pk, B, model.num_tokens, model.hidden)
+        if roof:
+            roof["share_of_step"] = row["ms_per_step"] / sum(r["ms_per_step"] for r in table)
+            break
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, ms = cpu_port_images_per_s(128, 3, 1)
+        cpu = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 steps of batch 128 of the same model (oracle port of the reference, torch fp32, {cores} threads)"}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(world), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
+                       "l2": "working set per step (>4 GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}"},
+            "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "h2d_bytes_per_step": B * (3 * 32 * 32 * 4 + 8) + 32, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(eng.launches_per_step * args.steps),
+            "launches_per_step": int(eng.launches_per_step),
+            "clocks": clocks,
+            "tensor_pipe_frac": {"of_burst": value * fl / world / 1e12 / pk["tf_burst"], "of_sustained": value * fl / world / 1e12 / pk["tf_sust"],
+                                 "train_flop_per_img": fl, "peaks": pk["src"]},
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "final_loss": final_loss,
+            "activation_bytes": eng.activation_bytes(),
+        }
+        print(json.dumps(out), flush=True)
+        if args.kernel_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
+            for row in table:
+                r = kernel_roofline(row, pk, B, model.num_tokens, model.hidden)
+                row["roofline"] = r
+            json.dump({"ms_per_step_graph": ms_dev / args.steps, "img_per_s": value, "kernels": table}, open(args.kernel_table, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default: the benchmark's 1024)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

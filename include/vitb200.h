@@ -38,6 +38,8 @@ extern "C" {
 int vitb_version(void);
 /* Text of the last error raised on the calling thread ("" if none). */
 const char* vitb_last_error(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph) in this process so far. */
+unsigned long long vitb_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (the kernels are sm_100a only). */
 int vitb_device_supported(void);
 

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds, loads, and exports exactly the symbols include/vitb200.h declares
+(no compute calls here: there is no GPU in the authoring container)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vitb200.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    import vit_cifar_b200 as vb
+    return vb
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vitb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_and_library_exports_same_symbols(built):
+    from vit_cifar_b200 import _lib
+    declared = header_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(_lib.SIGNATURES) == declared  # the ctypes table mirrors the header
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r"\bT (vitb_[a-z0-9_]+)\b", nm)))
+    assert exported == declared
+    lib = built.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.vitb_version() == _lib.ABI_VERSION
+    assert lib.vitb_last_error() == b""
+
+
+def test_workspace_size_queries_are_pure_host_functions(built):
+    lib = built.load_library()
+    assert lib.vitb_layernorm_bwd_ws_bytes(8320, 384) == 3 * 296 * 384 * 4
+    assert lib.vitb_colsum_ws_bytes(8320, 384) > 0
+    assert lib.vitb_colsum_ws_bytes(10, 100) == 0  # cols must be a multiple of 128 for the vectorised kernel
+    assert lib.vitb_gemm_wgrad_ws_bytes(66560, 384, 384, 1) >= 16 * 384 * 384 * 4
+    assert lib.vitb_patch_embed_bwd_ws_bytes(128, 32, 8, 384, 1) > 0
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(built):
+    """SASS evidence that the GEMM is a Blackwell-native kernel (UTCHMMA = tcgen05.mma, UTMALDG = TMA, LDTM = tcgen05.ld)."""
+    from vit_cifar_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "HMMA", "LDSM"):
+        assert mnemonic in r.stdout, mnemonic
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    vb = built
+    m = vb.ViT(3, 10, img_size=32, patch=8, num_layers=1, hidden=128, mlp_hidden=128, head=4)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(vb.VitbError):
+        m(torch.zeros(2, 3, 32, 32))
+    with pytest.raises(vb.VitbError):
+        vb.LabelSmoothingCrossEntropyLoss(10, 0.1)(torch.zeros(2, 10), torch.zeros(2, dtype=torch.long))

@@ -1,0 +1,294 @@
+"""GPU: every libvitb200 kernel, called through the C ABI (ctypes), against an fp32 CPU restatement.
+
+Tolerances: fp32 check mode 1e-4 relative (north_star), bf16 mode 2e-2 relative on outputs computed from the
+SAME bf16-rounded inputs (so only accumulation order / output rounding differ; most land near 4e-3).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def tol(dtype):
+    return 1e-4 if dtype == torch.float32 else 2e-2
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rnd(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(shape, generator=g) * scale).to(dtype)
+    return t  # CPU tensor already rounded to the storage dtype
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import vit_cifar_b200  # noqa: F401
+    from vit_cifar_b200 import ops as o
+    o.require_device()
+    return o
+
+
+def cu(t):
+    return t.cuda().contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,H", [(260, 128), (1040, 384), (77, 768)])
+def test_layernorm_fwd_bwd(ops, dtype, rows, H):
+    x = rnd((rows, H), dtype, 1, 2.0)
+    gam = rnd((H,), torch.float32, 2) * 0.2 + 1
+    bet = rnd((H,), torch.float32, 3) * 0.2
+    dy = rnd((rows, H), dtype, 4)
+    dres = rnd((rows, H), dtype, 5)
+    xr = x.float().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (H,), gr, br, 1e-5)
+    yr.backward(dy.float())
+    dx_ref = xr.grad + dres.float()
+
+    y = torch.empty_like(cu(x)); mean = torch.empty(rows, device="cuda"); rstd = torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(cu(x), H, cu(gam), cu(bet), y, mean, rstd, rows, H)
+    assert rel(y, yr.detach()) < tol(dtype)
+    dx = torch.empty_like(y); dg = torch.empty(H, device="cuda"); db = torch.empty(H, device="cuda"); dc = torch.empty(H, device="cuda")
+    ops.layernorm_bwd(cu(dy), cu(x), H, cu(gam), mean, rstd, cu(dres), dx, H, dg, db, dc, rows, H)
+    assert rel(dx, dx_ref) < tol(dtype)
+    assert rel(dg, gr.grad) < tol(dtype)
+    assert rel(db, br.grad) < tol(dtype)
+    assert rel(dc, dx_ref.sum(0)) < (1e-4 if dtype == torch.float32 else 5e-3)  # bias gradient of the producing Linear
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layernorm_strided_rows(ops, dtype):
+    B, T, H = 6, 17, 128
+    x = rnd((B, T, H), dtype, 11)
+    gam = torch.ones(H); bet = torch.zeros(H)
+    y = torch.empty((B, H), dtype=dtype, device="cuda"); mean = torch.empty(B, device="cuda"); rstd = torch.empty(B, device="cuda")
+    ops.layernorm_fwd(cu(x), T * H, cu(gam), cu(bet), y, mean, rstd, B, H)
+    assert rel(y, F.layer_norm(x[:, 0].float(), (H,))) < tol(dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(260, 128, 128), (260, 384, 128), (1040, 1152, 384), (520, 384, 384), (130, 256, 128), (128, 128, 64), (4, 10, 128)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "gelu_res_pre"])
+def test_gemm_fwd(ops, dtype, M, N, K, variant):
+    a = rnd((M, K), dtype, 1); w = rnd((N, K), dtype, 2, 1 / math.sqrt(K)); bias = rnd((N,), torch.float32, 3)
+    res = rnd((M, N), dtype, 4)
+    z_ref = a.float() @ w.float().t() + bias
+    out = torch.empty((M, N), dtype=dtype, device="cuda")
+    if variant == "plain":
+        ops.gemm_fwd(cu(a), cu(w), cu(bias), None, out, None, M, N, K)
+        assert rel(out, z_ref) < tol(dtype)
+    else:
+        pre = torch.empty_like(out)
+        ops.gemm_fwd(cu(a), cu(w), cu(bias), cu(res), out, pre, M, N, K, gelu=True)
+        assert rel(pre, z_ref) < tol(dtype)
+        assert rel(out, F.gelu(z_ref) + res.float()) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_fwd_out_f32_head(ops, dtype):
+    M, N, K = 7, 100, 384
+    a = rnd((M, K), dtype, 1); w = rnd((N, K), dtype, 2, 0.05); bias = rnd((N,), torch.float32, 3)
+    out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    ops.gemm_fwd(cu(a), cu(w), cu(bias), None, out, None, M, N, K, out_f32=True)
+    assert rel(out, a.float() @ w.float().t() + bias) < 1e-4  # fp32 accumulate and store in both modes
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES[:-1])
+@pytest.mark.parametrize("with_z", [False, True])
+def test_gemm_dgrad(ops, dtype, M, N, K, with_z):
+    dy = rnd((M, N), dtype, 1); w = rnd((N, K), dtype, 2, 1 / math.sqrt(N)); z = rnd((M, K), dtype, 3)
+    ref = dy.float() @ w.float()
+    if with_z:
+        zz = z.float().requires_grad_(True)
+        F.gelu(zz).sum().backward()
+        ref = ref * zz.grad
+    dx = torch.empty((M, K), dtype=dtype, device="cuda")
+    ops.gemm_dgrad(cu(dy), cu(w), cu(z) if with_z else None, dx, M, N, K)
+    assert rel(dx, ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES[:-1] + [(8320, 384, 384)])
+def test_gemm_wgrad_dbias(ops, dtype, M, N, K):
+    dy = rnd((M, N), dtype, 1); x = rnd((M, K), dtype, 2)
+    dw = torch.empty((N, K), dtype=torch.float32, device="cuda"); db = torch.empty((N,), dtype=torch.float32, device="cuda")
+    ops.gemm_wgrad(cu(dy), cu(x), dw, db, M, N, K)
+    assert rel(dw, dy.float().t() @ x.float()) < 1e-4   # fp32 accumulation of exact bf16 products
+    assert rel(db, dy.float().sum(0)) < 1e-4
+    dw2 = torch.empty_like(dw)
+    ops.gemm_wgrad(cu(dy), cu(x), dw2, None, M, N, K)
+    assert torch.equal(dw, dw2)  # deterministic split-K
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_head_backward_f32_dy(ops, dtype):
+    B, C, H = 5, 10, 128
+    dl = rnd((B, C), torch.float32, 1); hn = rnd((B, H), dtype, 2); w = rnd((C, H), dtype, 3)
+    dw = torch.empty((C, H), device="cuda"); db = torch.empty((C,), device="cuda")
+    ops.gemm_wgrad(cu(dl), cu(hn), dw, db, B, C, H, dy_f32=True)
+    assert rel(dw, dl.t() @ hn.float()) < 1e-4 and rel(db, dl.sum(0)) < 1e-5
+    dx = torch.empty((B, H), dtype=dtype, device="cuda")
+    ops.gemm_dgrad(cu(dl), cu(w), None, dx, B, C, H, dy_f32=True)
+    assert rel(dx, dl @ w.float()) < tol(dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+def attn_ref(qkv, B, T, heads, d, scale, do=None):
+    H = heads * d
+    qkv = qkv.float().view(B, T, 3, heads, d).requires_grad_(do is not None)
+    q, k, v = qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2), qkv[:, :, 2].transpose(1, 2)
+    s = torch.einsum("bhif,bhjf->bhij", q, k) * scale
+    p = s.softmax(-1)
+    o = torch.einsum("bhij,bhjf->bihf", p, v).reshape(B, T, H)
+    lse = torch.logsumexp(s, -1)
+    if do is None:
+        return o, lse, p
+    o.backward(do.float())
+    return o.detach(), lse.detach(), p.detach(), qkv.grad.reshape(B, T, 3 * H)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,T,heads,d", [(3, 65, 12, 32), (2, 17, 12, 32), (2, 16, 4, 32), (2, 64, 2, 64), (1, 65, 12, 64), (1, 100, 2, 32)])
+def test_attention_fwd_bwd(ops, dtype, B, T, heads, d):
+    H = heads * d
+    scale = 1.0 / math.sqrt(H)
+    qkv = rnd((B, T, 3 * H), dtype, 1, 2.0)
+    do = rnd((B, T, H), dtype, 2)
+    o_ref, lse_ref, p_ref, dqkv_ref = attn_ref(qkv, B, T, heads, d, scale, do)
+    o = torch.empty((B, T, H), dtype=dtype, device="cuda"); lse = torch.empty((B, heads, T), device="cuda")
+    am = torch.empty((B, heads, T, T), device="cuda")
+    ops.attn_fwd(cu(qkv), o, lse, am, B, T, heads, d, scale)
+    assert rel(o, o_ref) < tol(dtype)
+    assert rel(lse, lse_ref) < 1e-4
+    assert rel(am, p_ref) < (1e-4 if dtype == torch.float32 else 5e-3)
+    o2 = torch.empty_like(o); lse2 = torch.empty_like(lse)
+    ops.attn_fwd(cu(qkv), o2, lse2, None, B, T, heads, d, scale)
+    assert torch.equal(o, o2)
+    dqkv = torch.empty((B, T, 3 * H), dtype=dtype, device="cuda")
+    ops.attn_bwd(cu(qkv), cu(do), lse, dqkv, B, T, heads, d, scale)
+    assert rel(dqkv, dqkv_ref) < tol(dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,cols", [(260, 128), (1040, 384), (999, 1152), (33, 3072)])
+def test_gelu_bwd_and_colsum(ops, dtype, rows, cols):
+    dy = rnd((rows, cols), dtype, 1); z = rnd((rows, cols), dtype, 2, 1.5)
+    zz = z.float().requires_grad_(True)
+    F.gelu(zz).backward(dy.float())
+    dz = torch.empty((rows, cols), dtype=dtype, device="cuda"); cs = torch.empty(cols, device="cuda")
+    ops.gelu_bwd_colsum(cu(dy), cu(z), dz, cs, rows, cols)
+    assert rel(dz, zz.grad) < tol(dtype)
+    assert rel(cs, zz.grad.sum(0)) < (1e-4 if dtype == torch.float32 else 5e-3)
+    cs2 = torch.empty(cols, device="cuda")
+    ops.colsum(cu(dy), cs2, rows, cols)
+    assert rel(cs2, dy.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("P,has_cls", [(8, True), (4, True), (4, False)])
+def test_patch_embed_fwd_bwd(ops, dtype, P, has_cls):
+    import oracle
+    B, S, H = 5, 32, 128
+    cfg = oracle.ViTConfig(patch=P, hidden=H, is_cls_token=has_cls)
+    K, T = cfg.patch_len, cfg.num_tokens
+    img = rnd((B, 3, S, S), torch.float32, 1)
+    w = (rnd((H, K), torch.float32, 2) / math.sqrt(K)).requires_grad_(True)
+    b = rnd((H,), torch.float32, 3).requires_grad_(True)
+    cls = rnd((1, 1, H), torch.float32, 4).requires_grad_(True)
+    pos = rnd((1, T, H), torch.float32, 5).requires_grad_(True)
+    out_ref = F.linear(oracle.to_words(img, cfg), w, b)
+    if has_cls:
+        out_ref = torch.cat([cls.repeat(B, 1, 1), out_ref], 1)
+    out_ref = out_ref + pos
+    dout = rnd((B, T, H), dtype, 6)
+    out_ref.backward(dout.float())
+    out = torch.empty((B * T, H), dtype=dtype, device="cuda")
+    ops.patch_embed_fwd(cu(img), cu(w.detach()), cu(b.detach()), cu(cls.detach().view(-1)) if has_cls else None, cu(pos.detach().view(T, H)), out, P, has_cls)
+    assert rel(out.view(B, T, H), out_ref.detach()) < (1e-5 if dtype == torch.float32 else 5e-3)
+    dw = torch.empty((H, K), device="cuda"); db = torch.empty(H, device="cuda"); dpos = torch.empty((T, H), device="cuda")
+    dcls = torch.empty(H, device="cuda") if has_cls else None
+    ops.patch_embed_bwd(cu(img), cu(dout).view(B * T, H), dw, db, dcls, dpos, P, has_cls)
+    assert rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4 and rel(dpos, pos.grad.view(T, H)) < 1e-4
+    if has_cls:
+        assert rel(dcls, cls.grad.view(-1)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pool(ops, dtype, mode):
+    B, T, H = 4, 17, 128
+    x = rnd((B, T, H), dtype, 1); dy = rnd((B, H), dtype, 2)
+    y = torch.empty((B, H), dtype=dtype, device="cuda")
+    ops.pool_fwd(cu(x), y, B, T, H, mode)
+    ref = x.float()[:, 0] if mode == 0 else x.float().mean(1)
+    assert rel(y, ref) < tol(dtype)
+    dx = torch.full((B, T, H), 7.0, dtype=dtype, device="cuda")
+    ops.pool_bwd(cu(dy), dx, B, T, H, mode)
+    ref = torch.zeros(B, T, H)
+    if mode == 0:
+        ref[:, 0] = dy.float()
+    else:
+        ref[:] = dy.float()[:, None] / T
+    assert rel(dx, ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("B,C", [(4, 10), (128, 100), (1000, 10), (3, 1000)])
+def test_ls_ce(ops, B, C):
+    import oracle
+    z = rnd((B, C), torch.float32, 1, 3.0); y = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(2))
+    loss = torch.empty((), device="cuda"); dl = torch.empty((B, C), device="cuda")
+    ops.ls_ce(cu(z), cu(y), loss, dl, 0.1, 1.0)
+    assert abs(loss.item() - oracle.ls_ce_loss(z, y, C, 0.1).item()) < 1e-5 * max(1.0, abs(loss.item()))
+    assert rel(dl, oracle.ls_ce_dlogits(z, y, C, 0.1)) < 1e-5
+
+
+def test_adam_matches_oracle(ops):
+    import oracle
+    from vit_cifar_b200 import adam_hyper
+    n = 10007
+    p = rnd((n,), torch.float32, 1)
+    ref = {"p": p.clone()}
+    m = {"p": torch.zeros(n)}; v = {"p": torch.zeros(n)}
+    pd, md, vd = cu(p), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    sh = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    hd = torch.zeros(8, device="cuda")
+    for t in range(1, 5):
+        g = rnd((n,), torch.float32, 10 + t)
+        oracle.adam_step(ref, {"p": g}, m, v, t)
+        h = adam_hyper(t, 1e-3, 0.9, 0.999, 1e-8, 5e-5)
+        if t % 2:
+            ops.adam(pd, cu(g), md, vd, sh, hyper_host=h)
+        else:  # device-resident hyper-parameters (the CUDA-graph path)
+            hd.copy_(torch.tensor(h + [0.0]))
+            ops.adam(pd, cu(g), md, vd, sh, hyper_dev=hd)
+    assert rel(pd, ref["p"]) < 1e-6
+    assert rel(md, m["p"]) < 1e-6 and rel(vd, v["p"]) < 1e-6
+    assert torch.equal(sh.cpu(), pd.cpu().to(torch.bfloat16))
+
+
+def test_bad_arguments_raise(ops):
+    from vit_cifar_b200 import VitbError
+    x = torch.zeros((4, 100), device="cuda")
+    with pytest.raises(VitbError):
+        ops.layernorm_fwd(x, 100, x, x, x, x, x, 4, 100)  # H not a multiple of 128
+    with pytest.raises(VitbError):
+        ops.attn_fwd(x, x, x, None, 1, 200, 2, 32, 1.0)  # T > 128
+    with pytest.raises(VitbError):
+        ops.cast_f32_to_bf16(torch.zeros(4), torch.zeros(4, dtype=torch.bfloat16))  # CPU tensors: no fallback

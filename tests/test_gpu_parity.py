@@ -1,0 +1,242 @@
+"""GPU: the drop-in modules and the training engine against the CPU oracle and the committed golden fixtures.
+
+north_star tolerances: bf16 logits and gradients within 2e-2 relative; fp32 check mode within 1e-4 relative
+with bit-exact argmax predictions.
+"""
+import os
+
+import pytest
+import torch
+
+import oracle
+from oracle import ViTConfig
+
+pytestmark = pytest.mark.gpu
+
+ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture()
+def vb():
+    import vit_cifar_b200 as v
+    v.ops.require_device() if hasattr(v, "ops") else None
+    yield v
+    v.set_precision("bf16")
+
+
+def build(vb, cfg: ViTConfig, precision: str):
+    vb.set_precision(precision)
+    m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, dropout=0.0, num_layers=cfg.num_layers,
+               hidden=cfg.hidden, encoder_mlp=cfg.encoder_mlp, mlp_hidden=cfg.mlp_hidden, head=cfg.head,
+               is_cls_token=cfg.is_cls_token)
+    assert list(m.state_dict().keys()) == list(cfg.param_shapes().keys())  # reference state_dict names / order
+    m.load_state_dict(oracle.init_params(cfg, seed=0))
+    return m.cuda()
+
+
+CASES = {
+    "tiny65": (ViTConfig(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4), 4),
+    "tiny17c100": (ViTConfig(num_classes=100, patch=4, num_layers=1, hidden=128, mlp_hidden=256, head=2), 3),
+    "nocls_nomlp": (ViTConfig(num_classes=10, patch=4, num_layers=1, hidden=128, mlp_hidden=128, head=4,
+                              is_cls_token=False, encoder_mlp=False), 2),
+    "full65": (ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 4),
+    "full17c100": (ViTConfig(num_classes=100, patch=4, num_layers=7, hidden=384, mlp_hidden=384, head=12), 4),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_module_forward_backward_vs_oracle(vb, name, precision):
+    cfg, B = CASES[name]
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    model = build(vb, cfg, precision)
+    x, y = oracle.hash_inputs(cfg, B, seed=1)
+    logits_ref, loss_ref, grads_ref = oracle.train_step(oracle.init_params(cfg, 0), x, y, cfg, 0.1)
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    logits = model(x.cuda())
+    loss = crit(logits, y.cuda())
+    loss.backward()
+    assert logits.dtype == torch.float32 and logits.shape == logits_ref.shape
+    assert rel(logits, logits_ref) < tol, f"logits rel err {rel(logits, logits_ref)}"
+    assert abs(loss.item() - loss_ref.item()) < tol * abs(loss_ref.item())
+    if precision == "fp32":
+        assert torch.equal(logits.argmax(-1).cpu(), logits_ref.argmax(-1))  # bit-exact predictions
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        gr = grads_ref[k]
+        if gr is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        e = rel(p.grad, gr)
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < tol, f"worst grad {worst}"
+
+
+@pytest.mark.parametrize("name", ["tiny65", "tiny17c100", "nocls_nomlp"])
+def test_fp32_engine_matches_golden_after_3_adam_steps(vb, golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+    cfg, B = CASES[name]
+    model = build(vb, cfg, "fp32")
+    x, y = oracle.hash_inputs(cfg, B, seed=1)
+    eng = vb.TrainEngine(model, B, smoothing=g["smoothing"], use_graph=True, **ADAM)
+    losses = []
+    xd, yd = x.cuda(), y.cuda()
+    for _ in range(3):
+        losses.append(eng.step(xd, yd).item())
+        if len(losses) == 1:
+            assert rel(eng.logits, g["logits"]) < 1e-4
+            for k, gr in eng.grads().items():
+                assert rel(gr, g["grads"][k]) < 1e-4, k
+    assert losses == pytest.approx(g["losses"], rel=1e-4)
+    sd = model.state_dict()
+    for k, ref in g["params3"].items():
+        assert rel(sd[k], ref) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["full65", "full17c100"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_model_engine_vs_reference_golden(vb, golden_dir, name, precision):
+    """The 7-layer / 384-wide model of the README against numbers produced by the unmodified reference."""
+    g = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+    cfg, B = CASES[name]
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    model = build(vb, cfg, precision)
+    x, y = oracle.hash_inputs(cfg, B, seed=1)
+    eng = vb.TrainEngine(model, B, smoothing=g["smoothing"], use_graph=False, **ADAM)
+    loss = eng.step(x.cuda(), y.cuda()).item()
+    assert rel(eng.logits, g["logits"]) < tol
+    assert abs(loss - g["loss"]) < tol * abs(g["loss"])
+    if precision == "fp32":
+        assert torch.equal(eng.logits.argmax(-1).cpu(), g["logits"].argmax(-1))
+    for k, gr in eng.grads().items():
+        ref = g["grads"][k]
+        assert abs(gr.double().norm().item() - ref["norm"]) < 2 * tol * ref["norm"] + 1e-9, k
+        if precision == "fp32":
+            torch.testing.assert_close(gr.flatten()[:16].cpu(), ref["head"], rtol=2e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_graph_equals_eager_and_module_path(vb, precision):
+    cfg, B = CASES["tiny65"]
+    x, y = oracle.hash_inputs(cfg, B, seed=1)
+    xd, yd = x.cuda(), y.cuda()
+    res = []
+    for use_graph in (False, True):
+        model = build(vb, cfg, precision)
+        eng = vb.TrainEngine(model, B, smoothing=0.1, use_graph=use_graph, **ADAM)
+        ls = [eng.step(xd, yd).item() for _ in range(4)]
+        res.append((ls, {k: v.clone() for k, v in model.state_dict().items()}))
+    assert res[0][0] == res[1][0]  # same kernels, same order: bit-identical losses
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
+    # autograd module path + FusedAdam == engine
+    model = build(vb, cfg, precision)
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    opt = vb.FusedAdam(model, **ADAM)
+    ls = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss = crit(model(xd), yd)
+        loss.backward()
+        opt.step()
+        ls.append(loss.item())
+    assert ls == pytest.approx(res[0][0], rel=1e-6)
+    for k, v in model.state_dict().items():
+        assert rel(v, res[0][1][k]) < 1e-6, k
+
+
+def test_module_works_with_torch_adam_and_loss_decreases(vb):
+    """Drop-in use exactly as network.py does it: torch.optim.Adam over model.parameters()."""
+    cfg, B = CASES["tiny65"]
+    model = build(vb, cfg, "bf16")
+    x, y = oracle.hash_inputs(cfg, 16, seed=3)
+    xd, yd = x.cuda(), y.cuda()
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    opt = torch.optim.Adam(model.parameters(), **ADAM)
+    ls = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = crit(model(xd), yd)
+        loss.backward()
+        opt.step()
+        ls.append(loss.item())
+    assert ls[-1] < ls[0]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_attention_map_protocol(vb, golden_dir, precision):
+    """save_attn_map / get_attention_map (layers.py:50-65, run_model.py:45-47, attention/utils.py:62-68)."""
+    g = torch.load(os.path.join(golden_dir, "tiny65.pt"), weights_only=False)
+    cfg, B = CASES["tiny65"]
+    model = build(vb, cfg, precision).eval()
+    for m in model.modules():
+        if hasattr(m, "save_attn_map"):
+            m.save_attn_map = True
+    x, _ = oracle.hash_inputs(cfg, B, seed=1)
+    with torch.no_grad():
+        model(x.cuda())
+    maps = torch.stack([blk.get_attention_map() for blk in model.enc])
+    assert maps.shape == g["attn"].shape
+    assert rel(maps, g["attn"]) < (1e-4 if precision == "fp32" else 2e-2)
+    model.enc[0].save_attn_map = False
+    with pytest.raises(Exception):
+        model.enc[0].get_attention_map()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_standalone_blocks_vs_oracle(vb, precision):
+    """TransformerEncoder / MultiHeadSelfAttention used on their own: (B,T,F) -> (B,T,F)."""
+    vb.set_precision(precision)
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    torch.manual_seed(0)
+    B, T, Fd, heads = 3, 17, 128, 4
+    x = torch.randn(B, T, Fd)
+    enc = vb.TransformerEncoder(Fd, 256, head=heads)
+    p = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    enc = enc.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = enc(xg)
+    y.sum().backward()
+    xr = x.clone().requires_grad_(True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    yr = oracle.encoder_forward(leaf, "", xr, heads, True)
+    yr.sum().backward()
+    assert y.dtype == torch.float32 and rel(y, yr.detach()) < tol
+    assert rel(xg.grad, xr.grad) < tol
+    for k, prm in enc.named_parameters():
+        assert rel(prm.grad, leaf[k].grad) < tol, k
+    att = vb.MultiHeadSelfAttention(Fd, head=heads)
+    pa = {k: v.detach().clone() for k, v in att.state_dict().items()}
+    att = att.cuda()
+    ya = att(x.cuda())
+    assert rel(ya, oracle.mhsa_forward(pa, "", x, heads)) < tol
+
+
+def test_full_size_properties_b1024(vb):
+    """BASELINE config (7 layers, 384 wide, T=65) at the benchmark batch: size-independent properties.
+    (a) per-image independence: logits of a batch made of 256 copies of 4 images repeat with period 4 and equal
+        the B=4 logits bit for bit; (b) the mean-loss gradient of that batch equals the B=4 gradient;
+    (c) two runs are bit-identical (deterministic split-K, no float atomics)."""
+    cfg, _ = CASES["full65"]
+    x4, y4 = oracle.hash_inputs(cfg, 4, seed=1)
+    xb, yb = x4.repeat(256, 1, 1, 1).cuda(), y4.repeat(256).cuda()
+    model = build(vb, cfg, "bf16")
+    e4 = vb.TrainEngine(model, 4, use_graph=False, lr=0.0, weight_decay=0.0)
+    e4.step(x4.cuda(), y4.cuda())
+    l4, g4 = e4.logits.clone(), {k: v.clone() for k, v in e4.grads().items()}
+    eb = vb.TrainEngine(model, 1024, use_graph=False, lr=0.0, weight_decay=0.0)
+    loss1 = eb.step(xb, yb).item()
+    lb, gb = eb.logits.clone(), {k: v.clone() for k, v in eb.grads().items()}
+    assert torch.equal(lb[:4], l4) and torch.equal(lb.view(256, 4, -1)[17], l4)
+    for k in g4:
+        assert rel(gb[k], g4[k]) < 2e-2, k
+    loss2 = eb.step(xb, yb).item()
+    assert loss1 == loss2
+    for k, v in eb.grads().items():
+        assert torch.equal(v, gb[k]), k

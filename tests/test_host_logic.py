@@ -1,0 +1,154 @@
+"""CPU: host-side logic of the drop-in layer — constructor/state_dict compatibility with the reference,
+flat parameter layout and gradient buckets, Adam hyper-parameter arithmetic, and the data-parallel bucket
+all-reduce on a 2-rank gloo group."""
+import math
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from oracle.ref_shim import import_reference, reference_available
+
+README = dict(num_classes=10, img_size=32, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+
+
+def make(**kw):
+    import vit_cifar_b200 as vb
+    return vb.ViT(3, kw.pop("num_classes", 10), **kw)
+
+
+def test_constructor_signature_and_state_dict_match_oracle_names():
+    import inspect
+    import vit_cifar_b200 as vb
+    sig = inspect.signature(vb.ViT.__init__)
+    assert list(sig.parameters)[1:] == ["in_c", "num_classes", "img_size", "patch", "dropout", "num_layers", "hidden", "encoder_mlp",
+                                        "mlp_hidden", "head", "is_cls_token"]  # vit.py:20-33
+    d = {k: v.default for k, v in sig.parameters.items() if k != "self"}
+    assert d == dict(in_c=3, num_classes=10, img_size=224, patch=16, dropout=0.0, num_layers=12, hidden=768, encoder_mlp=True,
+                     mlp_hidden=3072, head=8, is_cls_token=True)
+    m = make(**README)
+    cfg = oracle.ViTConfig(**README)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == cfg.param_shapes()
+    assert list(sd.keys()) == list(cfg.param_shapes().keys())
+    assert sum(p.numel() for p in m.parameters()) == 6_268_810 and len(list(m.parameters())) == 120
+    with pytest.raises(AssertionError):
+        make(img_size=32, patch=5)  # vit.py:40
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_same_seed_gives_reference_initialisation_and_interchangeable_state_dict():
+    ref_vit, _, _ = import_reference()
+    kw = dict(img_size=32, patch=4, num_layers=2, hidden=128, mlp_hidden=256, head=4)
+    torch.manual_seed(2045)
+    ref = ref_vit.ViT(3, 100, **kw)
+    torch.manual_seed(2045)
+    ours = make(num_classes=100, **kw)
+    rsd, osd = ref.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), k  # same construction order -> same RNG stream
+    ours.load_state_dict(rsd)          # reference checkpoint -> ours
+    ref.load_state_dict(ours.state_dict())  # and back
+    # the block interfaces the reference's callers touch (network.py:411, run_model.py:45-47)
+    assert hasattr(ours.enc[0], "save_attn_map") and hasattr(ours.enc[0].attention, "save_attn_map")
+    ours.enc[0].save_attn_map = True
+    assert ours.enc[0].attention.save_attn_map is True
+    with pytest.raises(Exception):
+        ours.enc[1].get_attention_map()
+
+
+def test_flat_layout_and_buckets():
+    from vit_cifar_b200.params import ALIGN
+    m = make(**README)
+    lay = m._layout()
+    H = 384
+    offs = [s.off for s in lay.slots.values()]
+    assert all(o % ALIGN == 0 for o in offs)
+    q, k, v = (lay.slots[f"enc.3.attention.{n}.weight"] for n in ("Wq", "Wk", "Wv"))
+    assert k.off == q.off + H * H and v.off == k.off + H * H  # one (3H,H) operand for the fused QKV GEMM
+    bq, bv = lay.slots["enc.3.attention.Wq.bias"], lay.slots["enc.3.attention.Wv.bias"]
+    assert bv.off + bv.numel - bq.off == 3 * H
+    b = m.bucket_bounds()
+    assert len(b) == 7 + 2 and b[0][0] == 0 and b[-1][1] == lay.active_end
+    assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+    assert all(e - s == 888_576 for s, e in b[1:-1])  # 888,576 parameters per encoder layer
+    # a model without the MLP keeps la2 out of the optimised range (torch's Adam skips grad-less parameters)
+    m2 = make(img_size=32, patch=4, num_layers=1, hidden=128, mlp_hidden=128, head=4, encoder_mlp=False)
+    l2 = m2._layout()
+    assert l2.slots["enc.0.la2.weight"].off >= l2.active_end
+
+
+def test_adam_hyper_matches_torch_arithmetic():
+    import vit_cifar_b200 as vb
+    h = vb.adam_hyper(3, 1e-3, 0.9, 0.999, 1e-8, 5e-5, 0.5)
+    assert h[0] == 1e-3 / (1 - 0.9 ** 3) and h[1] == math.sqrt(1 - 0.999 ** 3) and h[2:] == [0.9, 0.999, 1e-8, 5e-5, 0.5]
+
+
+def test_dims_validation_messages():
+    from vit_cifar_b200.functional import Dims
+    Dims(B=2, T=65, H=384, heads=12, M=384).check()
+    with pytest.raises(ValueError):
+        Dims(B=2, T=65, H=100, heads=4, M=128).check()
+    with pytest.raises(ValueError):
+        Dims(B=2, T=65, H=384, heads=8, M=384).check()   # head_dim 48
+    with pytest.raises(ValueError):
+        Dims(B=2, T=197, H=384, heads=12, M=384).check()  # 14x14+1 tokens do not fit the short-sequence kernel
+
+
+def test_dropout_training_is_loud():
+    import vit_cifar_b200 as vb
+    m = vb.ViT(3, 10, img_size=32, patch=4, dropout=0.1, num_layers=1, hidden=128, mlp_hidden=128, head=4)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 32, 32))
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vit_cifar_b200.parallel import allreduce_all
+        import vit_cifar_b200 as vb
+        m = vb.ViT(3, 10, img_size=32, patch=4, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+        lay = m._layout()
+        buckets = m.bucket_bounds()
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = torch.randn(lay.total, generator=g)
+        flat[lay.active_end:] = 0
+        mine = flat.clone()
+        allreduce_all(flat, buckets, None)
+        q.put((rank, mine, flat))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucket_allreduce_two_ranks_gloo():
+    """world_size-2 data-parallel exchange on CPU: every bucket summed across ranks, identical on both, and
+    Adam with grad_scale = 1/2 on the sum equals Adam on the mean (DDP semantics)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        r, mine, red = q.get(timeout=120)
+        got[r] = (mine.clone(), red.clone())
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = got[0][0] + got[1][0]
+    assert torch.equal(got[0][1], got[1][1])
+    torch.testing.assert_close(got[0][1], total)
+    # mean semantics through the optimiser scale
+    p0 = torch.randn(64)
+    a = {"p": p0.clone()}; b = {"p": p0.clone()}
+    z = lambda: {"p": torch.zeros(64)}  # noqa: E731
+    gsum = total[:64]
+    oracle.adam_step(a, {"p": gsum / 2}, z(), z(), 1)
+    oracle.adam_step(b, {"p": gsum * 0.5}, z(), z(), 1)
+    assert torch.equal(a["p"], b["p"])

@@ -36,8 +36,13 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-// after a kernel launch
-#define VITB_LAUNCH_OK() VITB_CUDA_OK(cudaPeekAtLastError())
+// after a kernel launch (also counts launches: bench.py reports how many of OUR kernels ran per step)
+void count_launch();
+#define VITB_LAUNCH_OK()                   \
+  do {                                     \
+    ::vitb::count_launch();                \
+    VITB_CUDA_OK(cudaPeekAtLastError());   \
+  } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;  // host-side, single launching thread per process
+void count_launch() { ++g_launches; }
+
 // ---------------------------------------------------------------------------------------------
 // cast
 // ---------------------------------------------------------------------------------------------
@@ -301,6 +304,7 @@ extern "C" {
 
 int vitb_version(void) { return VITB_ABI_VERSION; }
 const char* vitb_last_error(void) { return g_err; }
+unsigned long long vitb_launch_count(void) { return g_launches; }
 
 int vitb_device_supported(void) {
   int dev = 0, major = 0;

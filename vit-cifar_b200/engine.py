@@ -1,0 +1,199 @@
+"""``TrainEngine``: the whole training step (forward + LS-CE + backward + gradient all-reduce + Adam) of a packed
+``ViT`` as ONE static kernel sequence, captured into a CUDA graph.
+
+This is the caller the reference gets from Lightning (network.py:149-208 + automatic optimisation + DDP,
+SURVEY.md §3.1) reduced to the hot loop: no autograd, no allocation, no host sync inside a step.  Data-parallel
+across ranks (one process per GPU): each encoder layer's gradients are one contiguous bucket of the flat gradient
+buffer, all-reduced (NCCL, sum) on a side stream as soon as that layer's backward has been issued, so the
+exchange overlaps the remaining backward; the 1/world_size of DDP's mean is folded into Adam's gradient scale.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import functional as Fn
+from . import ops
+from .layers import act_dtype
+from .optim import adam_hyper
+from .parallel import allreduce_bucket
+from .params import LayerViews
+from .vit import ViT
+
+
+class TrainEngine:
+    def __init__(self, model: ViT, batch_size: int, smoothing: float = 0.1, lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 5e-5, process_group=None, use_graph: bool = True,
+                 overlap_comm: bool = True):
+        ops.require_device()
+        self.model = model
+        self.B = int(batch_size)
+        self.smoothing = float(smoothing)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.use_graph = use_graph
+        self.overlap_comm = overlap_comm and self.world > 1
+        if model.p_drop > 0.0:
+            raise NotImplementedError("dropout > 0 is not implemented in the fused training step (reference default 0.0)")
+
+        st = model._ensure_packed()
+        self.store = st
+        self.dev = st.device
+        self.act = act_dtype()
+        L = st.layout
+        self.n = L.active_end
+        self.P = st.flat
+        self.G = torch.zeros_like(self.P)
+        self.Mo = torch.zeros_like(self.P)
+        self.V = torch.zeros_like(self.P)
+        if self.act == torch.bfloat16:
+            self.C = st.shadow()
+            ops.cast_f32_to_bf16(self.P, self.C)
+        else:
+            self.C = self.P
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.P, src=0, group=self.pg)  # identical replicas
+            if self.C is not self.P:
+                ops.cast_f32_to_bf16(self.P, self.C)
+
+        H, M = model.hidden, model.mlp_hidden
+        self.dm = Fn.Dims(B=self.B, T=model.num_tokens, H=H, heads=model.head, M=M, use_mlp=model.encoder_mlp)
+        self.dm.check()
+        mk = lambda buf, i: LayerViews(L, buf, f"enc.{i}.", H, M, model.encoder_mlp)  # noqa: E731
+        self.lp = [mk(self.P, i) for i in range(model.num_layers)]
+        self.lc = [mk(self.C, i) for i in range(model.num_layers)]
+        self.lg = [mk(self.G, i) for i in range(model.num_layers)]
+        v = L.view
+        self.has_cls = model.is_cls_token
+        self.stem_p = (v(self.P, "emb.weight"), v(self.P, "emb.bias"),
+                       v(self.P, "cls_token").view(-1) if self.has_cls else None, v(self.P, "pos_emb").view(model.num_tokens, H))
+        self.stem_g = (v(self.G, "emb.weight"), v(self.G, "emb.bias"),
+                       v(self.G, "cls_token").view(-1) if self.has_cls else None, v(self.G, "pos_emb").view(model.num_tokens, H))
+        self.head_p = (v(self.P, "fc.0.weight"), v(self.P, "fc.0.bias"), v(self.C, "fc.1.weight"), v(self.P, "fc.1.bias"))
+        self.head_g = (v(self.G, "fc.0.weight"), v(self.G, "fc.0.bias"), v(self.G, "fc.1.weight"), v(self.G, "fc.1.bias"))
+        self.buckets = model.bucket_bounds()  # [stem, layer0..layerL-1, head]
+
+        S = model.img_size
+        self.img = torch.zeros((self.B, 3, S, S), dtype=torch.float32, device=self.dev)
+        self.labels = torch.zeros((self.B,), dtype=torch.int64, device=self.dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.dlogits = torch.zeros((self.B, model.num_classes), dtype=torch.float32, device=self.dev)
+        self.logits: Optional[torch.Tensor] = None
+        self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        # ring of pinned slots: the async H2D of step k must not see the host writing step k+1's values
+        self.hyper_host = torch.zeros((1024, 8), dtype=torch.float32).pin_memory()
+        self.step_count = 0
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._comm_stream = torch.cuda.Stream(device=self.dev) if self.overlap_comm else None
+        self.launches_per_step = 0  # filled by the first (eager) step
+
+    # -- static buffers ---------------------------------------------------------------------------
+    def _alloc(self, scope: str):
+        def alloc(name: str, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
+            key = f"{scope}.{name}"
+            t = self._bufs.get(key)
+            if t is None:
+                t = torch.empty(shape, dtype=dtype, device=self.dev)
+                self._bufs[key] = t
+            return t
+        return alloc
+
+    def activation_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+
+    # -- the kernel sequence ----------------------------------------------------------------------
+    def _allreduce(self, bucket: Tuple[int, int]) -> None:
+        if self.world == 1:
+            return
+        allreduce_bucket(self.G, bucket, self.pg, self._comm_stream)
+
+    def _body(self) -> None:
+        m, dm = self.model, self.dm
+        B, T, H, Cn = self.B, m.num_tokens, m.hidden, m.num_classes
+        emb_w, emb_b, cls, pos = self.stem_p
+        x = Fn.stem_fwd(self.img, emb_w, emb_b, cls, pos, m.patch, self.act, self._alloc("stem"))
+        saved = []
+        for i in range(m.num_layers):
+            x, sv = Fn.encoder_fwd(x, self.lc[i], self.lp[i], dm, self._alloc(f"l{i}"))
+            saved.append(sv)
+        ln_w, ln_b, fc_w_c, fc_b = self.head_p
+        self.logits, hsaved = Fn.head_fwd(x, ln_w, ln_b, fc_w_c, fc_b, B, T, H, Cn, m.is_cls_token, self._alloc("head"))
+        ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0)
+
+        g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
+        dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
+                         self._alloc("headb"))
+        self._allreduce(self.buckets[-1])
+        for i in reversed(range(m.num_layers)):
+            # backward scratch is shared by all layers; the input-gradient buffer ping-pongs
+            dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i))
+            self._allreduce(self.buckets[1 + i])
+        g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
+        Fn.stem_bwd(self.img, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
+        self._allreduce(self.buckets[0])
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        n = self.n
+        ops.adam(self.P[:n], self.G[:n], self.Mo[:n], self.V[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
+
+    def _bwd_alloc(self, i: int):
+        shared = self._alloc("bwd")
+        pp = self._alloc(f"bwd{i & 1}")
+
+        def alloc(name: str, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
+            return pp(name, shape, dtype) if name == "dx" else shared(name, shape, dtype)
+        return alloc
+
+    # -- public API -------------------------------------------------------------------------------
+    def set_lr(self, lr: float) -> None:
+        self.lr = float(lr)
+
+    def load_batch(self, img: torch.Tensor, labels: torch.Tensor) -> None:
+        """Copy a batch (pinned host or device tensors) into the static input buffers on the current stream."""
+        self.img.copy_(img, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+
+    def step(self, img: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step.  Returns the (device) loss tensor of this step; no host synchronisation."""
+        if img is not None:
+            self.load_batch(img, labels)
+        self.step_count += 1
+        h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
+        slot[:7] = torch.tensor(h, dtype=torch.float32)
+        self.hyper_dev.copy_(slot, non_blocking=True)
+        if not self.use_graph:
+            n0 = ops.launch_count()
+            self._body()
+            self.launches_per_step = ops.launch_count() - n0
+        elif self._graph is None:
+            # warm-up run (allocates every static buffer, primes NCCL), then capture
+            n0 = ops.launch_count()
+            self._body()
+            self.launches_per_step = ops.launch_count() - n0
+            torch.cuda.current_stream().synchronize()
+            # the warm-up already applied this step's update; capture for the following ones
+            g = torch.cuda.CUDAGraph()
+            snapshot = (self.P.clone(), self.Mo.clone(), self.V.clone(), self.loss.clone())
+            with torch.cuda.graph(g):
+                self._body()
+            # capture does not execute, but restore state anyway in case a backend ran work eagerly
+            self.P.copy_(snapshot[0]); self.Mo.copy_(snapshot[1]); self.V.copy_(snapshot[2]); self.loss.copy_(snapshot[3])
+            if self.C is not self.P:
+                ops.cast_f32_to_bf16(self.P, self.C)
+            self._graph = g
+        else:
+            self._graph.replay()
+        return self.loss
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        """Views of the flat gradient buffer by state_dict name (of the LAST step; summed over ranks when world > 1)."""
+        L = self.store.layout
+        return {k: L.view(self.G, k) for k in L.slots if L.slots[k].off < self.n}

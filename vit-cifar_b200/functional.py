@@ -1,0 +1,191 @@
+"""Forward / backward of the ViT training step as explicit kernel sequences over libvitb200.
+
+No autograd in here: each function launches the kernels of one block in order and returns what the
+matching backward needs.  The module layer (layers.py / vit.py) wraps these in ``autograd.Function``s;
+the training engine (engine.py) calls them directly on static buffers inside a CUDA graph.
+
+`alloc(name, shape, dtype)` supplies output/scratch tensors: fresh ones under autograd, fixed ones in
+the engine.  Activations are (rows, H) row-major with rows = B*T.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+
+from . import ops
+from .params import LayerViews
+
+Alloc = Callable[[str, tuple, torch.dtype], torch.Tensor]
+
+
+def default_alloc(device: torch.device) -> Alloc:
+    def alloc(name: str, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=device)
+    return alloc
+
+
+@dataclass
+class Dims:
+    B: int
+    T: int
+    H: int
+    heads: int
+    M: int          # mlp_hidden
+    use_mlp: bool = True
+
+    @property
+    def rows(self) -> int:
+        return self.B * self.T
+
+    @property
+    def d(self) -> int:
+        return self.H // self.heads
+
+    @property
+    def scale(self) -> float:  # layers.py:79,97: 1/sqrt(features), NOT 1/sqrt(head_dim)
+        return 1.0 / (self.H ** 0.5)
+
+    def check(self) -> None:
+        if self.H % 128 != 0:
+            raise ValueError(f"hidden={self.H} must be a multiple of 128 for the vectorised LayerNorm kernels")
+        if self.H % self.heads != 0 or self.d not in (32, 64):
+            raise ValueError(f"head_dim={self.H}/{self.heads} must be 32 or 64 for the fused attention kernel")
+        if self.T > 128:
+            raise ValueError(f"{self.T} tokens > 128: the fused short-sequence attention kernel keeps (T x T) on chip")
+        if self.use_mlp and self.M % 128 != 0:
+            raise ValueError(f"mlp_hidden={self.M} must be a multiple of 128")
+
+
+# ---------------------------------------------------------------------------------------------
+# attention block: layers.py:90-103  (x -> out_project(attn(QKV(x))))
+# ---------------------------------------------------------------------------------------------
+def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: Alloc, residual: Optional[torch.Tensor],
+             attn_map: Optional[torch.Tensor] = None):
+    """x (rows,H) act -> y (rows,H) = out_project(attention(x)) (+ residual).  Returns (y, saved)."""
+    rows, H, act = dm.rows, dm.H, x.dtype
+    qkv = alloc("qkv", (rows, 3 * H), act)
+    ops.gemm_fwd(x, c.wqkv, p.bqkv, None, qkv, None, rows, 3 * H, H)
+    o = alloc("o", (rows, H), act)
+    lse = alloc("lse", (dm.B, dm.heads, dm.T), torch.float32)
+    ops.attn_fwd(qkv, o, lse, attn_map, dm.B, dm.T, dm.heads, dm.d, dm.scale)
+    y = alloc("x1", (rows, H), act)
+    ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H)
+    return y, (x, qkv, o, lse)
+
+
+def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc, bo_done: bool = False):
+    """dy (rows,H) = grad of the out_project output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x."""
+    x, qkv, o, lse = saved
+    rows, H, act = dm.rows, dm.H, dy.dtype
+    ops.gemm_wgrad(dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
+    do = alloc("do", (rows, H), act)
+    ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
+    dqkv = alloc("dqkv", (rows, 3 * H), act)
+    ops.attn_bwd(qkv, do, lse, dqkv, dm.B, dm.T, dm.heads, dm.d, dm.scale)
+    ops.gemm_wgrad(dqkv, x, g.wqkv, g.bqkv, rows, 3 * H, H)
+    dx = alloc("dxn", (rows, H), act)
+    ops.gemm_dgrad(dqkv, c.wqkv, None, dx, rows, 3 * H, H)
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder block: layers.py:44-48
+# ---------------------------------------------------------------------------------------------
+def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: Alloc, attn_map: Optional[torch.Tensor] = None):
+    rows, H, M, act = dm.rows, dm.H, dm.M, x.dtype
+    xn = alloc("xn", (rows, H), act)
+    mean1 = alloc("mean1", (rows,), torch.float32)
+    rstd1 = alloc("rstd1", (rows,), torch.float32)
+    ops.layernorm_fwd(x, H, p.ln1_w, p.ln1_b, xn, mean1, rstd1, rows, H)
+    x1, att_saved = mhsa_fwd(xn, c, p, dm, alloc, residual=x, attn_map=attn_map)  # out = attention(la1(x)) + x
+    if not dm.use_mlp:
+        return x1, (x, mean1, rstd1, att_saved, None)
+    x1n = alloc("x1n", (rows, H), act)
+    mean2 = alloc("mean2", (rows,), torch.float32)
+    rstd2 = alloc("rstd2", (rows,), torch.float32)
+    ops.layernorm_fwd(x1, H, p.ln2_w, p.ln2_b, x1n, mean2, rstd2, rows, H)
+    z1 = alloc("z1", (rows, M), act)
+    a1 = alloc("a1", (rows, M), act)
+    ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True)            # mlp[0], mlp[1]
+    z2 = alloc("z2", (rows, H), act)
+    x2 = alloc("x2", (rows, H), act)
+    ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True)                # mlp[3], mlp[4], + out
+    return x2, (x, mean1, rstd1, att_saved, (x1, x1n, mean2, rstd2, z1, a1, z2))
+
+
+def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc):
+    """dout = grad of the block output; fills every field of g; returns grad of the block input."""
+    x, mean1, rstd1, att_saved, mlp_saved = saved
+    rows, H, M, act = dm.rows, dm.H, dm.M, dout.dtype
+    if dm.use_mlp:
+        x1, x1n, mean2, rstd2, z1, a1, z2 = mlp_saved
+        dz2 = alloc("dz2", (rows, H), act)
+        ops.gelu_bwd_colsum(dout, z2, dz2, g.b2, rows, H)                # second GELU (layers.py:37) + db2
+        ops.gemm_wgrad(dz2, a1, g.w2, None, rows, H, M)
+        dz1 = alloc("dz1", (rows, M), act)
+        ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)                   # first GELU's backward fused in the epilogue
+        ops.gemm_wgrad(dz1, x1n, g.w1, g.b1, rows, M, H)
+        dx1n = alloc("dx1n", (rows, H), act)
+        ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
+        dx1 = alloc("dx1", (rows, H), act)
+        # grad of x1 = residual branch (dout) + LN2 backward; its column sums are out_project's bias grad
+        ops.layernorm_bwd(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, g.bo, rows, H)
+        bo_done = True
+    else:
+        dx1 = dout
+        bo_done = False
+    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done)
+    dx = alloc("dx", (rows, H), act)
+    ops.layernorm_bwd(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, None, rows, H)
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------
+# stem: vit.py:66-70   and   head: vit.py:72-76
+# ---------------------------------------------------------------------------------------------
+def stem_fwd(img: torch.Tensor, emb_w, emb_b, cls, pos, P: int, act: torch.dtype, alloc: Alloc) -> torch.Tensor:
+    B = img.shape[0]
+    has_cls = cls is not None
+    T = P * P + (1 if has_cls else 0)
+    H = emb_w.shape[0]
+    x0 = alloc("x0", (B * T, H), act)
+    ops.patch_embed_fwd(img, emb_w, emb_b, cls, pos, x0, P, has_cls)
+    return x0
+
+
+def stem_bwd(img: torch.Tensor, dx0: torch.Tensor, g_emb_w, g_emb_b, g_cls, g_pos, P: int) -> None:
+    ops.patch_embed_bwd(img, dx0, g_emb_w, g_emb_b, g_cls, g_pos, P, g_cls is not None)
+
+
+def head_fwd(x: torch.Tensor, ln_w, ln_b, fc_w_c, fc_b, B: int, T: int, H: int, C: int, is_cls: bool, alloc: Alloc):
+    """x (B*T,H) act -> logits (B,C) fp32."""
+    act = x.dtype
+    if is_cls:
+        src, stride = x, T * H          # LayerNorm reads out[:,0] in place (vit.py:73)
+    else:
+        src = alloc("pooled", (B, H), act)
+        ops.pool_fwd(x, src, B, T, H, 1)  # out.mean(1), vit.py:75
+        stride = H
+    hn = alloc("hn", (B, H), act)
+    mean = alloc("hmean", (B,), torch.float32)
+    rstd = alloc("hrstd", (B,), torch.float32)
+    ops.layernorm_fwd(src, stride, ln_w, ln_b, hn, mean, rstd, B, H)
+    logits = alloc("logits", (B, C), torch.float32)
+    ops.gemm_fwd(hn, fc_w_c, fc_b, None, logits, None, B, C, H, out_f32=True)
+    return logits, (src, stride, hn, mean, rstd)
+
+
+def head_bwd(dlogits: torch.Tensor, saved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B: int, T: int, H: int, C: int,
+             is_cls: bool, act: torch.dtype, alloc: Alloc) -> torch.Tensor:
+    """dlogits (B,C) fp32 -> grad of the encoder output (B*T,H) act (zeros where nothing flows)."""
+    src, stride, hn, mean, rstd = saved
+    ops.gemm_wgrad(dlogits, hn, g_fc_w, g_fc_b, B, C, H, dy_f32=True)
+    dhn = alloc("dhn", (B, H), act)
+    ops.gemm_dgrad(dlogits, fc_w_c, None, dhn, B, C, H, dy_f32=True)
+    dpool = alloc("dpool", (B, H), act)
+    ops.layernorm_bwd(dhn, src, stride, ln_w, mean, rstd, None, dpool, H, g_ln_w, g_ln_b, None, B, H)
+    dx = alloc("dxL", (B * T, H), act)
+    ops.pool_bwd(dpool, dx, B, T, H, 0 if is_cls else 1)
+    return dx

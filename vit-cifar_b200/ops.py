@@ -1,0 +1,191 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, raw device pointers + current stream out.
+
+PyTorch is plumbing here (device memory, streams); every FLOP on this path runs in libvitb200.so.
+All functions launch on ``torch.cuda.current_stream()`` and never synchronise, so a sequence of them can be
+captured into a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, GEMM_DY_F32, GEMM_GELU, GEMM_OUT_F32, check
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt_of(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"activation dtype must be float32 or bfloat16, got {t.dtype}") from None
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.VitbError("libvitb200 kernels take CUDA tensors only (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _contig(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise ValueError("libvitb200 ops need contiguous tensors")
+
+
+def require_device() -> None:
+    """Fail loudly when there is no usable B200 / library (the product path has no fallback)."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.VitbError("no CUDA device: the vit-cifar_b200 hot path runs on sm_100a only")
+    if not lib.vitb_device_supported():
+        raise _lib.VitbError("current CUDA device is not compute capability 10.x (B200)")
+
+
+def launch_count() -> int:
+    """Kernels launched (or captured) by libvitb200 so far in this process."""
+    return int(_lib.load().vitb_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# workspace: one growing scratch buffer per device; old buffers stay alive (graph safety)
+# ---------------------------------------------------------------------------------------------
+_ws: dict = {}
+_ws_keep: list = []
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    cur = _ws.get(key)
+    if cur is None or cur.numel() < nbytes:
+        size = max(int(nbytes), 1 << 20)
+        if cur is not None:
+            _ws_keep.append(cur)
+            size = max(size, 2 * cur.numel())
+        cur = torch.empty(size, dtype=torch.uint8, device=device)
+        _ws[key] = cur
+    return cur
+
+
+# ---------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------
+def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    _contig(src, dst)
+    check(_lib.load().vitb_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_f32_to_bf16")
+
+
+def patch_embed_fwd(img, w, bias, cls, pos, out, P: int, has_cls: bool) -> None:
+    B, _, S, _ = img.shape
+    H = w.shape[0]
+    assert img.dtype == torch.float32 and w.dtype == torch.float32
+    _contig(img, w, bias, cls, pos, out)
+    check(_lib.load().vitb_patch_embed_fwd(_ptr(img), _ptr(w), _ptr(bias), _ptr(cls), _ptr(pos), _ptr(out),
+                                           B, S, P, H, int(has_cls), dt_of(out), _stream()), "patch_embed_fwd")
+
+
+def patch_embed_bwd(img, dout, dw, dbias, dcls, dpos, P: int, has_cls: bool) -> None:
+    B, _, S, _ = img.shape
+    H = dw.shape[0]
+    lib = _lib.load()
+    _contig(img, dout, dw, dbias, dcls, dpos)
+    nb = lib.vitb_patch_embed_bwd_ws_bytes(B, S, P, H, int(has_cls))
+    ws = workspace(nb, img.device)
+    check(lib.vitb_patch_embed_bwd(_ptr(img), _ptr(dout), _ptr(dw), _ptr(dbias), _ptr(dcls), _ptr(dpos), _ptr(ws), ws.numel(),
+                                   B, S, P, H, int(has_cls), dt_of(dout), _stream()), "patch_embed_bwd")
+
+
+def layernorm_fwd(x, x_row_stride: int, gamma, beta, y, mean, rstd, rows: int, H: int, eps: float = 1e-5) -> None:
+    check(_lib.load().vitb_layernorm_fwd(_ptr(x), x_row_stride, _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd),
+                                         rows, H, eps, dt_of(y), _stream()), "layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, x_row_stride: int, gamma, mean, rstd, dres, dx, dx_row_stride: int, dgamma, dbeta, dx_colsum,
+                  rows: int, H: int) -> None:
+    lib = _lib.load()
+    nb = lib.vitb_layernorm_bwd_ws_bytes(rows, H)
+    ws = workspace(nb, dy.device)
+    check(lib.vitb_layernorm_bwd(_ptr(dy), _ptr(x), x_row_stride, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                 dx_row_stride, _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum), _ptr(ws), ws.numel(), rows, H,
+                                 dt_of(dy), _stream()), "layernorm_bwd")
+
+
+def gemm_fwd(a, w_act, bias, residual, out, preact, M: int, N: int, K: int, gelu: bool = False, out_f32: bool = False) -> None:
+    flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out_f32 else 0)
+    check(_lib.load().vitb_gemm_bias_act_fwd(_ptr(a), _ptr(w_act), _ptr(bias), _ptr(residual), _ptr(out), _ptr(preact),
+                                             M, N, K, flags, dt_of(a), _stream()), "gemm_bias_act_fwd")
+
+
+def gemm_dgrad(dy, w_act, z, dx, M: int, N: int, K: int, dy_f32: bool = False) -> None:
+    flags = GEMM_DY_F32 if dy_f32 else 0
+    check(_lib.load().vitb_gemm_dgrad(_ptr(dy), _ptr(w_act), _ptr(z), _ptr(dx), M, N, K, flags, dt_of(dx), _stream()), "gemm_dgrad")
+
+
+def gemm_wgrad(dy, x, dw, dbias, M: int, N: int, K: int, dy_f32: bool = False) -> None:
+    lib = _lib.load()
+    dt = dt_of(x)
+    nb = lib.vitb_gemm_wgrad_ws_bytes(M, N, K, dt)
+    ws = workspace(nb, x.device)
+    flags = GEMM_DY_F32 if dy_f32 else 0
+    check(lib.vitb_gemm_wgrad_dbias(_ptr(dy), _ptr(x), _ptr(dw), _ptr(dbias), _ptr(ws), ws.numel(), M, N, K, flags, dt, _stream()),
+          "gemm_wgrad_dbias")
+
+
+def attn_fwd(qkv, o, lse, attn_map, B: int, T: int, heads: int, d: int, scale: float) -> None:
+    check(_lib.load().vitb_attn_fwd(_ptr(qkv), _ptr(o), _ptr(lse), _ptr(attn_map), B, T, heads, d, scale, dt_of(qkv), _stream()), "attn_fwd")
+
+
+def attn_bwd(qkv, d_o, lse, dqkv, B: int, T: int, heads: int, d: int, scale: float) -> None:
+    check(_lib.load().vitb_attn_bwd(_ptr(qkv), _ptr(d_o), _ptr(lse), _ptr(dqkv), B, T, heads, d, scale, dt_of(qkv), _stream()), "attn_bwd")
+
+
+def gelu_bwd_colsum(dy, z, dz, colsum, rows: int, cols: int) -> None:
+    lib = _lib.load()
+    ws = workspace(lib.vitb_colsum_ws_bytes(rows, cols), dy.device)
+    check(lib.vitb_gelu_bwd_colsum(_ptr(dy), _ptr(z), _ptr(dz), _ptr(colsum), _ptr(ws), ws.numel(), rows, cols, dt_of(dy), _stream()),
+          "gelu_bwd_colsum")
+
+
+def colsum(x, out, rows: int, cols: int) -> None:
+    lib = _lib.load()
+    ws = workspace(lib.vitb_colsum_ws_bytes(rows, cols), x.device)
+    check(lib.vitb_colsum(_ptr(x), _ptr(out), _ptr(ws), ws.numel(), rows, cols, dt_of(x), _stream()), "colsum")
+
+
+def pool_fwd(x, y, B: int, T: int, H: int, mode: int) -> None:
+    check(_lib.load().vitb_pool_fwd(_ptr(x), _ptr(y), B, T, H, mode, dt_of(x), _stream()), "pool_fwd")
+
+
+def pool_bwd(dy, dx, B: int, T: int, H: int, mode: int) -> None:
+    check(_lib.load().vitb_pool_bwd(_ptr(dy), _ptr(dx), B, T, H, mode, dt_of(dx), _stream()), "pool_bwd")
+
+
+def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0) -> None:
+    B, Cn = logits.shape
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    _contig(logits, labels, dlogits)
+    check(_lib.load().vitb_ls_ce_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(loss), _ptr(dlogits), B, Cn, smoothing, grad_scale, _stream()),
+          "ls_ce_fwd_bwd")
+
+
+_HyperArr = C.c_float * 8
+
+
+def adam(p, g, m, v, shadow, hyper_host=None, hyper_dev=None) -> None:
+    """hyper_host: sequence of 7 floats (see vitb200.h) or None; hyper_dev: 8-float CUDA tensor or None."""
+    n = p.numel()
+    hh = None
+    if hyper_host is not None:
+        hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (8 - len(hyper_host))))
+    check(_lib.load().vitb_adam_multi(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n,
+                                      C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()), "adam_multi")
