@@ -132,9 +132,10 @@ int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, 
 
 /* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77
  * (lr main.py:48, betas :51-52, weight_decay :56, eps 1e-8).  g is multiplied by grad_scale first
- * (1/world_size after a sum all-reduce).  hyper: HOST values {step_size = lr/(1-b1^t),
- * bc2_sqrt = sqrt(1-b2^t), beta1, beta2, eps, weight_decay, grad_scale, 0}.  If hyper_dev != NULL
- * the 8 floats are read from device memory instead (so a captured CUDA graph sees new values).
+ * (1/world_size after a sum all-reduce).  hyper: 16 HOST floats {step_size = lr/(1-b1^t),
+ * bc2_sqrt = sqrt(1-b2^t), beta1, beta2, eps, weight_decay, grad_scale, 1-beta1, 1-beta2, 0...}
+ * (computed in double by the caller, as torch does).  If hyper_dev != NULL the 16 floats are read
+ * from device memory instead (so a captured CUDA graph sees new values every replay).
  * w_shadow (bf16, n) may be NULL; else it receives the updated parameters rounded to bf16. ---- */
 int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow, int64_t n,
                     const float* hyper_host, const float* hyper_dev, void* stream);

@@ -268,7 +268,7 @@ def test_adam_matches_oracle(ops):
     m = {"p": torch.zeros(n)}; v = {"p": torch.zeros(n)}
     pd, md, vd = cu(p), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
     sh = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
-    hd = torch.zeros(8, device="cuda")
+    hd = torch.zeros(16, device="cuda")
     for t in range(1, 5):
         g = rnd((n,), torch.float32, 10 + t)
         oracle.adam_step(ref, {"p": g}, m, v, t)
@@ -276,7 +276,7 @@ def test_adam_matches_oracle(ops):
         if t % 2:
             ops.adam(pd, cu(g), md, vd, sh, hyper_host=h)
         else:  # device-resident hyper-parameters (the CUDA-graph path)
-            hd.copy_(torch.tensor(h + [0.0]))
+            hd.copy_(torch.tensor(h + [0.0] * (16 - len(h))))
             ops.adam(pd, cu(g), md, vd, sh, hyper_dev=hd)
     assert rel(pd, ref["p"]) < 1e-6
     assert rel(md, m["p"]) < 1e-6 and rel(vd, v["p"]) < 1e-6

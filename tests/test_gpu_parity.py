@@ -21,6 +21,21 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def grad_scale_of(grads):
+    """RMS element of all reference gradients: the floor below which a gradient tensor counts as zero."""
+    ts = [g.double().flatten() for g in grads.values() if g is not None]
+    return torch.cat(ts).pow(2).mean().sqrt().item()
+
+
+def grad_err(a, b, scale):
+    """||a-b|| / (||b|| + scale*sqrt(n)).  Plain relative error for ordinary tensors; for tensors whose true gradient is
+    ~0 it measures the error against the model's typical gradient magnitude instead.  The case that needs it:
+    attention.Wk.bias — softmax is invariant to a per-row shift of the scores, so d loss / d b_k == 0 analytically and
+    the oracle's own value is 1e-10-level rounding noise."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + scale * b.numel() ** 0.5)).item()
+
+
 @pytest.fixture()
 def vb():
     import vit_cifar_b200 as v
@@ -67,12 +82,13 @@ def test_module_forward_backward_vs_oracle(vb, name, precision):
     if precision == "fp32":
         assert torch.equal(logits.argmax(-1).cpu(), logits_ref.argmax(-1))  # bit-exact predictions
     worst = ("", 0.0)
+    gs = grad_scale_of(grads_ref)
     for k, p in model.named_parameters():
         gr = grads_ref[k]
         if gr is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
-        e = rel(p.grad, gr)
+        e = rel(p.grad, gr) if "Wk.bias" not in k else grad_err(p.grad, gr, gs)
         if e > worst[1]:
             worst = (k, e)
     assert worst[1] < tol, f"worst grad {worst}"
@@ -91,8 +107,9 @@ def test_fp32_engine_matches_golden_after_3_adam_steps(vb, golden_dir, name):
         losses.append(eng.step(xd, yd).item())
         if len(losses) == 1:
             assert rel(eng.logits, g["logits"]) < 1e-4
+            gs = grad_scale_of(g["grads"])
             for k, gr in eng.grads().items():
-                assert rel(gr, g["grads"][k]) < 1e-4, k
+                assert (rel(gr, g["grads"][k]) if "Wk.bias" not in k else grad_err(gr, g["grads"][k], gs)) < 1e-4, k
     assert losses == pytest.approx(g["losses"], rel=1e-4)
     sd = model.state_dict()
     for k, ref in g["params3"].items():
@@ -116,6 +133,9 @@ def test_full_model_engine_vs_reference_golden(vb, golden_dir, name, precision):
         assert torch.equal(eng.logits.argmax(-1).cpu(), g["logits"].argmax(-1))
     for k, gr in eng.grads().items():
         ref = g["grads"][k]
+        if "Wk.bias" in k:  # analytically zero (see grad_err): only check it is negligible next to Wq.bias's gradient
+            assert gr.double().norm().item() < tol * g["grads"][k.replace("Wk", "Wq")]["norm"], k
+            continue
         assert abs(gr.double().norm().item() - ref["norm"]) < 2 * tol * ref["norm"] + 1e-9, k
         if precision == "fp32":
             torch.testing.assert_close(gr.flatten()[:16].cpu(), ref["head"], rtol=2e-3, atol=1e-6)
@@ -209,8 +229,9 @@ def test_standalone_blocks_vs_oracle(vb, precision):
     yr.sum().backward()
     assert y.dtype == torch.float32 and rel(y, yr.detach()) < tol
     assert rel(xg.grad, xr.grad) < tol
+    gs = grad_scale_of({k: v.grad for k, v in leaf.items()})
     for k, prm in enc.named_parameters():
-        assert rel(prm.grad, leaf[k].grad) < tol, k
+        assert (rel(prm.grad, leaf[k].grad) if "Wk.bias" not in k else grad_err(prm.grad, leaf[k].grad, gs)) < tol, k
     att = vb.MultiHeadSelfAttention(Fd, head=heads)
     pa = {k: v.detach().clone() for k, v in att.state_dict().items()}
     att = att.cuda()
@@ -234,8 +255,9 @@ def test_full_size_properties_b1024(vb):
     loss1 = eb.step(xb, yb).item()
     lb, gb = eb.logits.clone(), {k: v.clone() for k, v in eb.grads().items()}
     assert torch.equal(lb[:4], l4) and torch.equal(lb.view(256, 4, -1)[17], l4)
+    gs = grad_scale_of(g4)
     for k in g4:
-        assert rel(gb[k], g4[k]) < 2e-2, k
+        assert grad_err(gb[k], g4[k], 1e-3 * gs) < 2e-2, k
     loss2 = eb.step(xb, yb).item()
     assert loss1 == loss2
     for k, v in eb.grads().items():

@@ -85,7 +85,7 @@ def test_flat_layout_and_buckets():
 def test_adam_hyper_matches_torch_arithmetic():
     import vit_cifar_b200 as vb
     h = vb.adam_hyper(3, 1e-3, 0.9, 0.999, 1e-8, 5e-5, 0.5)
-    assert h[0] == 1e-3 / (1 - 0.9 ** 3) and h[1] == math.sqrt(1 - 0.999 ** 3) and h[2:] == [0.9, 0.999, 1e-8, 5e-5, 0.5]
+    assert h[0] == 1e-3 / (1 - 0.9 ** 3) and h[1] == math.sqrt(1 - 0.999 ** 3) and h[2:] == [0.9, 0.999, 1e-8, 5e-5, 0.5, 1.0 - 0.9, 1.0 - 0.999]
 
 
 def test_dims_validation_messages():
@@ -106,7 +106,7 @@ def test_dropout_training_is_loud():
         m(torch.zeros(1, 3, 32, 32))
 
 
-def _dp_worker(rank, world, port, q):
+def _dp_worker(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -120,7 +120,7 @@ def _dp_worker(rank, world, port, q):
         flat[lay.active_end:] = 0
         mine = flat.clone()
         allreduce_all(flat, buckets, None)
-        q.put((rank, mine, flat))
+        torch.save((mine, flat), os.path.join(outdir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -128,19 +128,17 @@ def _dp_worker(rank, world, port, q):
 def test_bucket_allreduce_two_ranks_gloo():
     """world_size-2 data-parallel exchange on CPU: every bucket summed across ranks, identical on both, and
     Adam with grad_scale = 1/2 on the sum equals Adam on the mean (DDP semantics)."""
+    import tempfile
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = {}
-    for _ in range(2):
-        r, mine, red = q.get(timeout=120)
-        got[r] = (mine.clone(), red.clone())
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    with tempfile.TemporaryDirectory() as outdir:
+        procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, outdir)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=180)
+            assert p.exitcode == 0
+        got = {r: torch.load(os.path.join(outdir, f"rank{r}.pt")) for r in range(2)}
     total = got[0][0] + got[1][0]
     assert torch.equal(got[0][1], got[1][1])
     torch.testing.assert_close(got[0][1], total)

@@ -55,13 +55,13 @@ __global__ void __launch_bounds__(1024)
 // Adam (coupled L2), torch.optim.Adam single-tensor arithmetic, over one flat buffer
 // ---------------------------------------------------------------------------------------------
 struct AdamHyper {
-  float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale, pad;
+  float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale, one_minus_beta1, one_minus_beta2;
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
   g = g * h.grad_scale + h.wd * p;
-  m = m + (g - m) * (1.0f - h.beta1);
-  v = v * h.beta2 + (1.0f - h.beta2) * g * g;
+  m = m + (g - m) * h.one_minus_beta1;            // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * h.beta2 + h.one_minus_beta2 * g * g;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
   p = p - h.step_size * (m / denom);
 }
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256)
   if (hyper_dev != nullptr) {
     h.step_size = hyper_dev[0]; h.bc2_sqrt = hyper_dev[1]; h.beta1 = hyper_dev[2]; h.beta2 = hyper_dev[3];
     h.eps = hyper_dev[4]; h.wd = hyper_dev[5]; h.grad_scale = hyper_dev[6];
+    h.one_minus_beta1 = hyper_dev[7]; h.one_minus_beta2 = hyper_dev[8];
   }
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -122,6 +123,7 @@ int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow
   if (hyper_host) {
     h.step_size = hyper_host[0]; h.bc2_sqrt = hyper_host[1]; h.beta1 = hyper_host[2]; h.beta2 = hyper_host[3];
     h.eps = hyper_host[4]; h.wd = hyper_host[5]; h.grad_scale = hyper_host[6];
+    h.one_minus_beta1 = hyper_host[7]; h.one_minus_beta2 = hyper_host[8];
   }
   int blocks = (int)ceil_div64(n / 4 + 1, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;

@@ -85,9 +85,9 @@ class TrainEngine:
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.dlogits = torch.zeros((self.B, model.num_classes), dtype=torch.float32, device=self.dev)
         self.logits: Optional[torch.Tensor] = None
-        self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=self.dev)
         # ring of pinned slots: the async H2D of step k must not see the host writing step k+1's values
-        self.hyper_host = torch.zeros((1024, 8), dtype=torch.float32).pin_memory()
+        self.hyper_host = torch.zeros((1024, 16), dtype=torch.float32).pin_memory()
         self.step_count = 0
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -167,7 +167,7 @@ class TrainEngine:
         self.step_count += 1
         h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
-        slot[:7] = torch.tensor(h, dtype=torch.float32)
+        slot[:9] = torch.tensor(h, dtype=torch.float32)
         self.hyper_dev.copy_(slot, non_blocking=True)
         if not self.use_graph:
             n0 = ops.launch_count()

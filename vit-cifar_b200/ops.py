@@ -178,14 +178,14 @@ def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1
           "ls_ce_fwd_bwd")
 
 
-_HyperArr = C.c_float * 8
+_HyperArr = C.c_float * 16
 
 
 def adam(p, g, m, v, shadow, hyper_host=None, hyper_dev=None) -> None:
-    """hyper_host: sequence of 7 floats (see vitb200.h) or None; hyper_dev: 8-float CUDA tensor or None."""
+    """hyper_host: sequence of 9 floats (optim.adam_hyper) or None; hyper_dev: 16-float CUDA tensor or None."""
     n = p.numel()
     hh = None
     if hyper_host is not None:
-        hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (8 - len(hyper_host))))
+        hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (16 - len(hyper_host))))
     check(_lib.load().vitb_adam_multi(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n,
                                       C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()), "adam_multi")

@@ -11,10 +11,10 @@ from . import ops
 
 
 def adam_hyper(step: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, grad_scale: float = 1.0):
-    """The 7 scalars of vitb_adam_multi, computed in double like torch.optim.Adam's single-tensor path."""
+    """The 9 scalars of vitb_adam_multi, computed in double like torch.optim.Adam's single-tensor path."""
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    return [lr / bc1, math.sqrt(bc2), beta1, beta2, eps, weight_decay, grad_scale]
+    return [lr / bc1, math.sqrt(bc2), beta1, beta2, eps, weight_decay, grad_scale, 1.0 - beta1, 1.0 - beta2]
 
 
 class FusedAdam:
