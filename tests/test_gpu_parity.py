@@ -113,7 +113,9 @@ def test_fp32_engine_matches_golden_after_3_adam_steps(vb, golden_dir, name):
     assert losses == pytest.approx(g["losses"], rel=1e-4)
     sd = model.state_dict()
     for k, ref in g["params3"].items():
-        assert rel(sd[k], ref) < 1e-5, k
+        # Wk.bias: its gradient is pure rounding noise (analytically 0), and Adam turns noise of any size into
+        # updates of ~lr * g/(|g| + eps), so the reference's own 3-step value is only reproducible to ~1e-6 absolute
+        assert rel(sd[k], ref) < (1e-5 if "Wk.bias" not in k else 1e-4), k
 
 
 @pytest.mark.parametrize("name", ["full65", "full17c100"])
