@@ -78,7 +78,8 @@ def test_layernorm_strided_rows(ops, dtype):
 
 
 # ---------------------------------------------------------------------------------------------
-GEMM_SHAPES = [(260, 128, 128), (260, 384, 128), (1040, 1152, 384), (520, 384, 384), (130, 256, 128), (128, 128, 64), (4, 10, 128)]
+GEMM_SHAPES = [(260, 128, 128), (260, 384, 128), (1040, 1152, 384), (520, 384, 384), (130, 256, 128), (128, 128, 64), (100, 128, 128),
+               (33, 256, 64), (20000, 384, 384), (4, 10, 128)]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -124,7 +125,7 @@ def test_gemm_dgrad(ops, dtype, M, N, K, with_z):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("M,N,K", GEMM_SHAPES[:-1] + [(8320, 384, 384)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES[:-1] + [(8320, 384, 384), (66560, 1152, 384)])
 def test_gemm_wgrad_dbias(ops, dtype, M, N, K):
     dy = rnd((M, N), dtype, 1); x = rnd((M, K), dtype, 2)
     dw = torch.empty((N, K), dtype=torch.float32, device="cuda"); db = torch.empty((N,), dtype=torch.float32, device="cuda")

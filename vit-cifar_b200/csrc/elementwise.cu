@@ -183,15 +183,26 @@ __global__ void __launch_bounds__(256)
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int c = (blockIdx.y * TX + tx) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = blockIdx.x * TY + ty; r < rows; r += gridDim.x * TY) {
+  const int step = gridDim.x * TY;
+  int r = blockIdx.x * TY + ty;
+  for (; r + step < rows; r += 2 * step) {  // two independent rows in flight per thread
+    const size_t off0 = (size_t)r * cols + c, off1 = (size_t)(r + step) * cols + c;
+    float4 v0 = ld4(a + off0), v1 = ld4(a + off1);
+    if (GELU_BWD) {
+      const float4 z0 = ld4(z + off0), z1 = ld4(z + off1);
+      v0.x *= gelu_grad_f(z0.x); v0.y *= gelu_grad_f(z0.y); v0.z *= gelu_grad_f(z0.z); v0.w *= gelu_grad_f(z0.w);
+      v1.x *= gelu_grad_f(z1.x); v1.y *= gelu_grad_f(z1.y); v1.z *= gelu_grad_f(z1.z); v1.w *= gelu_grad_f(z1.w);
+      st4(out + off0, v0);
+      st4(out + off1, v1);
+    }
+    acc.x += v0.x + v1.x; acc.y += v0.y + v1.y; acc.z += v0.z + v1.z; acc.w += v0.w + v1.w;
+  }
+  for (; r < rows; r += step) {
     const size_t off = (size_t)r * cols + c;
     float4 v = ld4(a + off);
     if (GELU_BWD) {
       const float4 zz = ld4(z + off);
-      v.x *= gelu_grad_f(zz.x);
-      v.y *= gelu_grad_f(zz.y);
-      v.z *= gelu_grad_f(zz.z);
-      v.w *= gelu_grad_f(zz.w);
+      v.x *= gelu_grad_f(zz.x); v.y *= gelu_grad_f(zz.y); v.z *= gelu_grad_f(zz.z); v.w *= gelu_grad_f(zz.w);
       st4(out + off, v);
     }
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -246,7 +257,7 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
     rows_colsum_kernel<T, false><<<grid, block, 0, st>>>((const T*)a, nullptr, nullptr, wsf, rows, cols);
   VITB_LAUNCH_OK();
   if (colsum != nullptr) {
-    partials_finalize_kernel<0><<<dim3(ceil_div(cols, 256), 1), 256, 0, st>>>(wsf, g.gx, cols, colsum, nullptr, nullptr);
+    partials_finalize_kernel<0><<<finalize_grid(cols, 1), finalize_block(), 0, st>>>(wsf, g.gx, cols, colsum, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   return 0;
@@ -373,7 +384,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
                              (const float*)dy, (const float*)x, xs, gamma, mean, rstd, (const float*)dres, (float*)dx, dxs, (float*)ws, want, rows)));
   }
   VITB_LAUNCH_OK();
-  partials_finalize_kernel<0><<<dim3(ceil_div(H, 256), 3), 256, 0, st>>>((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
+  partials_finalize_kernel<0><<<finalize_grid(H, 3), finalize_block(), 0, st>>>((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
   VITB_LAUNCH_OK();
   return 0;
 }

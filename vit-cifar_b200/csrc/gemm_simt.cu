@@ -118,13 +118,28 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g) {
     __syncthreads();
   }
   const size_t raw_off = (size_t)blockIdx.z * g.M * g.e.ldc;
+  const int col0 = n0 + tx * 4;
+  // fast path: plain activation output of 4 consecutive, aligned columns -> one 8/16-byte store per row
+  const bool vec = (g.e.mode == EPI_FWD) && !g.e.preact && !g.e.gelu && !g.e.residual && !g.e.out_f32 && (col0 + 3 < g.N) && (g.e.ldc % 4 == 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
     if (row >= g.M) continue;
+    if (vec) {
+      int prow = row;
+      if (g.e.rm_group > 0) prow = (row / g.e.rm_group) * g.e.rm_stride + g.e.rm_offset + row % g.e.rm_group;
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (g.e.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(g.e.bias + col0)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+      if (g.e.pos) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(g.e.pos + (size_t)(prow % g.e.rm_stride) * g.e.ldc + col0));
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      st4((TO*)g.e.out + (size_t)prow * g.e.ldc + col0, v);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tx * 4 + j;
+      const int col = col0 + j;
       if (col < g.N) epi_apply<TO>(g.e, row, col, acc[i][j], raw_off);
     }
   }
@@ -200,18 +215,29 @@ __global__ void patch_bias_cls_kernel(const float* __restrict__ dpos, float* __r
   if (has_cls && dcls) dcls[c] = dpos[c];
 }
 
-// dpos[j] = sum_b dout[b][j], j over T*H (batch-strided column sum, fixed order over b per split)
+// part[s][j] = sum over the s-th slice of the batch of dout[b][j], j over T*H (fixed order; finalize sums the slices)
 template <typename T>
-__global__ void batch_sum_kernel(const T* __restrict__ x, float* __restrict__ out, int B, int64_t n) {
+__global__ void batch_sum_kernel(const T* __restrict__ x, float* __restrict__ part, int B, int64_t n) {
   const int64_t j4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j4 >= n) return;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int b = 0; b < B; ++b) {
-    const float4 v = ld4(x + (int64_t)b * n + j4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  int b = b0;
+  for (; b + 2 <= b1; b += 2) {
+    const float4 v0 = ld4(x + (int64_t)b * n + j4);
+    const float4 v1 = ld4(x + (int64_t)(b + 1) * n + j4);
+    s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+    s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
   }
-  *reinterpret_cast<float4*>(out + j4) = s;
+  if (b < b1) {
+    const float4 v0 = ld4(x + (int64_t)b * n + j4);
+    s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+  }
+  *reinterpret_cast<float4*>(part + (int64_t)blockIdx.y * n + j4) = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
 }
+
+static int batch_sum_slices(int B) { return B >= 256 ? 16 : (B >= 32 ? 4 : 1); }
 
 }  // namespace vitb
 
@@ -248,7 +274,8 @@ size_t vitb_patch_embed_bwd_ws_bytes(int B, int S, int P, int H, int has_cls) {
   const int ps = S / P, K = ps * ps * 3;
   const int tiles = ceil_div(H, SB) * ceil_div(K, SB);
   const int splits = simt_pick_splits(tiles, B * P * P);
-  return align_up((size_t)splits * H * K * sizeof(float), 256);
+  const int Tn = P * P + (has_cls ? 1 : 0);
+  return align_up((size_t)splits * H * K * sizeof(float), 256) + align_up((size_t)batch_sum_slices(B) * Tn * H * sizeof(float), 256);
 }
 
 int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* dbias, float* dcls, float* dpos,
@@ -261,10 +288,17 @@ int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* d
   // 1) dpos = sum_b dout[b]; dcls, dbias from it
   {
     const int64_t n = (int64_t)Tn * H;
-    const int blocks = (int)ceil_div64(n / 4, 128);
-    if (dt == VITB_BF16) batch_sum_kernel<bf16><<<blocks, 128, 0, st>>>((const bf16*)dout, dpos, B, n);
-    else batch_sum_kernel<float><<<blocks, 128, 0, st>>>((const float*)dout, dpos, B, n);
+    const int slices = batch_sum_slices(B);
+    const int tiles0 = ceil_div(H, SB) * ceil_div(K, SB);
+    float* bpart = slices > 1 ? (float*)((char*)ws + align_up((size_t)simt_pick_splits(tiles0, B * PP) * H * K * sizeof(float), 256)) : dpos;
+    const dim3 grid((unsigned)ceil_div64(n / 4, 128), slices);
+    if (dt == VITB_BF16) batch_sum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)dout, bpart, B, n);
+    else batch_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)dout, bpart, B, n);
     VITB_LAUNCH_OK();
+    if (slices > 1) {
+      partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(bpart, slices, n, dpos, nullptr, nullptr);
+      VITB_LAUNCH_OK();
+    }
     patch_bias_cls_kernel<<<ceil_div(H, 128), 128, 0, st>>>(dpos, dbias, dcls, Tn, H, has_cls ? 1 : 0);
     VITB_LAUNCH_OK();
   }
@@ -282,7 +316,7 @@ int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* d
   if (rc) return rc;
   if (splits > 1) {
     const int64_t n = (int64_t)H * K;
-    partials_finalize_kernel<0><<<dim3((unsigned)ceil_div64(n, 256), 1), 256, 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+    partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   return 0;

@@ -3,8 +3,12 @@
 // bias / GELU / residual / pre-activation save / GELU-backward, or fp32 split-K partials.
 //
 // One persistent kernel, three roles (warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
-// warps 2-5: epilogue), two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of
-// tile i+1.  Operand layouts are chosen per GEMM so no tensor is ever transposed in memory:
+// warps 2-9: epilogue), two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  The epilogue never touches global memory with per-thread row accesses: every epilogue
+// warp owns a 32-row x 64-column slab, stages bf16 results in 128B-swizzled shared memory and moves
+// whole slabs with TMA (store for C / pre-activation, load for the residual / GELU-backward operand).
+// wgrad additionally computes the bias gradient with one extra N=16 MMA per k-step against an
+// all-ones operand (column sums of dY for free on the tensor pipe).  Operand layouts are chosen per GEMM so no tensor is ever transposed in memory:
 //   fwd   C[M,N]  = A[M,K]   · W[N,K]ᵀ : A K-major,  B K-major
 //   dgrad dX[M,K] = dY[M,N]  · W[N,K]  : A K-major,  B MN-major (reduction runs over W's rows)
 //   wgrad dW[N,K] = dY[M,N]ᵀ · X[M,K]  : A MN-major, B MN-major (reduction runs over the rows of both)
@@ -18,13 +22,18 @@ namespace vitb {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 along the contiguous dimension
 constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
-constexpr int kTcThreads = 192;  // 6 warps
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16, 128B swizzle
 
 struct TcArgs {
   int M;             // valid output rows (C rows; for wgrad: N_out)
   int N;             // output columns (multiple of BN)
   int num_m_blocks, num_n_blocks, splits;
   int kblocks_total, kblocks_per_split;
+  int has_in;        // tma_in valid: residual (EPI_FWD) or z for gelu' (EPI_DGRAD)
+  int has_pre;       // tma_pre valid: store the pre-activation
+  float* dbias_part; // wgrad: [splits][M] fp32 partial column sums of dY (or null)
   EpiParams e;
 };
 
@@ -68,6 +77,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -93,6 +111,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1)
@@ -106,9 +133,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// two accumulator stages of BN columns + two 16-column bias-gradient accumulators (wgrad)
 template <int BN>
 constexpr uint32_t tmem_cols() {
-  return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  return 2 * BN + 32 <= 64 ? 64 : 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
 }
 
 template <int BN, int STAGES>
@@ -116,35 +144,35 @@ struct TcSmem {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBarOff = STAGES * kStageBytes;
-  static constexpr uint32_t kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t kEpiOff = STAGES * kStageBytes;                 // 8 warps x {out, pre, in} slabs
+  static constexpr uint32_t kEpiBytes = kEpiWarps * 3 * kSlabBytes;          // (the all-ones wgrad operand overlays it)
+  static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
+  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + kEpiWarps;
+  static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr uint32_t kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
 
 // ---------------------------------------------------------------------------------------------
-// epilogue helpers: one thread = one output row, 32 consecutive columns per call
+// epilogue helpers: one thread = one row of a 32 x 64 slab (128 B per row, 128B swizzle: 16-byte chunk j of
+// row r lives at chunk position j ^ (r & 7), the layout TMA reads/writes with CU_TENSOR_MAP_SWIZZLE_128B;
+// a quarter-warp's 16-byte accesses then fall in 8 distinct bank groups -> conflict-free)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_row32_bf16(const bf16* p, float (&f)[32]) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ void slab_store_row64(uint32_t slab, int r, const float (&f)[64]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = q[i];
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    f[i * 8 + 0] = a.x; f[i * 8 + 1] = a.y; f[i * 8 + 2] = b.x; f[i * 8 + 3] = b.y;
-    f[i * 8 + 4] = c.x; f[i * 8 + 5] = c.y; f[i * 8 + 6] = d.x; f[i * 8 + 7] = d.y;
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = slab + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])),
+                 "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])), "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])),
+                 "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
+                 : "memory");
   }
 }
-__device__ __forceinline__ void store_row32_bf16(bf16* p, const float (&f)[32]) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
-    u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
-    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
-    u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
-    q[i] = u;
-  }
+__device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, float (&f)[8]) {
+  const uint32_t addr = slab + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+  uint32_t a, b, c, d;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+  float2 x = unpack_bf16x2(a), y = unpack_bf16x2(b), z = unpack_bf16x2(c), w = unpack_bf16x2(d);
+  f[0] = x.x; f[1] = x.y; f[2] = y.x; f[3] = y.y; f[4] = z.x; f[5] = z.y; f[6] = w.x; f[7] = w.y;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,8 +180,11 @@ __device__ __forceinline__ void store_row32_bf16(bf16* p, const float (&f)[32]) 
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcArgs p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
+                   const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
   using S = TcSmem<BN, STAGES>;
+  static_assert(BN == 128, "epilogue slabs assume two 64-column halves");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -163,30 +194,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   auto a_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes; };
   auto b_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes + S::kABytes; };
+  const uint32_t epi_base = smem_base + S::kEpiOff;
   const uint32_t bar_base = smem_base + S::kBarOff;
   auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (uint32_t)(STAGES + s) * 8; };
   auto tfull_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + a) * 8; };
   auto tempty_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + 2 + a) * 8; };
-  const uint32_t tmem_slot = bar_base + (2 * STAGES + 4) * 8;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOff + (2 * STAGES + 4) * 8);
+  auto in_bar = [&](int w) { return bar_base + (uint32_t)(2 * STAGES + 4 + w) * 8; };
+  const uint32_t tmem_slot = bar_base + S::kNumBars * 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOff + S::kNumBars * 8);
+
+  const bool want_dbias = (p.e.mode == EPI_RAW_F32) && (p.dbias_part != nullptr);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+    if (p.e.mode != EPI_RAW_F32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_out) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), kEpiWarps * 32);
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(in_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols<BN>()) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (want_dbias && warp >= 2) {
+    // all-ones bf16 operand (16 rows x 128 B, any layout reads ones); overlays the unused epilogue slabs
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + S::kEpiOff);
+    for (int i = threadIdx.x - 64; i < 2048 / 4; i += kEpiWarps * 32) ones[i] = 0x3F803F80u;
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -234,17 +277,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // bias-gradient MMA: same A, B = all-ones K-major tile, N = 16
+      const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
+                                  ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t ones_desc = make_smem_desc(epi_base, 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / tiles_per_split;
+        const int rem = tile - split * tiles_per_split;
+        const bool do_bias = want_dbias && (rem % p.num_n_blocks) == 0;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_bias = tmem_base + (uint32_t)(2 * BN + acc * 16);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -256,7 +306,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                         : make_smem_desc(a_stage(stage) + kk * (UK * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc(b_stage(stage) + kk * (UK * 128), BK * 128, 1024)
                                         : make_smem_desc(b_stage(stage) + kk * (UK * 2), 16, 1024);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+            if (do_bias) tc_mma_bf16(d_bias, adesc, ones_desc, idesc_ones, accum);
           }
           tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -267,76 +319,112 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
     }
   } else {
-    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
+    const int ew = warp - 2;
     const int quarter = warp & 3;
+    const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
+    const uint32_t slab_out = epi_base + (uint32_t)(ew * 3 + 0) * kSlabBytes;
+    const uint32_t slab_pre = epi_base + (uint32_t)(ew * 3 + 1) * kSlabBytes;
+    const uint32_t slab_in = epi_base + (uint32_t)(ew * 3 + 2) * kSlabBytes;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, in_phase = 0;
     const EpiParams& e = p.e;
+    bool stores_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int split = tile / tiles_per_split;
       const int rem = tile - split * tiles_per_split;
+      const int nblk = rem % p.num_n_blocks;
       const int m0 = (rem / p.num_n_blocks) * BM;
-      const int n0 = (rem % p.num_n_blocks) * BN;
+      const int n0 = nblk * BN + half * 64;
       const int grow = m0 + row_in_tile;
-      const bool valid = grow < p.M;
+      if (p.has_in && lane == 0) {  // fetch this warp's residual / z slab while the MMAs of the tile run
+        mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
+        tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        tc_ld32(taddr + (uint32_t)c0, raw);
-        tc_wait_ld();
-        if (c0 + 32 >= BN) {  // accumulator fully drained into registers: hand the stage back
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
-        if (!valid) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        const int col = n0 + c0;
-        if (e.mode == EPI_RAW_F32) {
-          float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + col;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          continue;
-        }
-        const size_t off = (size_t)grow * e.ldc + col;
-        if (e.mode == EPI_FWD) {
-          if (e.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (e.preact != nullptr) store_row32_bf16((bf16*)e.preact + off, v);
-          if (e.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
-          }
-          if (e.residual != nullptr) {
-            float r[32];
-            load_row32_bf16((const bf16*)e.residual + off, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
-          }
-        } else {  // EPI_DGRAD
-          if (e.aux != nullptr) {
-            float z[32];
-            load_row32_bf16((const bf16*)e.aux + off, z);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_f(z[j]);
-          }
-        }
-        store_row32_bf16((bf16*)e.out + off, v);
-      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+      uint32_t raw0[32], raw1[32];
+      tc_ld32(taddr, raw0);
+      tc_ld32(taddr + 32u, raw1);
+      uint32_t rawb[16];
+      const bool do_bias = want_dbias && nblk == 0 && half == 0;
+      if (do_bias) tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * BN + acc * 16), rawb);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+
+      float v[64];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(raw0[j]);
+        v[32 + j] = __uint_as_float(raw1[j]);
+      }
+      if (e.mode == EPI_RAW_F32) {
+        if (grow < p.M) {
+          float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + n0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (do_bias) p.dbias_part[(size_t)split * p.M + grow] = __uint_as_float(rawb[0]);
+        }
+        continue;
+      }
+      if (stores_pending) {  // the previous tile's TMA stores must have finished reading the slabs
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      if (e.mode == EPI_FWD) {
+        if (e.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.has_pre) slab_store_row64(slab_pre, lane, v);
+        if (e.gelu) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = gelu_f(v[j]);
+        }
+        if (p.has_in) {
+          mbar_wait(in_bar(ew), in_phase);
+          in_phase ^= 1u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float r[8];
+            slab_load_chunk8(slab_in, lane, j, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] += r[i];
+          }
+        }
+      } else {  // EPI_DGRAD
+        if (p.has_in) {
+          mbar_wait(in_bar(ew), in_phase);
+          in_phase ^= 1u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float z[8];
+            slab_load_chunk8(slab_in, lane, j, z);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_f(z[i]);
+          }
+        }
+      }
+      slab_store_row64(slab_out, lane, v);
+      fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tma_out, slab_out, n0, m0 + quarter * 32);  // rows >= M are clipped by the tensor map
+        if (p.has_pre) tma_store_2d(&tma_pre, slab_pre, n0, m0 + quarter * 32);
+        tma_store_commit();
+      }
+      stores_pending = true;
     }
+    if (stores_pending && lane == 0) tma_store_wait_all();
   }
 
   // teardown: everyone done with TMEM before the owning warp frees it
@@ -381,8 +469,12 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
+struct TcMaps {
+  CUtensorMap a, b, out, pre, in;
+};
+
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cudaStream_t st) {
+static int launch_tc(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
   static bool configured = false;  // per instantiation
@@ -392,15 +484,16 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs&
   }
   const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, kTcThreads, S::kDynBytes, st>>>(ma, mb, args);
+  kern<<<grid, kTcThreads, S::kDynBytes, st>>>(m.a, m.b, m.out, m.pre, m.in, args);
   VITB_LAUNCH_OK();
   return 0;
 }
 
 constexpr int kBN = 128;
-constexpr int kStages = 6;
+constexpr int kStages = 4;
+static_assert(TcSmem<kBN, kStages>::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
 
-static bool tc_shape_ok(int N, int K) { return N % kBN == 0 && K % BK == 0; }
+static bool tc_shape_ok(int M, int N, int K) { return M >= 32 && N % kBN == 0 && K % BK == 0; }
 
 static int check_dt(int dt) {
   VITB_REQUIRE(dt == VITB_F32 || dt == VITB_BF16, "dt must be VITB_F32 or VITB_BF16 (got %d)", dt);
@@ -422,14 +515,19 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
   EpiParams e = {};
   e.mode = EPI_FWD; e.gelu = (flags & VITB_GEMM_GELU) ? 1 : 0; e.out_f32 = (flags & VITB_GEMM_OUT_F32) ? 1 : 0;
   e.bias = bias; e.residual = residual; e.out = c; e.preact = preact; e.ldc = N;
-  if (dt == VITB_BF16 && tc_shape_ok(N, K) && !e.out_f32) {
-    CUtensorMap ma, mb;
-    if (make_map(&ma, a, K, M, K, BM)) return -1;
-    if (make_map(&mb, w, K, N, K, kBN)) return -1;
+  if (dt == VITB_BF16 && tc_shape_ok(M, N, K) && !e.out_f32) {
+    TcMaps m;
+    if (make_map(&m.a, a, K, M, K, BM)) return -1;
+    if (make_map(&m.b, w, K, N, K, kBN)) return -1;
+    if (make_map(&m.out, c, N, M, N, 32)) return -1;
+    m.pre = m.out; m.in = m.out;
+    if (preact && make_map(&m.pre, preact, N, M, N, 32)) return -1;
+    if (residual && make_map(&m.in, residual, N, M, N, 32)) return -1;
     TcArgs t = {};
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
     t.kblocks_total = K / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
-    return launch_tc<kBN, false, false, kStages>(ma, mb, t, st);
+    t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
+    return launch_tc<kBN, false, false, kStages>(m, t, st);
   }
   SimtGemmArgs g = {};
   g.a = a; g.b = w; g.M = M; g.N = N; g.K = K;
@@ -446,14 +544,18 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
   EpiParams e = {};
   e.mode = EPI_DGRAD; e.out = dx; e.aux = z; e.ldc = K;
   // GEMM view: C[M, K] = dY[M, N] (K-major, reduction N) x W[N, K] (MN-major: reduction over rows)
-  if (dt == VITB_BF16 && !dy_f32 && K % kBN == 0 && N % BK == 0) {
-    CUtensorMap ma, mb;
-    if (make_map(&ma, dy, N, M, N, BM)) return -1;
-    if (make_map(&mb, w, K, N, K, 64)) return -1;  // box: 64 output columns x 64 reduction rows
+  if (dt == VITB_BF16 && !dy_f32 && tc_shape_ok(M, K, N)) {
+    TcMaps m;
+    if (make_map(&m.a, dy, N, M, N, BM)) return -1;
+    if (make_map(&m.b, w, K, N, K, 64)) return -1;  // box: 64 output columns x 64 reduction rows
+    if (make_map(&m.out, dx, K, M, K, 32)) return -1;
+    m.pre = m.out; m.in = m.out;
+    if (z && make_map(&m.in, z, K, M, K, 32)) return -1;
     TcArgs t = {};
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
     t.kblocks_total = N / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
-    return launch_tc<kBN, false, true, kStages>(ma, mb, t, st);
+    t.has_in = z != nullptr;
+    return launch_tc<kBN, false, true, kStages>(m, t, st);
   }
   SimtGemmArgs g = {};
   g.a = dy; g.b = w; g.M = M; g.N = K; g.K = N;
@@ -480,6 +582,7 @@ static bool wgrad_tc_ok(int N, int K, int flags, int dt) {
 
 static int wgrad_simt_splits(int M, int N, int K) { return simt_pick_splits(ceil_div(N, 64) * ceil_div(K, 64), M); }
 
+// workspace: [dW partials: splits*N*K][dbias partials: splits*N][colsum scratch (SIMT path)]
 size_t vitb_gemm_wgrad_ws_bytes(int M, int N, int K, int dt) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int splits;
@@ -490,7 +593,8 @@ size_t vitb_gemm_wgrad_ws_bytes(int M, int N, int K, int dt) {
     splits = wgrad_simt_splits(M, N, K);
   }
   const size_t part = align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
-  return part + align_up(vitb_colsum_ws_bytes(M, N), 256) + 256;
+  const size_t bpart = align_up((size_t)splits * N * sizeof(float), 256);
+  return part + bpart + align_up(vitb_colsum_ws_bytes(M, N), 256) + 256;
 }
 
 int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias, void* ws, size_t ws_bytes, int M, int N, int K,
@@ -507,18 +611,34 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   if (wgrad_tc_ok(N, K, flags, dt)) {
     int kb_total, kb_per;
     wgrad_tc_plan(M, N, K, &splits, &kb_total, &kb_per);
+    const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
+    float* bpart = (float*)((char*)ws + part_bytes);
     // GEMM view: C[N, K] = dYᵀ (A MN-major: [M rows][N contiguous]) x X (B MN-major: [M rows][K contiguous]), reduction M
-    CUtensorMap ma, mb;
-    if (make_map(&ma, dy, N, M, N, 64)) return -1;
-    if (make_map(&mb, x, K, M, K, 64)) return -1;
+    TcMaps m;
+    if (make_map(&m.a, dy, N, M, N, 64)) return -1;
+    if (make_map(&m.b, x, K, M, K, 64)) return -1;
+    m.out = m.a; m.pre = m.a; m.in = m.a;  // unused in RAW mode
     TcArgs t = {};
     t.M = N; t.N = K; t.num_m_blocks = N / BM; t.num_n_blocks = K / kBN; t.splits = splits;
     t.kblocks_total = kb_total; t.kblocks_per_split = kb_per;
     t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = splits > 1 ? part : dw;
-    int rc = launch_tc<kBN, true, true, kStages>(ma, mb, t, st);
+    t.dbias_part = dbias ? (splits > 1 ? bpart : dbias) : nullptr;  // bias gradient rides on the tensor pipe (ones-operand MMA)
+    int rc = launch_tc<kBN, true, true, kStages>(m, t, st);
     if (rc) return rc;
-  } else {
-    splits = wgrad_simt_splits(M, N, K);
+    if (splits > 1) {
+      const int64_t n = (int64_t)N * K;
+      partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+      VITB_LAUNCH_OK();
+      if (dbias) {
+        partials_finalize_kernel<0><<<finalize_grid(N, 1), finalize_block(), 0, st>>>(bpart, splits, N, dbias, nullptr, nullptr);
+        VITB_LAUNCH_OK();
+      }
+    }
+    return 0;
+  }
+  splits = wgrad_simt_splits(M, N, K);
+  const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
+  {
     SimtGemmArgs g = {};
     g.a = dy; g.b = x; g.M = N; g.N = K; g.K = M;
     g.a_sm = 1; g.a_sk = N; g.b_sk = K; g.b_sn = 1;
@@ -528,12 +648,12 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   }
   if (splits > 1) {
     const int64_t n = (int64_t)N * K;
-    partials_finalize_kernel<0><<<dim3((unsigned)ceil_div64(n, 256), 1), 256, 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+    partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   if (dbias != nullptr) {
     if (N % 128 == 0) {
-      char* cws = (char*)ws + align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
+      char* cws = (char*)ws + part_bytes + align_up((size_t)splits * N * sizeof(float), 256);
       return vitb_colsum(dy, dbias, cws, vitb_colsum_ws_bytes(M, N), M, N, dy_dt, stream);
     }
     return colsum_small_launch(dy, dbias, M, N, N, dy_dt, st);
