@@ -105,10 +105,11 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
  * scale = 1/sqrt(features) (layers.py:79,97).  d in {32,64}, T <= 128. */
 int vitb_attn_fwd(const void* qkv, void* o, float* lse, float* attn_map, int B, int T, int heads,
                   int d, float scale, int dt, void* stream);
-/* dqkv act (B,T,3H) from do act (B,T,H): dP = dO·Vᵀ; dS = P∘(dP − rowsum(P∘dP)); dQ = dS·K·scale;
- * dK = dSᵀ·Q·scale; dV = Pᵀ·dO (autograd of layers.py:96-101). P is recomputed from lse. */
-int vitb_attn_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int T,
-                  int heads, int d, float scale, int dt, void* stream);
+/* dqkv act (B,T,3H) from d_o act (B,T,H): dP = dO·Vᵀ; dS = P∘(dP − D), D_i = rowsum(P∘dP)_i = sum_d dO_id·O_id;
+ * dQ = dS·K·scale; dK = dSᵀ·Q·scale; dV = Pᵀ·dO (autograd of layers.py:96-101).  P is recomputed from lse;
+ * o is the forward output (B,T,H) saved by vitb_attn_fwd (used for D). */
+int vitb_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B,
+                  int T, int heads, int d, float scale, int dt, void* stream);
 
 /* ---- GELU backward + column sums: dz = dy * gelu'(z); colsum fp32 (cols) = sum over rows of dz
  * (bias gradient of the Linear before the GELU, layers.py:36-37) if colsum != NULL. ---- */

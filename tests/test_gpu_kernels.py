@@ -182,7 +182,7 @@ def test_attention_fwd_bwd(ops, dtype, B, T, heads, d):
     ops.attn_fwd(cu(qkv), o2, lse2, None, B, T, heads, d, scale)
     assert torch.equal(o, o2)
     dqkv = torch.empty((B, T, 3 * H), dtype=dtype, device="cuda")
-    ops.attn_bwd(cu(qkv), cu(do), lse, dqkv, B, T, heads, d, scale)
+    ops.attn_bwd(cu(qkv), o, cu(do), lse, dqkv, B, T, heads, d, scale)
     assert rel(dqkv, dqkv_ref) < tol(dtype)
 
 

@@ -44,7 +44,7 @@ SIGNATURES = {
     "vitb_gemm_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "vitb_gemm_wgrad_dbias": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _p]),
     "vitb_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
-    "vitb_attn_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "vitb_attn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "vitb_colsum_ws_bytes": (_sz, [_i, _i]),
     "vitb_gelu_bwd_colsum": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
     "vitb_colsum": (_i, [_p, _p, _p, _sz, _i, _i, _i, _p]),

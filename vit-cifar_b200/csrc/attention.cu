@@ -21,6 +21,10 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+__device__ __forceinline__ void stsm_x4(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -257,116 +261,140 @@ __device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS,
   }
 }
 
+// One CTA per (image, head); low register count (scores are processed in 16-key chunks) so that 4 CTAs share an SM.
+//   D_i = sum_d dO_id * O_id  (= rowsum(P ∘ dP), flash-attention identity) from the saved forward output, so a chunk's
+//   dS can be formed without holding the whole score row.
 template <int D, int NT16>
-__global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 4 : (NT16 <= 5 ? 2 : 1)))
-    attn_bwd_bf16_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, const float* __restrict__ lse,
-                         bf16* __restrict__ dqkv, int n_items, int T, int heads, float scale) {
-  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8, TILE = TP * LD;
+__global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1)) : (NT16 <= 2 ? 4 : (NT16 <= 5 ? 2 : 1))))
+    attn_bwd_bf16_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                         const float* __restrict__ lse, bf16* __restrict__ dqkv, int T, int heads, float scale) {
+  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8, TILE = TP * LD, CH = D / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  bf16* sbuf = reinterpret_cast<bf16*>(smem_attn);  // [2][4][TILE]  (Q, K, V, dO)
-  bf16* sP = sbuf + 8 * TILE;                        // [TP][LP]
-  bf16* sdS = sP + TP * LP;                          // [TP][LP]
-  float* sLse = reinterpret_cast<float*>(sdS + TP * LP);  // [2][TP]
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + TILE;
+  bf16* sV = sK + TILE;
+  bf16* sdO = sV + TILE;
+  bf16* sP = sdO + TILE;     // [TP][LP]
+  bf16* sdS = sP + TP * LP;  // [TP][LP]
+  float* sD = reinterpret_cast<float*>(sdS + TP * LP);  // [TP]
+  float* sL = sD + TP;                                   // [TP] lse * log2(e)
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int Hd = heads * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-  for (int i = 0; i < 8; ++i) zero_pad_rows<D, TP>(sbuf + i * TILE, T, tid, nthr);
-
-  auto issue = [&](int item, int buf) {
-    const int b = item / heads, h = item % heads;
-    const bf16* base = qkv + (int64_t)b * T * 3 * Hd + h * D;
-    bf16* dst = sbuf + buf * 4 * TILE;
-    load_head_tile_async<D, TP>(dst, base, 3 * Hd, T, tid, nthr);
-    load_head_tile_async<D, TP>(dst + TILE, base + Hd, 3 * Hd, T, tid, nthr);
-    load_head_tile_async<D, TP>(dst + 2 * TILE, base + 2 * Hd, 3 * Hd, T, tid, nthr);
-    load_head_tile_async<D, TP>(dst + 3 * TILE, d_o + (int64_t)b * T * Hd + h * D, Hd, T, tid, nthr);
-    for (int r = tid; r < T; r += nthr) cp_async4(sLse + buf * TP + r, lse + ((int64_t)b * heads + h) * T + r);
-  };
-
-  int item = blockIdx.x;
-  if (item < n_items) issue(item, 0);
+  const bf16* base = qkv + (int64_t)b * T * 3 * Hd + h * D;
+  const int64_t orow = (int64_t)b * T * Hd + h * D;
+  // all tile loads are asynchronous (one round trip); the other CTAs resident on the SM compute meanwhile
+  load_head_tile_async<D, TP>(sQ, base, 3 * Hd, T, tid, nthr);
+  load_head_tile_async<D, TP>(sK, base + Hd, 3 * Hd, T, tid, nthr);
+  load_head_tile_async<D, TP>(sV, base + 2 * Hd, 3 * Hd, T, tid, nthr);
+  load_head_tile_async<D, TP>(sdO, d_o + orow, Hd, T, tid, nthr);
   cp_async_commit();
+  zero_pad_rows<D, TP>(sQ, T, tid, nthr);
+  zero_pad_rows<D, TP>(sK, T, tid, nthr);
+  zero_pad_rows<D, TP>(sV, T, tid, nthr);
+  zero_pad_rows<D, TP>(sdO, T, tid, nthr);
+  for (int r = tid; r < TP; r += nthr) sL[r] = r < T ? lse[((int64_t)b * heads + h) * T + r] * kLog2e : 0.f;
+  // D_i = sum_d dO_id * O_id straight from global memory: CH threads per row, 8 elements each
+  for (int idx = tid; idx < TP * CH; idx += nthr) {
+    const int r = idx / CH, c = idx % CH;
+    float v = 0.f;
+    if (r < T) {
+      const uint4 a = *reinterpret_cast<const uint4*>(d_o + orow + (int64_t)r * Hd + c * 8);
+      const uint4 q = *reinterpret_cast<const uint4*>(o + orow + (int64_t)r * Hd + c * 8);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 q0 = unpack_bf16x2(q.x), q1 = unpack_bf16x2(q.y), q2 = unpack_bf16x2(q.z), q3 = unpack_bf16x2(q.w);
+      v = (a0.x * q0.x + a0.y * q0.y) + (a1.x * q1.x + a1.y * q1.y) + (a2.x * q2.x + a2.y * q2.y) + (a3.x * q3.x + a3.y * q3.y);
+    }
+#pragma unroll
+    for (int off = CH / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);  // CH (4 or 8) adjacent lanes share a row
+    if (c == 0) sD[r] = v;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
   const int g = lane >> 2, t = lane & 3;
   const int r0 = 16 * warp + g, r1 = r0 + 8;
   const float sl2 = scale * kLog2e;
-  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
-    const int cur = it & 1;
-    const int nxt = item + gridDim.x;
-    if (nxt < n_items) issue(nxt, cur ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    bf16* sQ = sbuf + cur * 4 * TILE;
-    bf16* sK = sQ + TILE;
-    bf16* sV = sK + TILE;
-    bf16* sdO = sV + TILE;
-    const int b = item / heads, h = item % heads;
-
-    float s[2 * NT16][4], dp[2 * NT16][4];
-    qk_tile<D, NT16>(s, sQ, sK, warp, lane);    // S = Q Kᵀ
-    qk_tile<D, NT16>(dp, sdO, sV, warp, lane);  // dP = dO Vᵀ
-    const float l0 = r0 < T ? sLse[cur * TP + r0] * kLog2e : 0.f;
-    const float l1 = r1 < T ? sLse[cur * TP + r1] * kLog2e : 0.f;
-    float d0 = 0.f, d1 = 0.f;
+  const float l0 = sL[r0], l1 = sL[r1];
+  const float d0 = sD[r0], d1 = sD[r1];
+  const bool rv0 = r0 < T, rv1 = r1 < T;
+  uint32_t aq[D / 16][4], ado[D / 16][4];
 #pragma unroll
-    for (int j = 0; j < 2 * NT16; ++j) {
+  for (int kk = 0; kk < D / 16; ++kk) {
+    ldsm_x4(aq[kk], sQ + (16 * warp + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+    ldsm_x4(ado[kk], sdO + (16 * warp + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+  }
+  float dq[D / 8][4];
+#pragma unroll
+  for (int jn = 0; jn < D / 8; ++jn) dq[jn][0] = dq[jn][1] = dq[jn][2] = dq[jn][3] = 0.f;
+#pragma unroll
+  for (int jc = 0; jc < NT16; ++jc) {  // 16 keys per chunk
+    float s[2][4], dp[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = 2 * jc + u;
+      s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f;
+      dp[u][0] = dp[u][1] = dp[u][2] = dp[u][3] = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < D / 32; ++k2) {
+        uint32_t bk[4], bv[4];
+        ldsm_x4(bk, sK + (8 * j + (lane & 7)) * LD + k2 * 32 + (lane >> 3) * 8);
+        ldsm_x4(bv, sV + (8 * j + (lane & 7)) * LD + k2 * 32 + (lane >> 3) * 8);
+        mma_bf16(s[u], aq[2 * k2], bk[0], bk[1]);
+        mma_bf16(s[u], aq[2 * k2 + 1], bk[2], bk[3]);
+        mma_bf16(dp[u], ado[2 * k2], bv[0], bv[1]);
+        mma_bf16(dp[u], ado[2 * k2 + 1], bv[2], bv[3]);
+      }
       const int c = 8 * j + 2 * t;
       const bool v0 = c < T, v1 = c + 1 < T;
-      s[j][0] = (v0 && r0 < T) ? exp2f(s[j][0] * sl2 - l0) : 0.f;
-      s[j][1] = (v1 && r0 < T) ? exp2f(s[j][1] * sl2 - l0) : 0.f;
-      s[j][2] = (v0 && r1 < T) ? exp2f(s[j][2] * sl2 - l1) : 0.f;
-      s[j][3] = (v1 && r1 < T) ? exp2f(s[j][3] * sl2 - l1) : 0.f;
-      d0 += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
-      d1 += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
+      s[u][0] = (v0 && rv0) ? exp2f(s[u][0] * sl2 - l0) : 0.f;
+      s[u][1] = (v1 && rv0) ? exp2f(s[u][1] * sl2 - l0) : 0.f;
+      s[u][2] = (v0 && rv1) ? exp2f(s[u][2] * sl2 - l1) : 0.f;
+      s[u][3] = (v1 && rv1) ? exp2f(s[u][3] * sl2 - l1) : 0.f;
+      // dS = P ∘ (dP − D) / sqrt(features)
+      dp[u][0] = s[u][0] * (dp[u][0] - d0) * scale;
+      dp[u][1] = s[u][1] * (dp[u][1] - d0) * scale;
+      dp[u][2] = s[u][2] * (dp[u][2] - d1) * scale;
+      dp[u][3] = s[u][3] * (dp[u][3] - d1) * scale;
     }
-    d0 = quad_sum(d0);
-    d1 = quad_sum(d1);
+    uint32_t pa[4], da[4];  // A-operand fragments of this 16 x 16 chunk (also exactly what stmatrix stores)
+    pa[0] = pack_bf16x2(s[0][0], s[0][1]); pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+    pa[2] = pack_bf16x2(s[1][0], s[1][1]); pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+    da[0] = pack_bf16x2(dp[0][0], dp[0][1]); da[1] = pack_bf16x2(dp[0][2], dp[0][3]);
+    da[2] = pack_bf16x2(dp[1][0], dp[1][1]); da[3] = pack_bf16x2(dp[1][2], dp[1][3]);
+    // matrices: (rows 0-7, keys 0-7), (rows 8-15, keys 0-7), (rows 0-7, keys 8-15), (rows 8-15, keys 8-15) of the chunk
+    const int srow = 16 * warp + ((lane >> 3) & 1) * 8 + (lane & 7), scol = 16 * jc + (lane >> 4) * 8;
+    stsm_x4(sP + srow * LP + scol, pa[0], pa[1], pa[2], pa[3]);
+    stsm_x4(sdS + srow * LP + scol, da[0], da[1], da[2], da[3]);
+    // dQ += dS_chunk · K_chunk  (K rows = reduction index -> ldmatrix.trans)
 #pragma unroll
-    for (int j = 0; j < 2 * NT16; ++j) {
-      const int c = 8 * j + 2 * t;
-      // dS = P ∘ (dP − rowsum(P ∘ dP)) / sqrt(features)
-      dp[j][0] = s[j][0] * (dp[j][0] - d0) * scale;
-      dp[j][1] = s[j][1] * (dp[j][1] - d0) * scale;
-      dp[j][2] = s[j][2] * (dp[j][2] - d1) * scale;
-      dp[j][3] = s[j][3] * (dp[j][3] - d1) * scale;
-      *reinterpret_cast<uint32_t*>(sP + r0 * LP + c) = pack_bf16x2(s[j][0], s[j][1]);
-      *reinterpret_cast<uint32_t*>(sP + r1 * LP + c) = pack_bf16x2(s[j][2], s[j][3]);
-      *reinterpret_cast<uint32_t*>(sdS + r0 * LP + c) = pack_bf16x2(dp[j][0], dp[j][1]);
-      *reinterpret_cast<uint32_t*>(sdS + r1 * LP + c) = pack_bf16x2(dp[j][2], dp[j][3]);
+    for (int jp = 0; jp < D / 16; ++jp) {
+      uint32_t bb[4];
+      ldsm_x4_t(bb, sK + (16 * jc + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + jp * 16 + (lane >> 4) * 8);
+      mma_bf16(dq[2 * jp], da, bb[0], bb[1]);
+      mma_bf16(dq[2 * jp + 1], da, bb[2], bb[3]);
     }
-    // dQ = dS · K   (reduction over keys; K rows are the reduction index -> ldmatrix.trans)
-    float dq[D / 8][4];
-#pragma unroll
-    for (int jn = 0; jn < D / 8; ++jn) dq[jn][0] = dq[jn][1] = dq[jn][2] = dq[jn][3] = 0.f;
-    pv_tile<D, NT16>(dq, dp, sK, lane);
-    __syncthreads();  // sP / sdS complete
-
-    // this warp now owns key rows 16w..16w+15:  dV = Pᵀ · dO,  dK = dSᵀ · Q
-    float dv[D / 8][4], dk[D / 8][4];
-#pragma unroll
-    for (int jn = 0; jn < D / 8; ++jn) {
-      dv[jn][0] = dv[jn][1] = dv[jn][2] = dv[jn][3] = 0.f;
-      dk[jn][0] = dk[jn][1] = dk[jn][2] = dk[jn][3] = 0.f;
-    }
-    tn_tile<D, NT16>(dv, sP, sdO, warp, lane);
-    tn_tile<D, NT16>(dk, sdS, sQ, warp, lane);
-    __syncthreads();  // everyone is done reading sQ/sK/sV/sdO (and sP/sdS): reuse own rows as staging
-
-    const int rows_valid = min(16, T - 16 * warp);
-    if (rows_valid > 0) {
-      bf16* gd = dqkv + ((int64_t)b * T + 16 * warp) * 3 * Hd + h * D;
-      store_rows16<D>(dq, sQ + 16 * warp * LD, gd, 3 * Hd, rows_valid, lane);
-      store_rows16<D>(dk, sK + 16 * warp * LD, gd + Hd, 3 * Hd, rows_valid, lane);
-      store_rows16<D>(dv, sV + 16 * warp * LD, gd + 2 * Hd, 3 * Hd, rows_valid, lane);
-    }
-    // staging dirtied the padding rows of Q, K and V in this buffer: restore the zeros the next item relies on
-    __syncthreads();
-    zero_pad_rows<D, TP>(sQ, T, tid, nthr);
-    zero_pad_rows<D, TP>(sK, T, tid, nthr);
-    zero_pad_rows<D, TP>(sV, T, tid, nthr);
-    // (no barrier needed here: the next write into this buffer is the cp.async of rows < T two iterations later,
-    //  and every read of the padding rows is behind that iteration's __syncthreads)
   }
-  cp_async_wait<0>();
+  __syncthreads();  // sP / sdS complete
+
+  // this warp now owns key rows 16w..16w+15:  dV = Pᵀ · dO,  dK = dSᵀ · Q
+  float dv[D / 8][4], dk[D / 8][4];
+#pragma unroll
+  for (int jn = 0; jn < D / 8; ++jn) {
+    dv[jn][0] = dv[jn][1] = dv[jn][2] = dv[jn][3] = 0.f;
+    dk[jn][0] = dk[jn][1] = dk[jn][2] = dk[jn][3] = 0.f;
+  }
+  tn_tile<D, NT16>(dv, sP, sdO, warp, lane);
+  tn_tile<D, NT16>(dk, sdS, sQ, warp, lane);
+  __syncthreads();  // everyone is done reading sQ/sK/sV/sdO: reuse own rows as staging
+
+  const int rows_valid = min(16, T - 16 * warp);
+  if (rows_valid > 0) {
+    bf16* gd = dqkv + ((int64_t)b * T + 16 * warp) * 3 * Hd + h * D;
+    store_rows16<D>(dq, sQ + 16 * warp * LD, gd, 3 * Hd, rows_valid, lane);
+    store_rows16<D>(dk, sK + 16 * warp * LD, gd + Hd, 3 * Hd, rows_valid, lane);
+    store_rows16<D>(dv, sV + 16 * warp * LD, gd + 2 * Hd, 3 * Hd, rows_valid, lane);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -496,19 +524,17 @@ static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int 
   return 0;
 }
 template <int D, int NT16>
-static int launch_bwd_bf16(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, float scale, cudaStream_t st) {
-  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8;
-  constexpr size_t smem = ((size_t)8 * TP * LD + (size_t)2 * TP * LP) * sizeof(bf16) + (size_t)2 * TP * sizeof(float);
-  constexpr int per_sm = NT16 <= 2 ? 4 : (NT16 <= 5 ? 2 : 1);
+static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, float scale,
+                           cudaStream_t st) {
+  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8, TILE = TP * LD;
+  constexpr size_t smem = ((size_t)4 * TILE + (size_t)2 * TP * LP) * sizeof(bf16) + (size_t)2 * TP * sizeof(float);
   auto kern = attn_bwd_bf16_kernel<D, NT16>;
   static bool configured = false;
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int items = B * heads;
-  const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-  kern<<<grid, 32 * NT16, smem, st>>>((const bf16*)qkv, (const bf16*)d_o, lse, (bf16*)dqkv, items, T, heads, scale);
+  kern<<<B * heads, 32 * NT16, smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, T, heads, scale);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -556,12 +582,13 @@ int vitb_attn_fwd(const void* qkv, void* o, float* lse, float* attn_map, int B, 
   return 0;
 }
 
-int vitb_attn_bwd(const void* qkv, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, int d, float scale, int dt, void* stream) {
-  VITB_REQUIRE(qkv && d_o && lse && dqkv, "attn_bwd: null pointer");
+int vitb_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, int d, float scale,
+                  int dt, void* stream) {
+  VITB_REQUIRE(qkv && o && d_o && lse && dqkv, "attn_bwd: null pointer");
   VITB_REQUIRE(B > 0 && T > 0 && T <= 128 && heads > 0 && (d == 32 || d == 64), "attn_bwd: unsupported shape B=%d T=%d heads=%d d=%d (T<=128, d in {32,64})", B, T, heads, d);
   cudaStream_t st = (cudaStream_t)stream;
   if (dt == VITB_BF16) {
-    VITB_ATTN_DISPATCH(launch_bwd_bf16, qkv, d_o, lse, dqkv, B, T, heads, scale, st);
+    VITB_ATTN_DISPATCH(launch_bwd_bf16, qkv, o, d_o, lse, dqkv, B, T, heads, scale, st);
   }
   const size_t smem = ((size_t)4 * T * d + (size_t)2 * T * T) * sizeof(float);
   if (set_dyn_smem((const void*)attn_bwd_f32_kernel, smem)) return -1;

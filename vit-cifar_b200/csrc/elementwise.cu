@@ -85,12 +85,24 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, in
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnBwdWarps = 8;
 
-template <typename T, int VEC>
+// raw (storage-type) 4-element groups, so that the next row can be prefetched without converting it yet
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { float4 v; };
+template <> struct Raw4<bf16> { uint2 v; };
+__device__ __forceinline__ Raw4<float> ldraw(const float* p) { Raw4<float> r; r.v = *reinterpret_cast<const float4*>(p); return r; }
+__device__ __forceinline__ Raw4<bf16> ldraw(const bf16* p) { Raw4<bf16> r; r.v = *reinterpret_cast<const uint2*>(p); return r; }
+__device__ __forceinline__ float4 cvt4(const Raw4<float>& r) { return r.v; }
+__device__ __forceinline__ float4 cvt4(const Raw4<bf16>& r) {
+  const float2 a = unpack_bf16x2(r.v.x), b = unpack_bf16x2(r.v.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename T, int VEC, bool HAS_RES, bool COLSUM>
 __global__ void __launch_bounds__(kLnBwdWarps * 32)
     ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t xs,
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
-                  int64_t dxs, float* __restrict__ ws, int want_colsum, int rows) {
+                  int64_t dxs, float* __restrict__ ws, int rows) {
   constexpr int H = VEC * 128;
   __shared__ float red[kLnBwdWarps][H];
   const int lane = threadIdx.x & 31;
@@ -103,21 +115,43 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32)
     db[i] = dg[i];
     dc[i] = dg[i];
   }
-  for (int row = blockIdx.x * kLnBwdWarps + warp; row < rows; row += gridDim.x * kLnBwdWarps) {
-    const T* xr = x + (int64_t)row * xs;
-    const T* dyr = dy + (int64_t)row * H;
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[VEC], d[VEC];
-    float c1 = 0.f, c2 = 0.f;
+  const int stride = gridDim.x * kLnBwdWarps;
+  int row = blockIdx.x * kLnBwdWarps + warp;
+  Raw4<T> rx[VEC], rdy[VEC], rdr[VEC];
+  float mu = 0.f, rs = 0.f;
+  auto fetch = [&](int r) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int c = (i * 32 + lane) * 4;
-      const float4 xv = ld4(xr + c);
-      d[i] = ld4(dyr + c);
-      xh[i].x = (xv.x - mu) * rs;
-      xh[i].y = (xv.y - mu) * rs;
-      xh[i].z = (xv.z - mu) * rs;
-      xh[i].w = (xv.w - mu) * rs;
+      rx[i] = ldraw(x + (int64_t)r * xs + c);
+      rdy[i] = ldraw(dy + (int64_t)r * H + c);
+      if (HAS_RES) rdr[i] = ldraw(dres + (int64_t)r * H + c);
+    }
+    mu = mean[r];
+    rs = rstd[r];
+  };
+  if (row < rows) fetch(row);
+  while (row < rows) {
+    // convert the current row, then immediately start the loads of the next one (software pipeline)
+    float4 xh[VEC], d[VEC], res[VEC];
+    const float cmu = mu, crs = rs;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      xh[i] = cvt4(rx[i]);
+      d[i] = cvt4(rdy[i]);
+      if (HAS_RES) res[i] = cvt4(rdr[i]);
+    }
+    const int cur = row;
+    row += stride;
+    if (row < rows) fetch(row);
+
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      xh[i].x = (xh[i].x - cmu) * crs;
+      xh[i].y = (xh[i].y - cmu) * crs;
+      xh[i].z = (xh[i].z - cmu) * crs;
+      xh[i].w = (xh[i].w - cmu) * crs;
       // parameter gradients use dy, the input gradient uses g = dy * gamma
       dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y;
       dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
@@ -128,28 +162,24 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32)
     }
     c1 = warp_sum(c1) * (1.0f / H);
     c2 = warp_sum(c2) * (1.0f / H);
-    T* dxr = dx + (int64_t)row * dxs;
+    T* dxr = dx + (int64_t)cur * dxs;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const int c = (i * 32 + lane) * 4;
       float4 o;
-      o.x = rs * (d[i].x - c1 - xh[i].x * c2);
-      o.y = rs * (d[i].y - c1 - xh[i].y * c2);
-      o.z = rs * (d[i].z - c1 - xh[i].z * c2);
-      o.w = rs * (d[i].w - c1 - xh[i].w * c2);
-      if (dres != nullptr) {
-        const float4 r = ld4(dres + (int64_t)row * H + c);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      o.x = crs * (d[i].x - c1 - xh[i].x * c2);
+      o.y = crs * (d[i].y - c1 - xh[i].y * c2);
+      o.z = crs * (d[i].z - c1 - xh[i].z * c2);
+      o.w = crs * (d[i].w - c1 - xh[i].w * c2);
+      if (HAS_RES) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
       st4(dxr + c, o);
-      dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w;
+      if (COLSUM) { dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w; }
     }
   }
-  // block reduction of the three partial vectors, one at a time through the same smem
+  // block reduction of the partial vectors, one at a time through the same smem
   const int nparts = gridDim.x;
 #pragma unroll 1
-  for (int k = 0; k < 3; ++k) {
-    if (k == 2 && !want_colsum) break;
+  for (int k = 0; k < (COLSUM ? 3 : 2); ++k) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -375,14 +405,18 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   VITB_REQUIRE(ws_bytes >= vitb_layernorm_bwd_ws_bytes(rows, H), "layernorm_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = ln_bwd_blocks(rows);
-  const int want = dx_colsum != nullptr;
+  const bool res = dres != nullptr, cs = dx_colsum != nullptr;
+#define VITB_LN_BWD(T, RES, CS)                                                                                              \
+  VITB_DISPATCH_VEC(H, (ln_bwd_kernel<T, VEC, RES, CS><<<blocks, kLnBwdWarps * 32, 0, st>>>((const T*)dy, (const T*)x, xs, gamma, mean, rstd, \
+                                                                                         (const T*)dres, (T*)dx, dxs, (float*)ws, rows)))
   if (dt == VITB_BF16) {
-    VITB_DISPATCH_VEC(H, (ln_bwd_kernel<bf16, VEC><<<blocks, kLnBwdWarps * 32, 0, st>>>(
-                             (const bf16*)dy, (const bf16*)x, xs, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dxs, (float*)ws, want, rows)));
+    if (res && cs) { VITB_LN_BWD(bf16, true, true); } else if (res) { VITB_LN_BWD(bf16, true, false); }
+    else if (cs) { VITB_LN_BWD(bf16, false, true); } else { VITB_LN_BWD(bf16, false, false); }
   } else {
-    VITB_DISPATCH_VEC(H, (ln_bwd_kernel<float, VEC><<<blocks, kLnBwdWarps * 32, 0, st>>>(
-                             (const float*)dy, (const float*)x, xs, gamma, mean, rstd, (const float*)dres, (float*)dx, dxs, (float*)ws, want, rows)));
+    if (res && cs) { VITB_LN_BWD(float, true, true); } else if (res) { VITB_LN_BWD(float, true, false); }
+    else if (cs) { VITB_LN_BWD(float, false, true); } else { VITB_LN_BWD(float, false, false); }
   }
+#undef VITB_LN_BWD
   VITB_LAUNCH_OK();
   partials_finalize_kernel<0><<<finalize_grid(H, 3), finalize_block(), 0, st>>>((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
   VITB_LAUNCH_OK();

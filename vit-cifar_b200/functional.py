@@ -83,7 +83,7 @@ def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, al
     do = alloc("do", (rows, H), act)
     ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
     dqkv = alloc("dqkv", (rows, 3 * H), act)
-    ops.attn_bwd(qkv, do, lse, dqkv, dm.B, dm.T, dm.heads, dm.d, dm.scale)
+    ops.attn_bwd(qkv, o, do, lse, dqkv, dm.B, dm.T, dm.heads, dm.d, dm.scale)
     ops.gemm_wgrad(dqkv, x, g.wqkv, g.bqkv, rows, 3 * H, H)
     dx = alloc("dxn", (rows, H), act)
     ops.gemm_dgrad(dqkv, c.wqkv, None, dx, rows, 3 * H, H)

@@ -145,8 +145,9 @@ def attn_fwd(qkv, o, lse, attn_map, B: int, T: int, heads: int, d: int, scale: f
     check(_lib.load().vitb_attn_fwd(_ptr(qkv), _ptr(o), _ptr(lse), _ptr(attn_map), B, T, heads, d, scale, dt_of(qkv), _stream()), "attn_fwd")
 
 
-def attn_bwd(qkv, d_o, lse, dqkv, B: int, T: int, heads: int, d: int, scale: float) -> None:
-    check(_lib.load().vitb_attn_bwd(_ptr(qkv), _ptr(d_o), _ptr(lse), _ptr(dqkv), B, T, heads, d, scale, dt_of(qkv), _stream()), "attn_bwd")
+def attn_bwd(qkv, o, d_o, lse, dqkv, B: int, T: int, heads: int, d: int, scale: float) -> None:
+    check(_lib.load().vitb_attn_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(dqkv), B, T, heads, d, scale, dt_of(qkv), _stream()),
+          "attn_bwd")
 
 
 def gelu_bwd_colsum(dy, z, dz, colsum, rows: int, cols: int) -> None:
