@@ -51,15 +51,20 @@ int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
  * bias  fp32 (H);  cls fp32 (H) or NULL when has_cls == 0;  pos fp32 (T,H), T = P*P + has_cls
  * out   act  (B,T,H):  out[b,0] = cls+pos[0];  out[b,has_cls+n] = words[b,n]·wᵀ + bias + pos[has_cls+n]
  * P is the number of patches per side (the reference's `patch`, vit.py:37). */
-int vitb_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* cls,
-                         const float* pos, void* out, int B, int S, int P, int H, int has_cls,
-                         int dt, void* stream);
-/* Backward of the above (autograd of vit.py:66-70). dout act (B,T,H).  Writes (overwrites)
- * dw (H,K), dbias (H), dcls (H) (may be NULL), dpos (T,H).  ws: vitb_patch_embed_bwd_ws_bytes(). */
+size_t vitb_patch_embed_fwd_ws_bytes(int B, int S, int P, int H, int dt);
+/* w_act: emb.weight in the activation type (bf16 shadow) or NULL; words: act (B*P*P, K) or NULL.  When both are given in
+ * bf16 mode (and the shape allows) the product runs on the tensor cores: the patch matrix is written to `words` (kept
+ * for backward), multiplied by tcgen05 and assembled with cls/pos; ws: vitb_patch_embed_fwd_ws_bytes().  Otherwise
+ * (fp32 check mode) an fp32 FFMA kernel reads the image directly. */
+int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, const float* bias,
+                         const float* cls, const float* pos, void* out, void* words, void* ws,
+                         size_t ws_bytes, int B, int S, int P, int H, int has_cls, int dt, void* stream);
+/* Backward of the above (autograd of vit.py:66-70). dout act (B,T,H); words as written by the forward (or NULL).
+ * Writes (overwrites) dw (H,K), dbias (H), dcls (H) (may be NULL), dpos (T,H).  ws: vitb_patch_embed_bwd_ws_bytes(). */
 size_t vitb_patch_embed_bwd_ws_bytes(int B, int S, int P, int H, int has_cls);
-int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* dbias, float* dcls,
-                         float* dpos, void* ws, size_t ws_bytes, int B, int S, int P, int H,
-                         int has_cls, int dt, void* stream);
+int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, float* dw, float* dbias,
+                         float* dcls, float* dpos, void* ws, size_t ws_bytes, int B, int S, int P,
+                         int H, int has_cls, int dt, void* stream);
 
 /* ---- LayerNorm: layers.py:26,30,45,47 (la1/la2), vit.py:62 (fc[0]); eps 1e-5, affine ----
  * x act, row r at x + r*x_row_stride elements (lets the head read out[:,0], vit.py:73); y act (rows,H)

@@ -204,9 +204,10 @@ def test_gelu_bwd_and_colsum(ops, dtype, rows, cols):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("P,has_cls", [(8, True), (4, True), (4, False)])
-def test_patch_embed_fwd_bwd(ops, dtype, P, has_cls):
+@pytest.mark.parametrize("B", [5, 70])
+def test_patch_embed_fwd_bwd(ops, dtype, P, has_cls, B):
     import oracle
-    B, S, H = 5, 32, 128
+    S, H = 32, 128
     cfg = oracle.ViTConfig(patch=P, hidden=H, is_cls_token=has_cls)
     K, T = cfg.patch_len, cfg.num_tokens
     img = rnd((B, 3, S, S), torch.float32, 1)
@@ -221,12 +222,18 @@ def test_patch_embed_fwd_bwd(ops, dtype, P, has_cls):
     dout = rnd((B, T, H), dtype, 6)
     out_ref.backward(dout.float())
     out = torch.empty((B * T, H), dtype=dtype, device="cuda")
-    ops.patch_embed_fwd(cu(img), cu(w.detach()), cu(b.detach()), cu(cls.detach().view(-1)) if has_cls else None, cu(pos.detach().view(T, H)), out, P, has_cls)
+    words = torch.empty((B * P * P, K), dtype=dtype, device="cuda") if dtype == torch.bfloat16 else None
+    w_act = cu(w.detach().to(dtype)) if dtype == torch.bfloat16 else None
+    ops.patch_embed_fwd(cu(img), cu(w.detach()), w_act, cu(b.detach()), cu(cls.detach().view(-1)) if has_cls else None,
+                        cu(pos.detach().view(T, H)), out, words, P, has_cls)
     assert rel(out.view(B, T, H), out_ref.detach()) < (1e-5 if dtype == torch.float32 else 5e-3)
+    if words is not None:
+        assert rel(words.view(B, P * P, K), oracle.to_words(img, cfg)) < 3e-3
     dw = torch.empty((H, K), device="cuda"); db = torch.empty(H, device="cuda"); dpos = torch.empty((T, H), device="cuda")
     dcls = torch.empty(H, device="cuda") if has_cls else None
-    ops.patch_embed_bwd(cu(img), cu(dout).view(B * T, H), dw, db, dcls, dpos, P, has_cls)
-    assert rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4 and rel(dpos, pos.grad.view(T, H)) < 1e-4
+    ops.patch_embed_bwd(cu(img), words, cu(dout).view(B * T, H), dw, db, dcls, dpos, P, has_cls)
+    tol_w = 1e-4 if dtype == torch.float32 else 5e-3  # bf16 path multiplies the bf16-rounded patch matrix
+    assert rel(dw, w.grad) < tol_w and rel(db, b.grad) < 1e-4 and rel(dpos, pos.grad.view(T, H)) < 1e-4
     if has_cls:
         assert rel(dcls, cls.grad.view(-1)) < 1e-4
 

@@ -33,9 +33,10 @@ SIGNATURES = {
     "vitb_device_supported": (_i, []),
     "vitb_launch_count": (C.c_ulonglong, []),
     "vitb_cast_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
-    "vitb_patch_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vitb_patch_embed_fwd_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "vitb_patch_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
     "vitb_patch_embed_bwd_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "vitb_patch_embed_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
+    "vitb_patch_embed_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
     "vitb_layernorm_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _f, _i, _p]),
     "vitb_layernorm_bwd_ws_bytes": (_sz, [_i, _i]),
     "vitb_layernorm_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),

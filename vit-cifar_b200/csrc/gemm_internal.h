@@ -27,4 +27,14 @@ int simt_gemm_launch(const SimtGemmArgs& g, int a_dt, int b_dt, int o_dt, int sp
 int simt_pick_splits(int tiles, int K);
 int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t ld, int x_dt, cudaStream_t st);
 
+// tensor-core pieces of the patch embedding (gemm_tc.cu), bf16 only
+//   fwd:  tmp[M, H] = words[M, K] · w[H, K]ᵀ + bias        (K = 48 / 192: partial k-block, TMA zero-fills)
+//   bwd:  dw[H, K] = sum_m dout[b, off + n, :]ᵀ words[m, :] (A read through a 3-D tensor map that skips the cls rows),
+//         dbias[H] = column sums of those rows (ones-operand MMA)
+bool tc_patch_ok(int PP, int H, int K);
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, void* tmp, int M, int H, int K, cudaStream_t st);
+size_t tc_patch_wgrad_ws_bytes(int B, int PP, int H, int K);
+int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias, void* ws, size_t ws_bytes, int B, int Tn, int PP,
+                   int has_cls, int H, int K, cudaStream_t st);
+
 }  // namespace vitb

@@ -239,26 +239,96 @@ __global__ void batch_sum_kernel(const T* __restrict__ x, float* __restrict__ pa
 
 static int batch_sum_slices(int B) { return B >= 256 ? 16 : (B >= 32 ? 4 : 1); }
 
+// words[m][f..f+7] (bf16) for the tensor-core path: 8 consecutive features per thread (vit.py:79-89)
+__global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restrict__ words, int B, int S, int P) {
+  const int ps = S / P;
+  const int K = ps * ps * 3, K8 = K / 8;
+  const int64_t total = (int64_t)B * P * P * K8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f0 = (int)(i % K8) * 8;
+    const int m = (int)(i / K8);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gather_word(img, m, f0 + j, S, P);
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(words + (int64_t)m * K + f0) = u;
+  }
+}
+
+// out[b, off+n, :] = tmp[b*PP+n, :] + pos[off+n, :];  out[b, 0, :] = cls + pos[0, :]   (vit.py:68-70), 8 columns per thread
+__global__ void patch_assemble_kernel(const bf16* __restrict__ tmp, const float* __restrict__ cls, const float* __restrict__ pos,
+                                      bf16* __restrict__ out, int B, int PP, int Tn, int H, int has_cls) {
+  const int H8 = H / 8;
+  const int64_t total = (int64_t)B * Tn * H8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H8) * 8;
+    const int64_t bt = i / H8;
+    const int t = (int)(bt % Tn);
+    const int64_t b = bt / Tn;
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * H + c));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * H + c + 4));
+    float v[8];
+    if (has_cls && t == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + c)), c1 = __ldg(reinterpret_cast<const float4*>(cls + c + 4));
+      v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
+    } else {
+      const uint4 u = *reinterpret_cast<const uint4*>(tmp + ((size_t)b * PP + (t - has_cls)) * H + c);
+      const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
+      v[0] = a.x; v[1] = a.y; v[2] = d.x; v[3] = d.y; v[4] = e.x; v[5] = e.y; v[6] = f.x; v[7] = f.y;
+    }
+    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
+  }
+}
+
 }  // namespace vitb
 
 using namespace vitb;
 
 extern "C" {
 
-int vitb_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* cls, const float* pos,
-                         void* out, int B, int S, int P, int H, int has_cls, int dt, void* stream) {
+static bool patch_tc_path(const void* words, const void* w_act, int P, int S, int H, int dt) {
+  if (dt != VITB_BF16 || words == nullptr || w_act == nullptr || P <= 0 || S % P) return false;
+  const int ps = S / P;
+  return tc_patch_ok(P * P, H, ps * ps * 3);
+}
+
+size_t vitb_patch_embed_fwd_ws_bytes(int B, int S, int P, int H, int dt) {
+  if (dt != VITB_BF16 || P <= 0) return 0;
+  return align_up((size_t)B * P * P * H * sizeof(bf16), 256);  // un-assembled GEMM output of the tensor-core path
+}
+
+int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, const float* bias, const float* cls, const float* pos,
+                         void* out, void* words, void* ws, size_t ws_bytes, int B, int S, int P, int H, int has_cls, int dt, void* stream) {
   VITB_REQUIRE(img && w && bias && pos && out, "patch_embed_fwd: null pointer");
   VITB_REQUIRE(B > 0 && P > 0 && S % P == 0 && H % 4 == 0, "patch_embed_fwd: bad shape S=%d P=%d H=%d", S, P, H);
   VITB_REQUIRE(!has_cls || cls, "patch_embed_fwd: has_cls without cls pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int ps = S / P, K = ps * ps * 3, Tn = P * P + (has_cls ? 1 : 0);
+  const int ps = S / P, K = ps * ps * 3, PP = P * P, Tn = PP + (has_cls ? 1 : 0);
+  if (patch_tc_path(words, w_act, P, S, H, dt) && ws != nullptr && ws_bytes >= vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)) {
+    // tensor-core path: words (bf16) -> tcgen05 GEMM (+bias) -> assemble with cls / pos_emb
+    int blocks = (int)ceil_div64((int64_t)B * PP * (K / 8), 256);
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    words_bf16_kernel<<<blocks, 256, 0, st>>>(img, (bf16*)words, B, S, P);
+    VITB_LAUNCH_OK();
+    int rc = tc_patch_fwd(words, w_act, bias, ws, B * PP, H, K, st);
+    if (rc) return rc;
+    blocks = (int)ceil_div64((int64_t)B * Tn * (H / 8), 256);
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    patch_assemble_kernel<<<blocks, 256, 0, st>>>((const bf16*)ws, cls, pos, (bf16*)out, B, PP, Tn, H, has_cls ? 1 : 0);
+    VITB_LAUNCH_OK();
+    return 0;
+  }
   SimtGemmArgs g = {};
   g.a = img; g.b = w;
-  g.M = B * P * P; g.N = H; g.K = K;
+  g.M = B * PP; g.N = H; g.K = K;
   g.a_gather = 1; g.gather_S = S; g.gather_P = P;  // A(m,k) = words(m,k) read straight from the image
-  g.b_sk = 1; g.b_sn = K;          // B(k,n) = w[n][k]
+  g.b_sk = 1; g.b_sn = K;                          // B(k,n) = w[n][k]
   g.e.mode = EPI_FWD; g.e.bias = bias; g.e.out = out; g.e.ldc = H;
-  g.e.rm_group = P * P; g.e.rm_stride = Tn; g.e.rm_offset = has_cls ? 1 : 0; g.e.pos = pos;
+  g.e.rm_group = PP; g.e.rm_stride = Tn; g.e.rm_offset = has_cls ? 1 : 0; g.e.pos = pos;
   int rc = simt_gemm_launch(g, VITB_F32, VITB_F32, dt, 1, st);
   if (rc) return rc;
   if (has_cls) {
@@ -269,28 +339,37 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const float* bias, co
   return 0;
 }
 
-size_t vitb_patch_embed_bwd_ws_bytes(int B, int S, int P, int H, int has_cls) {
-  if (P <= 0 || S % P) return 0;
-  const int ps = S / P, K = ps * ps * 3;
+static size_t patch_bwd_simt_part_bytes(int B, int PP, int H, int K) {
   const int tiles = ceil_div(H, SB) * ceil_div(K, SB);
-  const int splits = simt_pick_splits(tiles, B * P * P);
-  const int Tn = P * P + (has_cls ? 1 : 0);
-  return align_up((size_t)splits * H * K * sizeof(float), 256) + align_up((size_t)batch_sum_slices(B) * Tn * H * sizeof(float), 256);
+  return align_up((size_t)simt_pick_splits(tiles, B * PP) * H * K * sizeof(float), 256);
 }
 
-int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* dbias, float* dcls, float* dpos,
+size_t vitb_patch_embed_bwd_ws_bytes(int B, int S, int P, int H, int has_cls) {
+  if (P <= 0 || S % P) return 0;
+  const int ps = S / P, K = ps * ps * 3, PP = P * P;
+  const int Tn = PP + (has_cls ? 1 : 0);
+  size_t wg = patch_bwd_simt_part_bytes(B, PP, H, K);
+  if (tc_patch_ok(PP, H, K)) {
+    const size_t t = tc_patch_wgrad_ws_bytes(B, PP, H, K);
+    if (t > wg) wg = t;
+  }
+  return wg + align_up((size_t)batch_sum_slices(B) * Tn * H * sizeof(float), 256);
+}
+
+int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, float* dw, float* dbias, float* dcls, float* dpos,
                          void* ws, size_t ws_bytes, int B, int S, int P, int H, int has_cls, int dt, void* stream) {
   VITB_REQUIRE(img && dout && dw && dbias && dpos && ws, "patch_embed_bwd: null pointer");
   VITB_REQUIRE(B > 0 && P > 0 && S % P == 0 && H % 4 == 0, "patch_embed_bwd: bad shape");
   VITB_REQUIRE(ws_bytes >= vitb_patch_embed_bwd_ws_bytes(B, S, P, H, has_cls), "patch_embed_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int ps = S / P, K = ps * ps * 3, PP = P * P, Tn = PP + (has_cls ? 1 : 0);
-  // 1) dpos = sum_b dout[b]; dcls, dbias from it
+  const bool tc = dt == VITB_BF16 && words != nullptr && tc_patch_ok(PP, H, K);
+  const size_t wg_bytes = vitb_patch_embed_bwd_ws_bytes(B, S, P, H, has_cls) - align_up((size_t)batch_sum_slices(B) * Tn * H * sizeof(float), 256);
+  // 1) dpos = sum_b dout[b]; dcls (and, on the SIMT path, dbias) from it
   {
     const int64_t n = (int64_t)Tn * H;
     const int slices = batch_sum_slices(B);
-    const int tiles0 = ceil_div(H, SB) * ceil_div(K, SB);
-    float* bpart = slices > 1 ? (float*)((char*)ws + align_up((size_t)simt_pick_splits(tiles0, B * PP) * H * K * sizeof(float), 256)) : dpos;
+    float* bpart = slices > 1 ? (float*)((char*)ws + wg_bytes) : dpos;
     const dim3 grid((unsigned)ceil_div64(n / 4, 128), slices);
     if (dt == VITB_BF16) batch_sum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)dout, bpart, B, n);
     else batch_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)dout, bpart, B, n);
@@ -302,7 +381,8 @@ int vitb_patch_embed_bwd(const float* img, const void* dout, float* dw, float* d
     patch_bias_cls_kernel<<<ceil_div(H, 128), 128, 0, st>>>(dpos, dbias, dcls, Tn, H, has_cls ? 1 : 0);
     VITB_LAUNCH_OK();
   }
-  // 2) dW[h][k] = sum_m dout[phys(m)][h] * words(m,k)  (split over m, fixed-order finalize)
+  // 2) dW[h][k] = sum_m dout[phys(m)][h] * words(m,k)
+  if (tc) return tc_patch_wgrad(dout, words, dw, dbias, ws, wg_bytes, B, Tn, PP, has_cls, H, K, st);  // (rewrites dbias, same value)
   float* part = (float*)ws;
   const int tiles = ceil_div(H, SB) * ceil_div(K, SB);
   const int splits = simt_pick_splits(tiles, B * PP);

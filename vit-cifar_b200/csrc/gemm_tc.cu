@@ -34,6 +34,9 @@ struct TcArgs {
   int has_in;        // tma_in valid: residual (EPI_FWD) or z for gelu' (EPI_DGRAD)
   int has_pre;       // tma_pre valid: store the pre-activation
   float* dbias_part; // wgrad: [splits][M] fp32 partial column sums of dY (or null)
+  int valid_n;       // RAW epilogue: columns >= valid_n are not stored (patch-embedding wgrad: K = 48 inside a 128 tile)
+  int a3_pp;         // > 0: the MN-major A operand is a (B, T, H) tensor read through a 3-D map, a3_pp token rows per image
+  int a3_off;        //      first token row used (1 when a cls row is skipped)
   EpiParams e;
 };
 
@@ -75,6 +78,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -139,13 +148,13 @@ constexpr uint32_t tmem_cols() {
   return 2 * BN + 32 <= 64 ? 64 : 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NSLAB>
 struct TcSmem {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kEpiOff = STAGES * kStageBytes;                 // 8 warps x {out, pre, in} slabs
-  static constexpr uint32_t kEpiBytes = kEpiWarps * 3 * kSlabBytes;          // (the all-ones wgrad operand overlays it)
+  static constexpr uint32_t kEpiBytes = NSLAB > 0 ? kEpiWarps * NSLAB * kSlabBytes : 2048;  // NSLAB slabs per epilogue warp, or the all-ones wgrad operand
   static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
   static constexpr uint32_t kNumBars = 2 * STAGES + 4 + kEpiWarps;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
@@ -178,12 +187,12 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                    const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, NSLAB>;
   static_assert(BN == 128, "epilogue slabs assume two 64-column halves");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -257,6 +266,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int k0 = kb * BK;
           if (!A_MN) {
             tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), k0, m0);
+          } else if (p.a3_pp > 0) {
+            // 64 reduction rows = token rows [a3_off + k0 % pp, +64) of image k0 / pp  (pp >= 64), or all pp token rows of
+            // 64 / pp consecutive images (pp < 64); the box of the 3-D map has exactly that shape
+            const int img = k0 / p.a3_pp, tok = p.a3_off + (p.a3_pp >= 64 ? k0 % p.a3_pp : 0);
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, tok, img);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, k0);
@@ -324,9 +339,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int quarter = warp & 3;
     const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    const uint32_t slab_out = epi_base + (uint32_t)(ew * 3 + 0) * kSlabBytes;
-    const uint32_t slab_pre = epi_base + (uint32_t)(ew * 3 + 1) * kSlabBytes;
-    const uint32_t slab_in = epi_base + (uint32_t)(ew * 3 + 2) * kSlabBytes;
+    // slab 0: output; slab 1: pre-activation (or the input operand when there is no pre-activation); slab 2: input operand
+    const uint32_t slab_out = epi_base + (uint32_t)(ew * NSLAB + 0) * kSlabBytes;
+    const uint32_t slab_pre = epi_base + (uint32_t)(ew * NSLAB + (NSLAB > 1 ? 1 : 0)) * kSlabBytes;
+    const uint32_t slab_in = epi_base + (uint32_t)(ew * NSLAB + (NSLAB > 2 ? 2 : (NSLAB > 1 ? 1 : 0))) * kSlabBytes;
     int acc = 0;
     uint32_t acc_phase = 0, in_phase = 0;
     const EpiParams& e = p.e;
@@ -367,7 +383,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (grow < p.M) {
           float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + n0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 16; ++j)
+            if (n0 + 4 * j + 3 < p.valid_n) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           if (do_bias) p.dbias_part[(size_t)split * p.M + grow] = __uint_as_float(rawb[0]);
         }
         continue;
@@ -469,14 +486,30 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
+// 3-D bf16 tensor (B, T, H) read as 64 H-columns x `rows` token rows x `imgs` images (128B swizzle): the MN-major A operand
+// of the patch-embedding wgrad, which must skip the cls row of every image
+static int make_map3(CUtensorMap* map, const void* ptr, uint64_t H, uint64_t Tn, uint64_t B, uint32_t rows, uint32_t imgs) {
+  EncodeTiledFn fn = get_encode_fn();
+  VITB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[3] = {H, Tn, B};
+  cuuint64_t gstr[2] = {H * 2, Tn * H * 2};
+  cuuint32_t box[3] = {64, rows, imgs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VITB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-static int launch_tc(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB>
+static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES, NSLAB>;
+  static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, NSLAB>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
@@ -490,13 +523,89 @@ static int launch_tc(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
 }
 
 constexpr int kBN = 128;
-constexpr int kStages = 4;
-static_assert(TcSmem<kBN, kStages>::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
 
-static bool tc_shape_ok(int M, int N, int K) { return M >= 32 && N % kBN == 0 && K % BK == 0; }
+// The smem ring gets whatever the epilogue slabs leave free: more TMA bytes in flight when the epilogue needs fewer slabs.
+//   slabs per epilogue warp = 1 (output) + pre-activation + input operand;  0 = fp32 direct-store epilogue (wgrad)
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
+  if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 6, 0>(m, args, st);
+  const int nslab = 1 + (args.has_pre ? 1 : 0) + (args.has_in ? 1 : 0);
+  if (nslab == 1) return launch_tc_impl<BN, A_MN, B_MN, 6, 1>(m, args, st);
+  if (nslab == 2) return launch_tc_impl<BN, A_MN, B_MN, 5, 2>(m, args, st);
+  return launch_tc_impl<BN, A_MN, B_MN, 4, 3>(m, args, st);
+}
+
+// K needs only a 16-byte row pitch: a partial last k-block is zero-filled by TMA
+static bool tc_shape_ok(int M, int N, int K) { return M >= 32 && N % kBN == 0 && K % 8 == 0; }
 
 static int check_dt(int dt) {
   VITB_REQUIRE(dt == VITB_F32 || dt == VITB_BF16, "dt must be VITB_F32 or VITB_BF16 (got %d)", dt);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch embedding on the tensor cores (called from gemm_simt.cu's front end)
+// ---------------------------------------------------------------------------------------------
+bool tc_patch_ok(int PP, int H, int K) {
+  return H % 128 == 0 && K % 8 == 0 && K <= 256 && ((PP >= 64 && PP % 64 == 0) || (PP < 64 && 64 % PP == 0));
+}
+
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, void* tmp, int M, int H, int K, cudaStream_t st) {
+  TcMaps m;
+  if (make_map(&m.a, words, K, M, K, BM)) return -1;
+  if (make_map(&m.b, w_bf16, K, H, K, kBN)) return -1;
+  if (make_map(&m.out, tmp, H, M, H, 32)) return -1;
+  m.pre = m.out; m.in = m.out;
+  TcArgs t = {};
+  t.M = M; t.N = H; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = H / kBN; t.splits = 1;
+  t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.valid_n = H;
+  t.e.mode = EPI_FWD; t.e.bias = bias; t.e.out = tmp; t.e.ldc = H;
+  return launch_tc<kBN, false, false>(m, t, st);
+}
+
+static void patch_wgrad_plan(int B, int PP, int H, int* splits, int* kb_total, int* kb_per) {
+  const int tiles = H / BM;  // one 128-wide n block holds all K <= 128 columns (two for K = 192)
+  const int total = ceil_div(B * PP, BK);
+  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > total) s = total;
+  const int per = ceil_div(total, s);
+  *splits = ceil_div(total, per);
+  *kb_total = total;
+  *kb_per = per;
+}
+
+size_t tc_patch_wgrad_ws_bytes(int B, int PP, int H, int K) {
+  int splits, a, b;
+  patch_wgrad_plan(B, PP, H, &splits, &a, &b);
+  return align_up((size_t)splits * H * K * sizeof(float), 256) + align_up((size_t)splits * H * sizeof(float), 256);
+}
+
+int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias, void* ws, size_t ws_bytes, int B, int Tn, int PP,
+                   int has_cls, int H, int K, cudaStream_t st) {
+  VITB_REQUIRE(ws && ws_bytes >= tc_patch_wgrad_ws_bytes(B, PP, H, K), "patch wgrad: workspace too small");
+  int splits, kb_total, kb_per;
+  patch_wgrad_plan(B, PP, H, &splits, &kb_total, &kb_per);
+  float* part = (float*)ws;
+  float* bpart = (float*)((char*)ws + align_up((size_t)splits * H * K * sizeof(float), 256));
+  TcMaps m;
+  const uint32_t rows = PP >= 64 ? 64 : PP, imgs = PP >= 64 ? 1 : 64 / PP;
+  if (make_map3(&m.a, dout, H, Tn, B, rows, imgs)) return -1;
+  if (make_map(&m.b, words, K, (uint64_t)B * PP, K, 64)) return -1;
+  m.out = m.b; m.pre = m.b; m.in = m.b;
+  TcArgs t = {};
+  t.M = H; t.N = ceil_div(K, kBN) * kBN; t.num_m_blocks = H / BM; t.num_n_blocks = ceil_div(K, kBN); t.splits = splits;
+  t.kblocks_total = kb_total; t.kblocks_per_split = kb_per;
+  t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = part; t.valid_n = K;
+  t.dbias_part = bpart;
+  t.a3_pp = PP; t.a3_off = has_cls ? 1 : 0;
+  int rc = launch_tc<kBN, true, true>(m, t, st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)H * K;
+  partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+  VITB_LAUNCH_OK();
+  partials_finalize_kernel<0><<<finalize_grid(H, 1), finalize_block(), 0, st>>>(bpart, splits, H, dbias, nullptr, nullptr);
+  VITB_LAUNCH_OK();
   return 0;
 }
 
@@ -525,9 +634,9 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     if (residual && make_map(&m.in, residual, N, M, N, 32)) return -1;
     TcArgs t = {};
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
-    t.kblocks_total = K / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
+    t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = N;
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
-    return launch_tc<kBN, false, false, kStages>(m, t, st);
+    return launch_tc<kBN, false, false>(m, t, st);
   }
   SimtGemmArgs g = {};
   g.a = a; g.b = w; g.M = M; g.N = N; g.K = K;
@@ -553,9 +662,9 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     if (z && make_map(&m.in, z, K, M, K, 32)) return -1;
     TcArgs t = {};
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
-    t.kblocks_total = N / BK; t.kblocks_per_split = t.kblocks_total; t.e = e;
+    t.kblocks_total = ceil_div(N, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = K;
     t.has_in = z != nullptr;
-    return launch_tc<kBN, false, true, kStages>(m, t, st);
+    return launch_tc<kBN, false, true>(m, t, st);
   }
   SimtGemmArgs g = {};
   g.a = dy; g.b = w; g.M = M; g.N = K; g.K = N;
@@ -621,9 +730,9 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
     TcArgs t = {};
     t.M = N; t.N = K; t.num_m_blocks = N / BM; t.num_n_blocks = K / kBN; t.splits = splits;
     t.kblocks_total = kb_total; t.kblocks_per_split = kb_per;
-    t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = splits > 1 ? part : dw;
+    t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = splits > 1 ? part : dw; t.valid_n = K;
     t.dbias_part = dbias ? (splits > 1 ? bpart : dbias) : nullptr;  // bias gradient rides on the tensor pipe (ones-operand MMA)
-    int rc = launch_tc<kBN, true, true, kStages>(m, t, st);
+    int rc = launch_tc<kBN, true, true>(m, t, st);
     if (rc) return rc;
     if (splits > 1) {
       const int64_t n = (int64_t)N * K;

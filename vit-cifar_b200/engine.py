@@ -118,7 +118,8 @@ class TrainEngine:
         m, dm = self.model, self.dm
         B, T, H, Cn = self.B, m.num_tokens, m.hidden, m.num_classes
         emb_w, emb_b, cls, pos = self.stem_p
-        x = Fn.stem_fwd(self.img, emb_w, emb_b, cls, pos, m.patch, self.act, self._alloc("stem"))
+        emb_w_c = self.store.layout.view(self.C, "emb.weight") if self.C is not self.P else None
+        x, words = Fn.stem_fwd(self.img, emb_w, emb_w_c, emb_b, cls, pos, m.patch, self.act, self._alloc("stem"))
         saved = []
         for i in range(m.num_layers):
             x, sv = Fn.encoder_fwd(x, self.lc[i], self.lp[i], dm, self._alloc(f"l{i}"))
@@ -136,7 +137,7 @@ class TrainEngine:
             dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i))
             self._allreduce(self.buckets[1 + i])
         g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
-        Fn.stem_bwd(self.img, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
+        Fn.stem_bwd(self.img, words, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
         self._allreduce(self.buckets[0])
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)

@@ -145,18 +145,20 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
 # ---------------------------------------------------------------------------------------------
 # stem: vit.py:66-70   and   head: vit.py:72-76
 # ---------------------------------------------------------------------------------------------
-def stem_fwd(img: torch.Tensor, emb_w, emb_b, cls, pos, P: int, act: torch.dtype, alloc: Alloc) -> torch.Tensor:
-    B = img.shape[0]
+def stem_fwd(img: torch.Tensor, emb_w, emb_w_c, emb_b, cls, pos, P: int, act: torch.dtype, alloc: Alloc):
+    """emb_w: fp32 master; emb_w_c: the same weight in the activation dtype (bf16 shadow) or None.  Returns (x0, words)."""
+    B, _, S, _ = img.shape
     has_cls = cls is not None
     T = P * P + (1 if has_cls else 0)
-    H = emb_w.shape[0]
+    H, K = emb_w.shape
     x0 = alloc("x0", (B * T, H), act)
-    ops.patch_embed_fwd(img, emb_w, emb_b, cls, pos, x0, P, has_cls)
-    return x0
+    words = alloc("words", (B * P * P, K), act) if (act == torch.bfloat16 and emb_w_c is not None) else None
+    ops.patch_embed_fwd(img, emb_w, emb_w_c if words is not None else None, emb_b, cls, pos, x0, words, P, has_cls)
+    return x0, words
 
 
-def stem_bwd(img: torch.Tensor, dx0: torch.Tensor, g_emb_w, g_emb_b, g_cls, g_pos, P: int) -> None:
-    ops.patch_embed_bwd(img, dx0, g_emb_w, g_emb_b, g_cls, g_pos, P, g_cls is not None)
+def stem_bwd(img: torch.Tensor, words, dx0: torch.Tensor, g_emb_w, g_emb_b, g_cls, g_pos, P: int) -> None:
+    ops.patch_embed_bwd(img, words, dx0, g_emb_w, g_emb_b, g_cls, g_pos, P, g_cls is not None)
 
 
 def head_fwd(x: torch.Tensor, ln_w, ln_b, fc_w_c, fc_b, B: int, T: int, H: int, C: int, is_cls: bool, alloc: Alloc):

@@ -85,23 +85,28 @@ def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     check(_lib.load().vitb_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_f32_to_bf16")
 
 
-def patch_embed_fwd(img, w, bias, cls, pos, out, P: int, has_cls: bool) -> None:
+def patch_embed_fwd(img, w, w_act, bias, cls, pos, out, words, P: int, has_cls: bool) -> None:
+    """w_act / words: bf16 shadow of emb.weight and the (B*P*P, K) patch-matrix buffer (tensor-core path) or None."""
     B, _, S, _ = img.shape
     H = w.shape[0]
     assert img.dtype == torch.float32 and w.dtype == torch.float32
-    _contig(img, w, bias, cls, pos, out)
-    check(_lib.load().vitb_patch_embed_fwd(_ptr(img), _ptr(w), _ptr(bias), _ptr(cls), _ptr(pos), _ptr(out),
-                                           B, S, P, H, int(has_cls), dt_of(out), _stream()), "patch_embed_fwd")
+    _contig(img, w, bias, cls, pos, out, words)
+    lib = _lib.load()
+    dt = dt_of(out)
+    nb = lib.vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)
+    ws = workspace(nb, img.device) if nb else None
+    check(lib.vitb_patch_embed_fwd(_ptr(img), _ptr(w), _ptr(w_act), _ptr(bias), _ptr(cls), _ptr(pos), _ptr(out), _ptr(words),
+                                   _ptr(ws), ws.numel() if ws is not None else 0, B, S, P, H, int(has_cls), dt, _stream()), "patch_embed_fwd")
 
 
-def patch_embed_bwd(img, dout, dw, dbias, dcls, dpos, P: int, has_cls: bool) -> None:
+def patch_embed_bwd(img, words, dout, dw, dbias, dcls, dpos, P: int, has_cls: bool) -> None:
     B, _, S, _ = img.shape
     H = dw.shape[0]
     lib = _lib.load()
-    _contig(img, dout, dw, dbias, dcls, dpos)
+    _contig(img, dout, dw, dbias, dcls, dpos, words)
     nb = lib.vitb_patch_embed_bwd_ws_bytes(B, S, P, H, int(has_cls))
     ws = workspace(nb, img.device)
-    check(lib.vitb_patch_embed_bwd(_ptr(img), _ptr(dout), _ptr(dw), _ptr(dbias), _ptr(dcls), _ptr(dpos), _ptr(ws), ws.numel(),
+    check(lib.vitb_patch_embed_bwd(_ptr(img), _ptr(words), _ptr(dout), _ptr(dw), _ptr(dbias), _ptr(dcls), _ptr(dpos), _ptr(ws), ws.numel(),
                                    B, S, P, H, int(has_cls), dt_of(dout), _stream()), "patch_embed_bwd")
 
 

@@ -17,25 +17,25 @@ from .params import FlatLayout, FlatStore, layer_entries
 
 class _StemFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, model, emb_w, emb_b, pos, cls):
+    def forward(ctx, img, model, emb_w_c, emb_w, emb_b, pos, cls):
         img = img.contiguous().float()
-        x0 = Fn.stem_fwd(img, emb_w.detach(), emb_b.detach(), None if cls is None else cls.detach().view(-1),
-                         pos.detach().view(pos.shape[-2], pos.shape[-1]), model.patch, act_dtype(), Fn.default_alloc(img.device))
-        ctx.saved = (img, model, cls is not None)
+        x0, words = Fn.stem_fwd(img, emb_w.detach(), emb_w_c, emb_b.detach(), None if cls is None else cls.detach().view(-1),
+                                pos.detach().view(pos.shape[-2], pos.shape[-1]), model.patch, act_dtype(), Fn.default_alloc(img.device))
+        ctx.saved = (img, model, cls is not None, words)
         B = img.shape[0]
         return x0.view(B, -1, x0.shape[-1])
 
     @staticmethod
     def backward(ctx, dx0):
-        img, model, has_cls = ctx.saved
+        img, model, has_cls, words = ctx.saved
         H, K, T = model.hidden, model.emb.in_features, model.num_tokens
         dev = dx0.device
         g_w = torch.empty((H, K), dtype=torch.float32, device=dev)
         g_b = torch.empty((H,), dtype=torch.float32, device=dev)
         g_pos = torch.empty((T, H), dtype=torch.float32, device=dev)
         g_cls = torch.empty((H,), dtype=torch.float32, device=dev) if has_cls else None
-        Fn.stem_bwd(img, dx0.reshape(-1, H).contiguous(), g_w, g_b, g_cls, g_pos, model.patch)
-        return None, None, g_w, g_b, g_pos.view(1, T, H), (g_cls.view(1, 1, H) if has_cls else None)
+        Fn.stem_bwd(img, words, dx0.reshape(-1, H).contiguous(), g_w, g_b, g_cls, g_pos, model.patch)
+        return None, None, None, g_w, g_b, g_pos.view(1, T, H), (g_cls.view(1, 1, H) if has_cls else None)
 
 
 class _HeadFn(torch.autograd.Function):
@@ -136,7 +136,8 @@ class ViT(nn.Module, _FlatRoot):
         current = st.consistent
         for i, blk in enumerate(self.enc):
             object.__setattr__(blk, "_parent_views", (st.layout, st.flat, cbuf, f"enc.{i}.", current))
-        out = _StemFn.apply(x, self, self.emb.weight, self.emb.bias, self.pos_emb, self.cls_token)  # vit.py:66-70
+        emb_w_c = st.layout.view(cbuf, "emb.weight") if cbuf is not st.flat else None
+        out = _StemFn.apply(x, self, emb_w_c, self.emb.weight, self.emb.bias, self.pos_emb, self.cls_token)  # vit.py:66-70
         out = self.enc(out)                                                                     # vit.py:71
         fc_w_c = st.layout.view(cbuf, "fc.1.weight")
         return _HeadFn.apply(out, self, fc_w_c, self.fc[0].weight, self.fc[0].bias, self.fc[1].weight, self.fc[1].bias)  # vit.py:72-76
