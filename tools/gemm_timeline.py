@@ -1,0 +1,63 @@
+"""GPU tool: where does a tcgen05 GEMM CTA spend its time?  Cycle counters of the MMA-issuing thread:
+total, waiting for operands (full barrier), waiting for a free accumulator (tmem-empty), and of one epilogue warp
+waiting for the accumulator (tmem-full).   python tools/gemm_timeline.py"""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import vit_cifar_b200 as vb
+from vit_cifar_b200 import ops, _lib
+
+lib = _lib.load()
+lib.vitb_debug_gemm_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+bf = torch.bfloat16
+
+
+def run(kind, M, N, K, mode, extra=""):
+    dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    a = torch.randn(M, K, device="cuda").to(bf); w = torch.randn(N, K, device="cuda").to(bf)
+    bias = torch.zeros(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=bf)
+    res = torch.randn(M, N, device="cuda").to(bf) if "res" in extra else None
+    pre = torch.empty_like(out) if "pre" in extra else None
+    def call():
+        if kind == "fwd":
+            ops.gemm_fwd(a, w, bias, res, out, pre, M, N, K, gelu="gelu" in extra)
+        elif kind == "dgrad":   # dX[M,K] = dY[M,N] W[N,K]
+            ops.gemm_dgrad(out, w, None, a, M, N, K)
+        else:
+            dw = torch.empty(N, K, device="cuda"); db = torch.empty(N, device="cuda")
+            ops.gemm_wgrad(out, a, dw, db, M, N, K)
+    lib.vitb_debug_gemm_timeline(None, mode)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        call()
+    e.record(); torch.cuda.synchronize()
+    us = s.elapsed_time(e) * 100
+    dbg.zero_()
+    lib.vitb_debug_gemm_timeline(dbg.data_ptr(), mode)
+    call(); torch.cuda.synchronize()
+    lib.vitb_debug_gemm_timeline(None, 0)
+    d = dbg.view(148, 8).double()
+    act = d[:, 4] > 0
+    d = d[act]
+    tiles = d[:, 4].mean().item()
+    print(f"{kind:5s} M={M} N={N} K={K} {extra:10s} mode={mode} {us:7.1f} us | per tile cycles: total {d[:,0].mean().item()/tiles:7.0f} "
+          f"wait_operands {d[:,1].mean().item()/tiles:7.0f} wait_acc_free {d[:,2].mean().item()/tiles:7.0f} w_load {d[:,3].mean().item():7.0f} "
+          f"| epilogue wait_acc_full {d[:,5].mean().item()/tiles:7.0f} | tiles/CTA {tiles:.1f}")
+
+
+if __name__ == "__main__":
+    M = 66560
+    for mode in (1, 2):
+        run("fwd", M, 1152, 384, mode)
+        run("fwd", M, 384, 384, mode)
+        run("fwd", M, 384, 384, mode, "res")
+        run("fwd", M, 384, 384, mode, "gelu pre")
+        run("dgrad", M, 384, 384, mode)
+    run("dgrad", M, 1152, 384, 1)
+    run("wgrad", M, 384, 384, 0)
+    run("wgrad", M, 1152, 384, 0)

@@ -37,6 +37,7 @@ struct TcArgs {
   int valid_n;       // RAW epilogue: columns >= valid_n are not stored (patch-embedding wgrad: K = 48 inside a 128 tile)
   int a3_pp;         // > 0: the MN-major A operand is a (B, T, H) tensor read through a 3-D map, a3_pp token rows per image
   int a3_off;        //      first token row used (1 when a cls row is skipped)
+  long long* dbg;    // optional per-CTA cycle counters (tools/gemm_timeline.py); null in production
   EpiParams e;
 };
 
@@ -148,15 +149,20 @@ constexpr uint32_t tmem_cols() {
   return 2 * BN + 32 <= 64 ? 64 : 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
 }
 
-template <int BN, int STAGES, int NSLAB>
+constexpr int kMaxResKB = 6;  // resident-B mode keeps up to 6 k-blocks (K <= 384) of the weight tile in shared memory
+
+// shared-memory plan: [resident B slab (W_RES)] [ring: STAGES x (A | B) tiles] [epilogue slabs / ones operand] [barriers] [tmem slot]
+template <int BN, int STAGES, int NSLAB, bool W_RES>
 struct TcSmem {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kEpiOff = STAGES * kStageBytes;                 // 8 warps x {out, pre, in} slabs
+  static constexpr uint32_t kStageBytes = W_RES ? kABytes : kABytes + kBBytes;
+  static constexpr uint32_t kResBytes = W_RES ? kMaxResKB * kBBytes : 0;
+  static constexpr uint32_t kRingOff = kResBytes;
+  static constexpr uint32_t kEpiOff = kRingOff + STAGES * kStageBytes;
   static constexpr uint32_t kEpiBytes = NSLAB > 0 ? kEpiWarps * NSLAB * kSlabBytes : 2048;  // NSLAB slabs per epilogue warp, or the all-ones wgrad operand
   static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
-  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + kEpiWarps;
+  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + kEpiWarps + 1;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr uint32_t kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
@@ -187,12 +193,15 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB>
+// W_RES ("resident weights", fwd / dgrad with K <= 384): the CTA owns ONE 128-column block of the output, loads that
+// block's B operand (all k-blocks) into shared memory once, and streams only A tiles for its share of the m-blocks —
+// half the L2->SM traffic per tile of the streaming mode, which is what bounds these 384-wide GEMMs.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB, bool W_RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                    const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
-  using S = TcSmem<BN, STAGES, NSLAB>;
+  using S = TcSmem<BN, STAGES, NSLAB, W_RES>;
   static_assert(BN == 128, "epilogue slabs assume two 64-column halves");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -201,8 +210,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  auto a_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes; };
-  auto b_stage = [&](int s) { return smem_base + (uint32_t)s * S::kStageBytes + S::kABytes; };
+  auto a_stage = [&](int s) { return smem_base + S::kRingOff + (uint32_t)s * S::kStageBytes; };
+  auto b_stage = [&](int s) { return smem_base + S::kRingOff + (uint32_t)s * S::kStageBytes + S::kABytes; };
+  auto b_res = [&](int kb) { return smem_base + (uint32_t)kb * S::kBBytes; };  // W_RES: resident k-block kb of B
   const uint32_t epi_base = smem_base + S::kEpiOff;
   const uint32_t bar_base = smem_base + S::kBarOff;
   auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
@@ -210,6 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   auto tfull_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + a) * 8; };
   auto tempty_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + 2 + a) * 8; };
   auto in_bar = [&](int w) { return bar_base + (uint32_t)(2 * STAGES + 4 + w) * 8; };
+  const uint32_t wfull_bar = bar_base + (uint32_t)(2 * STAGES + 4 + kEpiWarps) * 8;
   const uint32_t tmem_slot = bar_base + S::kNumBars * 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOff + S::kNumBars * 8);
 
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_init(tempty_bar(a), kEpiWarps * 32);
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(in_bar(w), 1);
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -247,17 +259,49 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   const int tiles_per_split = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_per_split * p.splits;
+  // work decomposition.  streaming: tile = blockIdx.x + it * gridDim.x over (split, m-block, n-block), n fastest.
+  // W_RES: CTA = (n-block group, member); member walks m-blocks member, member + members, ...
+  const int res_groups = p.num_n_blocks;
+  const int res_members = W_RES ? (int)gridDim.x / res_groups : 1;
+  const int res_group = W_RES ? (int)blockIdx.x % res_groups : 0;
+  const int res_member = W_RES ? (int)blockIdx.x / res_groups : 0;
+  const bool res_active = !W_RES || res_member < res_members;
+  auto get_tile = [&](int it, int& m0, int& n0, int& nblk, int& split) -> bool {
+    if (W_RES) {
+      const int mb = res_member + it * res_members;
+      if (!res_active || mb >= p.num_m_blocks) return false;
+      m0 = mb * BM; nblk = res_group; n0 = nblk * BN; split = 0;
+      return true;
+    }
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    if (tile >= num_tiles) return false;
+    split = tile / tiles_per_split;
+    const int rem = tile - split * tiles_per_split;
+    m0 = (rem / p.num_n_blocks) * BM;
+    nblk = rem % p.num_n_blocks;
+    n0 = nblk * BN;
+    return true;
+  };
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_per_split;
-        const int rem = tile - split * tiles_per_split;
-        const int m0 = (rem / p.num_n_blocks) * BM;
-        const int n0 = (rem % p.num_n_blocks) * BN;
+      if (W_RES && res_active) {  // the weight block of this CTA: every k-block, once
+        const int n0 = res_group * BN;
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.kblocks_total * S::kBBytes);
+        for (int kb = 0; kb < p.kblocks_total; ++kb) {
+          if (!B_MN) {
+            tma_load_2d(b_res(kb), &tma_b, wfull_bar, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_res(kb) + j * (64 * BK * 2), &tma_b, wfull_bar, n0 + j * 64, kb * BK);
+          }
+        }
+      }
+      int m0, n0, nblk, split;
+      for (int it = 0; get_tile(it, m0, n0, nblk, split); ++it) {
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -276,11 +320,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, k0);
           }
-          if (!B_MN) {
-            tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), k0, n0);
-          } else {
+          if (!W_RES) {
+            if (!B_MN) {
+              tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), k0, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_stage(stage) + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + j * 64, k0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_stage(stage) + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + j * 64, k0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -300,27 +346,39 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_per_split;
-        const int rem = tile - split * tiles_per_split;
-        const bool do_bias = want_dbias && (rem % p.num_n_blocks) == 0;
+      long long t_full = 0, t_tempty = 0, t_begin = clock64();
+      if (W_RES && res_active) {
+        mbar_wait(wfull_bar, 0);
+        tc_fence_after();
+      }
+      const long long t_w = clock64() - t_begin;
+      int m0, n0, nblk, split;
+      int ntiles = 0;
+      for (int it = 0; get_tile(it, m0, n0, nblk, split); ++it) {
+        ++ntiles;
+        const bool do_bias = want_dbias && nblk == 0;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        if (p.dbg) t_tempty += clock64() - t0;
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         const uint32_t d_bias = tmem_base + (uint32_t)(2 * BN + acc * 16);
         for (int kb = kb0; kb < kb1; ++kb) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (p.dbg) t_full += clock64() - t0;
+          const uint32_t b_base = W_RES ? b_res(kb) : b_stage(stage);
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
             // K-major: advance 16 elements (32 B) inside the swizzle atom; SBO = 8 rows * 128 B.
             // MN-major: advance 16 k-rows (2048 B); SBO = 8 k-rows * 128 B, LBO = next 64-wide MN atom.
             const uint64_t adesc = A_MN ? make_smem_desc(a_stage(stage) + kk * (UK * 128), BK * 128, 1024)
                                         : make_smem_desc(a_stage(stage) + kk * (UK * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_stage(stage) + kk * (UK * 128), BK * 128, 1024)
-                                        : make_smem_desc(b_stage(stage) + kk * (UK * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_base + kk * (UK * 128), BK * 128, 1024)
+                                        : make_smem_desc(b_base + kk * (UK * 2), 16, 1024);
             const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
             tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
             if (do_bias) tc_mma_bf16(d_bias, adesc, ones_desc, idesc_ones, accum);
@@ -332,6 +390,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
+      if (p.dbg) {
+        long long* d = p.dbg + (size_t)blockIdx.x * 8;
+        d[0] = clock64() - t_begin; d[1] = t_full; d[2] = t_tempty; d[3] = t_w; d[4] = ntiles;
+      }
     }
   } else {
     // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
@@ -339,27 +401,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int quarter = warp & 3;
     const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    // slab 0: output; slab 1: pre-activation (or the input operand when there is no pre-activation); slab 2: input operand
+    // slab 0: output — and, before that, the input operand (residual / z), which is consumed in place; slab 1: pre-activation
     const uint32_t slab_out = epi_base + (uint32_t)(ew * NSLAB + 0) * kSlabBytes;
     const uint32_t slab_pre = epi_base + (uint32_t)(ew * NSLAB + (NSLAB > 1 ? 1 : 0)) * kSlabBytes;
-    const uint32_t slab_in = epi_base + (uint32_t)(ew * NSLAB + (NSLAB > 2 ? 2 : (NSLAB > 1 ? 1 : 0))) * kSlabBytes;
+    const uint32_t slab_in = slab_out;
     int acc = 0;
     uint32_t acc_phase = 0, in_phase = 0;
     const EpiParams& e = p.e;
     bool stores_pending = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_per_split;
-      const int rem = tile - split * tiles_per_split;
-      const int nblk = rem % p.num_n_blocks;
-      const int m0 = (rem / p.num_n_blocks) * BM;
-      const int n0 = nblk * BN + half * 64;
+    int m0, nb0, nblk, split;
+    for (int it = 0; get_tile(it, m0, nb0, nblk, split); ++it) {
+      const int n0 = nb0 + half * 64;
       const int grow = m0 + row_in_tile;
-      if (p.has_in && lane == 0) {  // fetch this warp's residual / z slab while the MMAs of the tile run
-        mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
-        tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
+      if (p.has_in) {  // fetch this warp's residual / z slab while the MMAs of the tile run
+        if (lane == 0) {
+          if (stores_pending) tma_store_wait_read();  // the slab doubles as the output slab of the previous tile
+          mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
+          tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
+        }
       }
+      const long long e0 = (p.dbg && ew == 0 && lane == 0) ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (p.dbg && ew == 0 && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] += clock64() - e0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 64);
       uint32_t raw0[32], raw1[32];
       tc_ld32(taddr, raw0);
@@ -390,7 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         continue;
       }
       if (stores_pending) {  // the previous tile's TMA stores must have finished reading the slabs
-        if (lane == 0) tma_store_wait_read();
+        if (lane == 0 && !p.has_in) tma_store_wait_read();  // (with an input operand lane 0 already waited before refilling the slab)
         __syncwarp();
       }
       if (e.mode == EPI_FWD) {
@@ -505,18 +569,23 @@ struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB, bool W_RES>
 static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES, NSLAB>;
+  using S = TcSmem<BN, STAGES, NSLAB, W_RES>;
   static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, NSLAB>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, NSLAB, W_RES>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
     configured = true;
   }
-  const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  int grid;
+  if (W_RES) {
+    grid = (kNumSMs / args.num_n_blocks) * args.num_n_blocks;  // (members per column block) x (column blocks)
+  } else {
+    const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
+    grid = tiles < kNumSMs ? tiles : kNumSMs;
+  }
   kern<<<grid, kTcThreads, S::kDynBytes, st>>>(m.a, m.b, m.out, m.pre, m.in, args);
   VITB_LAUNCH_OK();
   return 0;
@@ -524,15 +593,30 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
 
 constexpr int kBN = 128;
 
+static long long* g_tc_dbg = nullptr;  // set through vitb_debug_gemm_timeline (tools only)
+static int g_tc_force_mode = 0;        // 0 auto, 1 never resident, 2 always resident (when legal)
+
+static bool use_resident_weights(const TcArgs& a) {
+  if (a.e.mode == EPI_RAW_F32 || a.splits != 1 || a.kblocks_total > kMaxResKB || a.num_n_blocks > kNumSMs) return false;
+  if (g_tc_force_mode == 1) return false;
+  if (g_tc_force_mode == 2) return true;
+  const int members = kNumSMs / a.num_n_blocks;
+  return a.num_m_blocks >= 2 * members;  // enough row blocks per CTA to amortise loading the weight block
+}
+
 // The smem ring gets whatever the epilogue slabs leave free: more TMA bytes in flight when the epilogue needs fewer slabs.
-//   slabs per epilogue warp = 1 (output) + pre-activation + input operand;  0 = fp32 direct-store epilogue (wgrad)
+//   slabs per epilogue warp = 1 (output, shared with the input operand) + pre-activation;  0 = fp32 direct-store epilogue (wgrad)
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
-  if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 6, 0>(m, args, st);
-  const int nslab = 1 + (args.has_pre ? 1 : 0) + (args.has_in ? 1 : 0);
-  if (nslab == 1) return launch_tc_impl<BN, A_MN, B_MN, 6, 1>(m, args, st);
-  if (nslab == 2) return launch_tc_impl<BN, A_MN, B_MN, 5, 2>(m, args, st);
-  return launch_tc_impl<BN, A_MN, B_MN, 4, 3>(m, args, st);
+static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
+  TcArgs args = args_in;
+  args.dbg = g_tc_dbg;
+  if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 6, 0, false>(m, args, st);
+  if (!A_MN && use_resident_weights(args)) {
+    if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 4, 2, true>(m, args, st);
+    return launch_tc_impl<BN, A_MN, B_MN, 6, 1, true>(m, args, st);
+  }
+  if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 5, 2, false>(m, args, st);
+  return launch_tc_impl<BN, A_MN, B_MN, 6, 1, false>(m, args, st);
 }
 
 // K needs only a 16-byte row pitch: a partial last k-block is zero-filled by TMA
@@ -614,6 +698,13 @@ int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias,
 using namespace vitb;
 
 extern "C" {
+
+/* tools only (not in vitb200.h): dbg = device buffer of 148*8 int64 cycle counters, or NULL; mode 0 auto / 1 streaming / 2 resident */
+int vitb_debug_gemm_timeline(long long* dbg, int mode) {
+  g_tc_dbg = dbg;
+  g_tc_force_mode = mode;
+  return 0;
+}
 
 int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, const void* residual, void* c, void* preact,
                            int M, int N, int K, int flags, int dt, void* stream) {
