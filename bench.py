@@ -354,7 +354,13 @@ def run_ours(args):
                 row["roofline"] = r
             json.dump({"ms_per_step_graph": ms_dev / args.steps, "img_per_s": value, "kernels": table}, open(args.kernel_table, "w"), indent=1)
     if world > 1:
-        dist.destroy_process_group()
+        # All ranks are done (barrier), results are printed.  Tearing NCCL down while captured CUDA graphs still reference
+        # its communicator hung on B200 (observed at N=2), so leave without the interpreter/NCCL teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -9,6 +9,7 @@ exchange overlaps the remaining backward; the 1/world_size of DDP's mean is fold
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -25,7 +26,7 @@ from .vit import ViT
 class TrainEngine:
     def __init__(self, model: ViT, batch_size: int, smoothing: float = 0.1, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 5e-5, process_group=None, use_graph: bool = True,
-                 overlap_comm: bool = True):
+                 overlap_comm: bool = False):
         ops.require_device()
         self.model = model
         self.B = int(batch_size)
@@ -37,7 +38,11 @@ class TrainEngine:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.use_graph = use_graph
-        self.overlap_comm = overlap_comm and self.world > 1
+        # "overlap": per-layer buckets on a side stream while backward continues; "single": one all-reduce of the whole flat
+        # gradient buffer after backward (no SM contention between NCCL's CTAs and the persistent GEMM kernels)
+        mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "single")
+        self._dp_mode = mode
+        self.overlap_comm = (mode == "overlap") and self.world > 1
         if model.p_drop > 0.0:
             raise NotImplementedError("dropout > 0 is not implemented in the fused training step (reference default 0.0)")
 
@@ -109,10 +114,15 @@ class TrainEngine:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())
 
     # -- the kernel sequence ----------------------------------------------------------------------
-    def _allreduce(self, bucket: Tuple[int, int]) -> None:
+    def _allreduce(self, bucket: Tuple[int, int], last: bool = False) -> None:
         if self.world == 1:
             return
-        allreduce_bucket(self.G, bucket, self.pg, self._comm_stream)
+        if self._dp_mode == "none":  # diagnostic only: replicas drift apart
+            return
+        if self.overlap_comm:
+            allreduce_bucket(self.G, bucket, self.pg, self._comm_stream)
+        elif last:
+            allreduce_bucket(self.G, (0, self.n), self.pg, None)
 
     def _body(self) -> None:
         m, dm = self.model, self.dm
@@ -138,7 +148,7 @@ class TrainEngine:
             self._allreduce(self.buckets[1 + i])
         g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
         Fn.stem_bwd(self.img, words, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
-        self._allreduce(self.buckets[0])
+        self._allreduce(self.buckets[0], last=True)
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         n = self.n
