@@ -13,7 +13,7 @@ lib.vitb_debug_gemm_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
 bf = torch.bfloat16
 
 
-def run(kind, M, N, K, mode, extra=""):
+def run(kind, M, N, K, mode, extra="", flags=0):
     dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
     a = torch.randn(M, K, device="cuda").to(bf); w = torch.randn(N, K, device="cuda").to(bf)
     bias = torch.zeros(N, device="cuda"); out = torch.empty(M, N, device="cuda", dtype=bf)
@@ -28,17 +28,31 @@ def run(kind, M, N, K, mode, extra=""):
             dw = torch.empty(N, K, device="cuda"); db = torch.empty(N, device="cuda")
             ops.gemm_wgrad(out, a, dw, db, M, N, K)
     lib.vitb_debug_gemm_timeline(None, mode)
+    if kind == "wgrad":
+        dw = torch.empty(N, K, device="cuda"); db = torch.empty(N, device="cuda")
+        def call():
+            ops.gemm_wgrad(out, a, dw, db, M, N, K)
     for _ in range(3):
         call()
     torch.cuda.synchronize()
+    # GPU time of 10 back-to-back launches replayed from a CUDA graph (eager launches are CPU-bound at these sizes)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        call()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(10):
+                call()
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(10):
-        call()
+    g.replay()
     e.record(); torch.cuda.synchronize()
     us = s.elapsed_time(e) * 100
     dbg.zero_()
-    lib.vitb_debug_gemm_timeline(dbg.data_ptr(), mode)
+    lib.vitb_debug_gemm_timeline(dbg.data_ptr(), mode | (flags << 8))
     call(); torch.cuda.synchronize()
     lib.vitb_debug_gemm_timeline(None, 0)
     d = dbg.view(148, 8).double()
@@ -47,17 +61,19 @@ def run(kind, M, N, K, mode, extra=""):
     tiles = d[:, 4].mean().item()
     print(f"{kind:5s} M={M} N={N} K={K} {extra:10s} mode={mode} {us:7.1f} us | per tile cycles: total {d[:,0].mean().item()/tiles:7.0f} "
           f"wait_operands {d[:,1].mean().item()/tiles:7.0f} wait_acc_free {d[:,2].mean().item()/tiles:7.0f} w_load {d[:,3].mean().item():7.0f} "
-          f"| epilogue wait_acc_full {d[:,5].mean().item()/tiles:7.0f} | tiles/CTA {tiles:.1f}")
+          f"| epilogue wait_acc_full {d[:,5].mean().item()/tiles:7.0f} | issue {d[:,6].mean().item()/tiles:6.0f} commit {d[:,7].mean().item()/tiles:5.0f} | tiles/CTA {tiles:.1f} flags={flags}")
 
 
 if __name__ == "__main__":
     M = 66560
-    for mode in (1, 2):
-        run("fwd", M, 1152, 384, mode)
-        run("fwd", M, 384, 384, mode)
-        run("fwd", M, 384, 384, mode, "res")
-        run("fwd", M, 384, 384, mode, "gelu pre")
-        run("dgrad", M, 384, 384, mode)
-    run("dgrad", M, 1152, 384, 1)
-    run("wgrad", M, 384, 384, 0)
-    run("wgrad", M, 1152, 384, 0)
+    for pf_t, pf_k, ns1 in ((0, 0, 0), (1, 4, 0), (2, 8, 0), (4, 16, 0), (2, 8, 0x10)):
+        lib.vitb_debug_gemm_prefetch(pf_t, pf_k)
+        print(f"prefetch distance: {pf_t} tiles / {pf_k} k-blocks; " + ("single stream" if ns1 else "dual stream"))
+        run("fwd", M, 384, 384, 2 | ns1)
+        run("fwd", M, 1152, 384, 2 | ns1)
+        run("fwd", M, 384, 384, 2 | ns1, "res")
+        run("fwd", M, 384, 384, 2 | ns1, "gelu pre")
+        run("dgrad", M, 384, 384, 2 | ns1)
+        run("dgrad", M, 1152, 384, 1 | ns1)
+        run("wgrad", M, 384, 384, 0 | ns1)
+        run("wgrad", M, 1152, 384, 0 | ns1)

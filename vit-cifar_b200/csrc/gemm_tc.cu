@@ -2,9 +2,13 @@
 // tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue with fused
 // bias / GELU / residual / pre-activation save / GELU-backward, or fp32 split-K partials.
 //
-// One persistent kernel, three roles (warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
-// warps 2-9: epilogue), two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of
-// tile i+1.  The epilogue never touches global memory with per-thread row accesses: every epilogue
+// One persistent kernel, three roles: TMA producer warp(s), MMA issuer warp(s), 8 epilogue warps; TMEM
+// accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// NS = 2 ("dual stream"): a 128x128x16 MMA occupies the tensor pipe for 64 cycles, but ONE issuing thread
+// needs ~50 cycles per MMA plus ~300 per barrier wait / tcgen05.commit round trip (measured, tools/mma_bench.cu
+// and tools/gemm_timeline.py), so a single producer/issuer pair leaves the pipe half idle at this tile width.
+// Two independent producer/issuer pairs ("streams") walk alternate tiles of the CTA's tile list with their own
+// smem rings, barriers and TMEM accumulators (and share the resident weight block); the pipe interleaves them.  The epilogue never touches global memory with per-thread row accesses: every epilogue
 // warp owns a 32-row x 64-column slab, stages bf16 results in 128B-swizzled shared memory and moves
 // whole slabs with TMA (store for C / pre-activation, load for the residual / GELU-backward operand).
 // wgrad additionally computes the bias gradient with one extra N=16 MMA per k-step against an
@@ -23,7 +27,8 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 along the contiguous dimension
 constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarps = 8;
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int tc_threads(int ns) { return (2 * ns + kEpiWarps) * 32; }  // NS TMA warps + NS MMA warps + 8 epilogue warps
+constexpr uint32_t kTmemCols = 512;  // NS x ACC accumulators of 128 columns (+ 16-column bias-gradient accumulators in wgrad)
 constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16, 128B swizzle
 
 struct TcArgs {
@@ -38,6 +43,9 @@ struct TcArgs {
   int a3_pp;         // > 0: the MN-major A operand is a (B, T, H) tensor read through a 3-D map, a3_pp token rows per image
   int a3_off;        //      first token row used (1 when a cls row is skipped)
   long long* dbg;    // optional per-CTA cycle counters (tools/gemm_timeline.py); null in production
+  int pf_tiles;      // fwd/dgrad: prefetch the A tile this many tiles (per stream) ahead into L2; 0 = off
+  int pf_kblocks;    // wgrad: prefetch operands this many k-blocks ahead into L2; 0 = off
+  int dbg_flags;     // tools only: 1 = epilogue skips its work (accumulator handed straight back), 2 = producer loads nothing
   EpiParams e;
 };
 
@@ -87,6 +95,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a box: costs no shared memory, so operands can be requested from HBM much further ahead than the ring holds
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
@@ -132,6 +144,8 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+
 // shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -143,26 +157,39 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// two accumulator stages of BN columns + two 16-column bias-gradient accumulators (wgrad)
-template <int BN>
-constexpr uint32_t tmem_cols() {
-  return 2 * BN + 32 <= 64 ? 64 : 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
+// The high word of every descriptor used here is one constant (SBO = 1024 B, version 1, SWIZZLE_128B); the low word is
+// (address >> 4) | (LBO >> 4) << 16, so walking k or the ring is a single add on a precomputed low word.
+constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; }
+// one lane of a converged warp; code under `if (elect_one())` is compiled as warp-uniform (no per-lane waterfall loops
+// around the uniform-datapath tcgen05 / TMA instructions, which cost more than the MMAs they issue)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 constexpr int kMaxResKB = 6;  // resident-B mode keeps up to 6 k-blocks (K <= 384) of the weight tile in shared memory
 
-// shared-memory plan: [resident B slab (W_RES)] [ring: STAGES x (A | B) tiles] [epilogue slabs / ones operand] [barriers] [tmem slot]
-template <int BN, int STAGES, int NSLAB, bool W_RES>
+// shared-memory plan: [resident B slab (W_RES)] [ring: STAGES x KPS x (A | B) tiles] [epilogue slabs / ones operand] [barriers] [tmem slot]
+// A ring stage holds KPS consecutive k-blocks behind ONE full/empty barrier pair: the MMA-issuing thread pays its
+// wait + commit round trip (which the tensor pipe cannot hide: tools/mma_bench.cu) once per 4*KPS MMAs.
+template <int BN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
 struct TcSmem {
+  static constexpr int kAcc = (NS == 2 && NSLAB == 0) ? 1 : 2;  // TMEM accumulator stages per stream (wgrad items are long: 1 is enough)
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
-  static constexpr uint32_t kStageBytes = W_RES ? kABytes : kABytes + kBBytes;
+  static constexpr uint32_t kSubBytes = W_RES ? kABytes : kABytes + kBBytes;  // one k-block
+  static constexpr uint32_t kStageBytes = KPS * kSubBytes;
   static constexpr uint32_t kResBytes = W_RES ? kMaxResKB * kBBytes : 0;
   static constexpr uint32_t kRingOff = kResBytes;
-  static constexpr uint32_t kEpiOff = kRingOff + STAGES * kStageBytes;
+  static constexpr uint32_t kRingBytes = STAGES * kStageBytes;  // per stream
+  static constexpr uint32_t kEpiOff = kRingOff + NS * kRingBytes;
   static constexpr uint32_t kEpiBytes = NSLAB > 0 ? kEpiWarps * NSLAB * kSlabBytes : 2048;  // NSLAB slabs per epilogue warp, or the all-ones wgrad operand
   static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
-  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + kEpiWarps + 1;
+  static constexpr uint32_t kBarsPerStream = 2 * STAGES + 4;  // full[STAGES] empty[STAGES] tfull[2] tempty[2]
+  static constexpr uint32_t kNumBars = NS * kBarsPerStream + kEpiWarps + 1;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr uint32_t kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
@@ -196,12 +223,14 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // W_RES ("resident weights", fwd / dgrad with K <= 384): the CTA owns ONE 128-column block of the output, loads that
 // block's B operand (all k-blocks) into shared memory once, and streams only A tiles for its share of the m-blocks —
 // half the L2->SM traffic per tile of the streaming mode, which is what bounds these 384-wide GEMMs.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB, bool W_RES>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
+__global__ void __launch_bounds__(tc_threads(NS), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                    const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
-  using S = TcSmem<BN, STAGES, NSLAB, W_RES>;
+  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES>;
+  constexpr int ACC = S::kAcc;
+  static_assert(NS * ACC * BN + NS * 16 <= (int)kTmemCols || NSLAB > 0, "TMEM plan");
   static_assert(BN == 128, "epilogue slabs assume two 64-column halves");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,17 +239,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  auto a_stage = [&](int s) { return smem_base + S::kRingOff + (uint32_t)s * S::kStageBytes; };
-  auto b_stage = [&](int s) { return smem_base + S::kRingOff + (uint32_t)s * S::kStageBytes + S::kABytes; };
+  // st = stream, s = ring stage, j = k-block inside the stage
+  auto a_stage = [&](int st, int s, int j) {
+    return smem_base + S::kRingOff + (uint32_t)st * S::kRingBytes + (uint32_t)s * S::kStageBytes + (uint32_t)j * S::kSubBytes;
+  };
+  auto b_stage = [&](int st, int s, int j) { return a_stage(st, s, j) + S::kABytes; };
   auto b_res = [&](int kb) { return smem_base + (uint32_t)kb * S::kBBytes; };  // W_RES: resident k-block kb of B
   const uint32_t epi_base = smem_base + S::kEpiOff;
   const uint32_t bar_base = smem_base + S::kBarOff;
-  auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
-  auto empty_bar = [&](int s) { return bar_base + (uint32_t)(STAGES + s) * 8; };
-  auto tfull_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + a) * 8; };
-  auto tempty_bar = [&](int a) { return bar_base + (uint32_t)(2 * STAGES + 2 + a) * 8; };
-  auto in_bar = [&](int w) { return bar_base + (uint32_t)(2 * STAGES + 4 + w) * 8; };
-  const uint32_t wfull_bar = bar_base + (uint32_t)(2 * STAGES + 4 + kEpiWarps) * 8;
+  auto full_bar = [&](int st, int s) { return bar_base + (uint32_t)(st * S::kBarsPerStream + s) * 8; };
+  auto empty_bar = [&](int st, int s) { return bar_base + (uint32_t)(st * S::kBarsPerStream + STAGES + s) * 8; };
+  auto tfull_bar = [&](int st, int a) { return bar_base + (uint32_t)(st * S::kBarsPerStream + 2 * STAGES + a) * 8; };
+  auto tempty_bar = [&](int st, int a) { return bar_base + (uint32_t)(st * S::kBarsPerStream + 2 * STAGES + 2 + a) * 8; };
+  auto in_bar = [&](int w) { return bar_base + (uint32_t)(NS * S::kBarsPerStream + w) * 8; };
+  const uint32_t wfull_bar = bar_base + (uint32_t)(NS * S::kBarsPerStream + kEpiWarps) * 8;
+  // TMEM columns: accumulator a of stream st, and the stream's 16-column bias-gradient accumulator (wgrad)
+  auto acc_col = [&](int st, int a) { return (uint32_t)((st * ACC + a) * BN); };
+  auto bias_col = [&](int st, int a) { return (uint32_t)(NS * ACC * BN + (st * ACC + a) * 16); };
   const uint32_t tmem_slot = bar_base + S::kNumBars * 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOff + S::kNumBars * 8);
 
@@ -230,26 +265,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
     if (p.e.mode != EPI_RAW_F32) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_out) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps * 32);
+    for (int st = 0; st < NS; ++st) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar(st, s), 1);
+        mbar_init(empty_bar(st, s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(st, a), 1);
+        mbar_init(tempty_bar(st, a), kEpiWarps);  // one arrival per epilogue warp
+      }
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(in_bar(w), 1);
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols<BN>()) : "memory");
+  if (warp == NS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (want_dbias && warp >= 2) {
+  if (want_dbias && warp >= 2 * NS) {
     // all-ones bf16 operand (16 rows x 128 B, any layout reads ones); overlays the unused epilogue slabs
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + S::kEpiOff);
-    for (int i = threadIdx.x - 64; i < 2048 / 4; i += kEpiWarps * 32) ones[i] = 0x3F803F80u;
+    for (int i = threadIdx.x - 64 * NS; i < 2048 / 4; i += kEpiWarps * 32) ones[i] = 0x3F803F80u;
     fence_async_smem();
   }
   tc_fence_before();
@@ -283,121 +320,184 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     return true;
   };
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      if (W_RES && res_active) {  // the weight block of this CTA: every k-block, once
-        const int n0 = res_group * BN;
-        mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.kblocks_total * S::kBBytes);
-        for (int kb = 0; kb < p.kblocks_total; ++kb) {
-          if (!B_MN) {
-            tma_load_2d(b_res(kb), &tma_b, wfull_bar, kb * BK, n0);
-          } else {
+  if (warp < NS) {
+    // ================= TMA producer of stream `warp`: the whole warp walks the loop, one elected lane issues =================
+    const int st_ = warp;
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    if (W_RES && res_active && leader && st_ == 0) {  // the weight block of this CTA: every k-block, once
+      const int n0 = res_group * BN;
+      mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.kblocks_total * S::kBBytes);
+      for (int kb = 0; kb < p.kblocks_total; ++kb) {
+        if (!B_MN) {
+          tma_load_2d(b_res(kb), &tma_b, wfull_bar, kb * BK, n0);
+        } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_res(kb) + j * (64 * BK * 2), &tma_b, wfull_bar, n0 + j * 64, kb * BK);
-          }
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_res(kb) + j * (64 * BK * 2), &tma_b, wfull_bar, n0 + j * 64, kb * BK);
         }
       }
-      int m0, n0, nblk, split;
-      for (int it = 0; get_tile(it, m0, n0, nblk, split); ++it) {
-        const int kb0 = split * p.kblocks_per_split;
-        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
-          const int k0 = kb * BK;
-          if (!A_MN) {
-            tma_load_2d(a_stage(stage), &tma_a, full_bar(stage), k0, m0);
-          } else if (p.a3_pp > 0) {
-            // 64 reduction rows = token rows [a3_off + k0 % pp, +64) of image k0 / pp  (pp >= 64), or all pp token rows of
-            // 64 / pp consecutive images (pp < 64); the box of the 3-D map has exactly that shape
-            const int img = k0 / p.a3_pp, tok = p.a3_off + (p.a3_pp >= 64 ? k0 % p.a3_pp : 0);
+    }
+    __syncwarp();
+    int m0, n0, nblk, split;
+    for (int it = st_; get_tile(it, m0, n0, nblk, split); it += NS) {
+      const int kb0 = split * p.kblocks_per_split;
+      const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+      if (!A_MN && p.pf_tiles > 0 && leader) {
+        // The ring holds < 1 tile of A per stream, HBM latency under load is several tile times: ask L2 for the A rows of a
+        // tile further ahead.  Every row block is requested once: resident mode splits the k-blocks over the CTAs that share
+        // the row block (one per column block, same pace); streaming mode lets the CTA at column block 0 do it.
+        if (W_RES) {
+          int pm0, pn0, pnblk, psplit;
+          if (get_tile(it + p.pf_tiles * NS, pm0, pn0, pnblk, psplit))
+            for (int kb = res_group; kb < p.kblocks_total; kb += res_groups) tma_prefetch_2d(&tma_a, kb * BK, pm0);
+        } else if (nblk == 0) {
+          const int pm0 = m0 + ceil_div_dev(p.pf_tiles * NS * (int)gridDim.x, p.num_n_blocks) * BM;
+          if (pm0 < p.num_m_blocks * BM)
+            for (int kb = kb0; kb < kb1; ++kb) tma_prefetch_2d(&tma_a, kb * BK, pm0);
+        }
+      }
+      for (int kb = kb0; kb < kb1; kb += KPS) {
+        const int nsub = min(KPS, kb1 - kb);
+        if (A_MN && p.pf_kblocks > 0 && leader && p.a3_pp == 0) {
+          // wgrad: both operands stream from HBM along the reduction; the CTAs of one split share them (A over the column
+          // blocks, B over the row blocks), so the one at block 0 of the other dimension prefetches
+          const int pk = (kb + p.pf_kblocks) * BK;
+          if (kb + p.pf_kblocks < kb1) {
+            if (nblk == 0) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_3d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, tok, img);
-          } else {
+              for (int q = 0; q < BM / 64; ++q) tma_prefetch_2d(&tma_a, m0 + q * 64, pk);
+            }
+            if (m0 == 0) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_stage(stage) + j * (64 * BK * 2), &tma_a, full_bar(stage), m0 + j * 64, k0);
-          }
-          if (!W_RES) {
-            if (!B_MN) {
-              tma_load_2d(b_stage(stage), &tma_b, full_bar(stage), k0, n0);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_stage(stage) + j * (64 * BK * 2), &tma_b, full_bar(stage), n0 + j * 64, k0);
+              for (int q = 0; q < BN / 64; ++q) tma_prefetch_2d(&tma_b, n0 + q * 64, pk);
             }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        mbar_wait(empty_bar(st_, stage), phase ^ 1u);
+        const uint32_t fbar = full_bar(st_, stage);
+        if (leader && (p.dbg_flags & 2)) {
+          mbar_arrive(fbar);
+        } else if (leader) {
+          mbar_arrive_expect_tx(fbar, (uint32_t)nsub * S::kSubBytes);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nsub) {
+              const int k0 = (kb + j) * BK;
+              const uint32_t sa = a_stage(st_, stage, j), sb = b_stage(st_, stage, j);
+              if (!A_MN) {
+                tma_load_2d(sa, &tma_a, fbar, k0, m0);
+              } else if (p.a3_pp > 0) {
+                // 64 reduction rows = token rows [a3_off + k0 % pp, +64) of image k0 / pp  (pp >= 64), or all pp token rows of
+                // 64 / pp consecutive images (pp < 64); the box of the 3-D map has exactly that shape
+                const int img = k0 / p.a3_pp, tok = p.a3_off + (p.a3_pp >= 64 ? k0 % p.a3_pp : 0);
+#pragma unroll
+                for (int q = 0; q < BM / 64; ++q) tma_load_3d(sa + q * (64 * BK * 2), &tma_a, fbar, m0 + q * 64, tok, img);
+              } else {
+#pragma unroll
+                for (int q = 0; q < BM / 64; ++q) tma_load_2d(sa + q * (64 * BK * 2), &tma_a, fbar, m0 + q * 64, k0);
+              }
+              if (!W_RES) {
+                if (!B_MN) {
+                  tma_load_2d(sb, &tma_b, fbar, k0, n0);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < BN / 64; ++q) tma_load_2d(sb + q * (64 * BK * 2), &tma_b, fbar, n0 + q * 64, k0);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // bias-gradient MMA: same A, B = all-ones K-major tile, N = 16
-      const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
-                                  ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint64_t ones_desc = make_smem_desc(epi_base, 16, 1024);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      long long t_full = 0, t_tempty = 0, t_begin = clock64();
-      if (W_RES && res_active) {
-        mbar_wait(wfull_bar, 0);
+  } else if (warp < 2 * NS) {
+    // ================= MMA issuer of stream `warp - NS`: the whole warp walks the loop, one elected lane issues =================
+    const int st_ = warp - NS;
+    const bool leader = elect_one();
+    // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // bias-gradient MMA: same A, B = all-ones K-major tile, N = 16
+    const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
+                                ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint64_t ones_desc = make_smem_desc(epi_base, 16, 1024);
+    // K-major: a k-step is 16 elements (32 B) inside the swizzle atom, LBO unused (16).  MN-major: a k-step is 16 k-rows
+    // (2048 B), LBO = distance between 64-wide MN atoms.
+    constexpr uint32_t kALbo = A_MN ? BK * 128 : 16, kBLbo = B_MN ? BK * 128 : 16;
+    constexpr uint32_t kAStep = (A_MN ? UK * 128 : UK * 2) >> 4, kBStep = (B_MN ? UK * 128 : UK * 2) >> 4;
+    const uint32_t a_lo0 = desc_lo(a_stage(st_, 0, 0), kALbo);
+    const uint32_t b_lo0 = desc_lo(W_RES ? b_res(0) : b_stage(st_, 0, 0), kBLbo);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long t_full = 0, t_tempty = 0, t_issue = 0, t_commit = 0, t_begin = clock64();
+    if (W_RES && res_active) {
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+    }
+    const long long t_w = clock64() - t_begin;
+    int m0, n0, nblk, split;
+    int ntiles = 0;
+    for (int it = st_; get_tile(it, m0, n0, nblk, split); it += NS) {
+      ++ntiles;
+      const bool do_bias = want_dbias && nblk == 0;
+      const int kb0 = split * p.kblocks_per_split;
+      const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+      long long t0 = p.dbg ? clock64() : 0;
+      mbar_wait(tempty_bar(st_, acc), acc_phase ^ 1u);
+      tc_fence_after();
+      if (p.dbg) t_tempty += clock64() - t0;
+      const uint32_t d_tmem = tmem_base + acc_col(st_, acc);
+      const uint32_t d_bias = tmem_base + bias_col(st_, acc);
+      for (int kb = kb0; kb < kb1; kb += KPS) {
+        const int nsub = min(KPS, kb1 - kb);
+        t0 = p.dbg ? clock64() : 0;
+        mbar_wait(full_bar(st_, stage), phase);
         tc_fence_after();
-      }
-      const long long t_w = clock64() - t_begin;
-      int m0, n0, nblk, split;
-      int ntiles = 0;
-      for (int it = 0; get_tile(it, m0, n0, nblk, split); ++it) {
-        ++ntiles;
-        const bool do_bias = want_dbias && nblk == 0;
-        const int kb0 = split * p.kblocks_per_split;
-        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
-        long long t0 = p.dbg ? clock64() : 0;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        if (p.dbg) t_tempty += clock64() - t0;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t d_bias = tmem_base + (uint32_t)(2 * BN + acc * 16);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          t0 = p.dbg ? clock64() : 0;
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (p.dbg) t_full += clock64() - t0;
-          const uint32_t b_base = W_RES ? b_res(kb) : b_stage(stage);
+        if (p.dbg) t_full += clock64() - t0;
+        if (leader) {
+          const long long ti0 = p.dbg ? clock64() : 0;
 #pragma unroll
-          for (int kk = 0; kk < BK / UK; ++kk) {
-            // K-major: advance 16 elements (32 B) inside the swizzle atom; SBO = 8 rows * 128 B.
-            // MN-major: advance 16 k-rows (2048 B); SBO = 8 k-rows * 128 B, LBO = next 64-wide MN atom.
-            const uint64_t adesc = A_MN ? make_smem_desc(a_stage(stage) + kk * (UK * 128), BK * 128, 1024)
-                                        : make_smem_desc(a_stage(stage) + kk * (UK * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_base + kk * (UK * 128), BK * 128, 1024)
-                                        : make_smem_desc(b_base + kk * (UK * 2), 16, 1024);
-            const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-            if (do_bias) tc_mma_bf16(d_bias, adesc, ones_desc, idesc_ones, accum);
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nsub) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)(stage * KPS + j) * (S::kSubBytes >> 4);
+              const uint32_t b_lo = b_lo0 + (W_RES ? (uint32_t)(kb + j) * (S::kBBytes >> 4) : (uint32_t)(stage * KPS + j) * (S::kSubBytes >> 4));
+              const uint32_t first = (kb + j) > kb0 ? 1u : 0u;
+              if (!do_bias) {
+#pragma unroll
+                for (int kk = 0; kk < BK / UK; ++kk)
+                  tc_mma_bf16(d_tmem, desc_from_lo(a_lo + kk * kAStep), desc_from_lo(b_lo + kk * kBStep), idesc, kk > 0 ? 1u : first);
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < BK / UK; ++kk) {
+                  tc_mma_bf16(d_tmem, desc_from_lo(a_lo + kk * kAStep), desc_from_lo(b_lo + kk * kBStep), idesc, kk > 0 ? 1u : first);
+                  tc_mma_bf16(d_bias, desc_from_lo(a_lo + kk * kAStep), ones_desc, idesc_ones, kk > 0 ? 1u : first);
+                }
+              }
+            }
           }
-          tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          const long long ti1 = p.dbg ? clock64() : 0;
+          tc_commit(empty_bar(st_, stage));  // frees the smem slot once these MMAs have read it
+          if (p.dbg) { t_issue += ti1 - ti0; t_commit += clock64() - ti1; }
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (p.dbg) {
-        long long* d = p.dbg + (size_t)blockIdx.x * 8;
-        d[0] = clock64() - t_begin; d[1] = t_full; d[2] = t_tempty; d[3] = t_w; d[4] = ntiles;
-      }
+      if (leader) tc_commit(tfull_bar(st_, acc));  // accumulator complete
+      __syncwarp();
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (p.dbg && leader && st_ == 0) {
+      long long* d = p.dbg + (size_t)blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = t_full; d[2] = t_tempty; d[3] = t_w; d[4] = ntiles; d[6] = t_issue; d[7] = t_commit;
     }
   } else {
-    // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
-    const int ew = warp - 2;
+    // ================= epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = ew / 4.  Tiles are drained in
+    // the CTA's tile order, alternating between the streams ==========
+    const int ew = warp - 2 * NS;
     const int quarter = warp & 3;
     const int half = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
@@ -405,12 +505,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t slab_out = epi_base + (uint32_t)(ew * NSLAB + 0) * kSlabBytes;
     const uint32_t slab_pre = epi_base + (uint32_t)(ew * NSLAB + (NSLAB > 1 ? 1 : 0)) * kSlabBytes;
     const uint32_t slab_in = slab_out;
-    int acc = 0;
-    uint32_t acc_phase = 0, in_phase = 0;
+    uint32_t in_phase = 0;
     const EpiParams& e = p.e;
     bool stores_pending = false;
     int m0, nb0, nblk, split;
     for (int it = 0; get_tile(it, m0, nb0, nblk, split); ++it) {
+      const int st_ = it % NS, jt = it / NS;           // stream, and the tile's index inside the stream
+      const int acc = jt % ACC;
+      const uint32_t acc_phase = (uint32_t)(jt / ACC) & 1u;
       const int n0 = nb0 + half * 64;
       const int grow = m0 + row_in_tile;
       if (p.has_in) {  // fetch this warp's residual / z slab while the MMAs of the tile run
@@ -421,21 +523,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
       const long long e0 = (p.dbg && ew == 0 && lane == 0) ? clock64() : 0;
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(st_, acc), acc_phase);
       tc_fence_after();
+      if (p.dbg_flags & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(st_, acc));
+        continue;
+      }
       if (p.dbg && ew == 0 && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] += clock64() - e0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col(st_, acc) + (uint32_t)(half * 64);
       uint32_t raw0[32], raw1[32];
       tc_ld32(taddr, raw0);
       tc_ld32(taddr + 32u, raw1);
       uint32_t rawb[16];
       const bool do_bias = want_dbias && nblk == 0 && half == 0;
-      if (do_bias) tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * BN + acc * 16), rawb);
+      if (do_bias) tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + bias_col(st_, acc), rawb);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(st_, acc));  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
 
       float v[64];
 #pragma unroll
@@ -511,9 +618,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   // teardown: everyone done with TMEM before the owning warp frees it
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == NS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols<BN>()) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -569,11 +676,11 @@ struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES, int NSLAB, bool W_RES>
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
 static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES, NSLAB, W_RES>;
+  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES>;
   static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, NSLAB, W_RES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NS, STAGES, KPS, NSLAB, W_RES>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
@@ -586,7 +693,7 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
     const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
     grid = tiles < kNumSMs ? tiles : kNumSMs;
   }
-  kern<<<grid, kTcThreads, S::kDynBytes, st>>>(m.a, m.b, m.out, m.pre, m.in, args);
+  kern<<<grid, tc_threads(NS), S::kDynBytes, st>>>(m.a, m.b, m.out, m.pre, m.in, args);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -595,6 +702,8 @@ constexpr int kBN = 128;
 
 static long long* g_tc_dbg = nullptr;  // set through vitb_debug_gemm_timeline (tools only)
 static int g_tc_force_mode = 0;        // 0 auto, 1 never resident, 2 always resident (when legal)
+static int g_tc_dbg_flags = 0;
+static int g_tc_pf_tiles = 2, g_tc_pf_kblocks = 8;  // L2 prefetch distances (tools can change them)
 
 static bool use_resident_weights(const TcArgs& a) {
   if (a.e.mode == EPI_RAW_F32 || a.splits != 1 || a.kblocks_total > kMaxResKB || a.num_n_blocks > kNumSMs) return false;
@@ -604,19 +713,36 @@ static bool use_resident_weights(const TcArgs& a) {
   return a.num_m_blocks >= 2 * members;  // enough row blocks per CTA to amortise loading the weight block
 }
 
-// The smem ring gets whatever the epilogue slabs leave free: more TMA bytes in flight when the epilogue needs fewer slabs.
+// The smem rings get whatever the resident weights and the epilogue slabs leave free (227 KB per CTA):
 //   slabs per epilogue warp = 1 (output, shared with the input operand) + pre-activation;  0 = fp32 direct-store epilogue (wgrad)
+//   <NS, STAGES, KPS> dual stream: wgrad 2 x 3 x 32 KB;  resident 2 x 3 x 16 KB (2 x 2 with a pre-activation slab);
+//   streaming 2 x 3 x 32 KB (2 x 2 x 32 KB).   g_tc_streams = 1 (tools) selects the single-stream plans.
+static int g_tc_streams = 2;
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   TcArgs args = args_in;
   args.dbg = g_tc_dbg;
-  if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 6, 0, false>(m, args, st);
-  if (!A_MN && use_resident_weights(args)) {
-    if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 4, 2, true>(m, args, st);
-    return launch_tc_impl<BN, A_MN, B_MN, 6, 1, true>(m, args, st);
+  args.dbg_flags = g_tc_dbg_flags;
+  args.pf_tiles = g_tc_pf_tiles;
+  args.pf_kblocks = g_tc_pf_kblocks;
+  const bool res = !A_MN && use_resident_weights(args);
+  if (g_tc_streams == 1) {
+    if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 0, false>(m, args, st);
+    if (res) {
+      if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 1, 2, 2, 2, true>(m, args, st);
+      return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, true>(m, args, st);
+    }
+    if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 1, 2, 2, 2, false>(m, args, st);
+    return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, false>(m, args, st);
   }
-  if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 5, 2, false>(m, args, st);
-  return launch_tc_impl<BN, A_MN, B_MN, 6, 1, false>(m, args, st);
+  if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 0, false>(m, args, st);
+  if (res) {
+    if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 2, 1, 2, true>(m, args, st);
+    return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, true>(m, args, st);
+  }
+  if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 2, 1, 2, false>(m, args, st);
+  return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, false>(m, args, st);
 }
 
 // K needs only a 16-byte row pitch: a partial last k-block is zero-filled by TMA
@@ -650,7 +776,7 @@ int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, void*
 static void patch_wgrad_plan(int B, int PP, int H, int* splits, int* kb_total, int* kb_per) {
   const int tiles = H / BM;  // one 128-wide n block holds all K <= 128 columns (two for K = 192)
   const int total = ceil_div(B * PP, BK);
-  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  int s = (kNumSMs * g_tc_streams) / (tiles > 0 ? tiles : 1);  // one work item per stream of every CTA
   if (s < 1) s = 1;
   if (s > total) s = total;
   const int per = ceil_div(total, s);
@@ -700,9 +826,17 @@ using namespace vitb;
 extern "C" {
 
 /* tools only (not in vitb200.h): dbg = device buffer of 148*8 int64 cycle counters, or NULL; mode 0 auto / 1 streaming / 2 resident */
+int vitb_debug_gemm_prefetch(int tiles, int kblocks) {
+  g_tc_pf_tiles = tiles;
+  g_tc_pf_kblocks = kblocks;
+  return 0;
+}
+
 int vitb_debug_gemm_timeline(long long* dbg, int mode) {
   g_tc_dbg = dbg;
-  g_tc_force_mode = mode;
+  g_tc_force_mode = mode & 0xf;
+  g_tc_streams = (mode & 0x10) ? 1 : 2;
+  g_tc_dbg_flags = mode >> 8;
   return 0;
 }
 
@@ -767,7 +901,7 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
 static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* kb_per) {
   const int tiles = (N / BM) * (K / kBN);
   const int total = ceil_div(M, BK);
-  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  int s = (kNumSMs * g_tc_streams) / (tiles > 0 ? tiles : 1);  // one work item per stream of every CTA
   if (s < 1) s = 1;
   if (s > total) s = total;
   const int per = ceil_div(total, s);
