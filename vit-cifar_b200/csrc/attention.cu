@@ -6,7 +6,10 @@
 // (tcgen05's 128-row tiles do not fit a 65x65x32 problem), softmax in registers with quad shuffles;
 // only the per-row log-sum-exp is kept for backward, which recomputes P.  fp32 path (check mode):
 // plain FFMA with the score tile in shared memory.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "gemm_internal.h"
 
 namespace vitb {
 
@@ -44,67 +47,124 @@ __device__ __forceinline__ float quad_max(float v) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
-// load a (T x D) head slice of the packed (B,T,3H) tensor into padded smem, zero rows >= T
-template <int D, int TP>
-__device__ __forceinline__ void load_head_tile(bf16* dst, const bf16* src, int64_t row_stride, int T, int tid, int nthr) {
-  constexpr int LD = D + 8, CH = D / 8;
-  for (int idx = tid; idx < TP * CH; idx += nthr) {
-    const int r = idx / CH, c = idx % CH;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < T) v = *reinterpret_cast<const uint4*>(src + (int64_t)r * row_stride + c * 8);
-    *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+__device__ __forceinline__ float ex2_fast(float x) {  // one MUFU.EX2; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// key-column masking without per-element selects: the T valid keys fill `nfull` 8-key tiles completely and `rem` columns of
+// the next one; tiles beyond are never computed (their scores are -inf), the partial tile gets an additive 0 / -inf per thread.
+struct KeyMask {
+  int nfull, rem;
+  float pm0, pm1;  // additive mask of this thread's two columns (2t, 2t+1) in the partial tile
+};
+__device__ __forceinline__ KeyMask make_key_mask(int T, int lane) {
+  KeyMask m;
+  m.nfull = T >> 3;
+  m.rem = T & 7;
+  const int t = lane & 3;
+  m.pm0 = (2 * t < m.rem) ? 0.f : -INFINITY;
+  m.pm1 = (2 * t + 1 < m.rem) ? 0.f : -INFINITY;
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA plumbing.  A head tile is a (D x T) box of a 3-D tensor map {columns, tokens, images}: one instruction loads it,
+// token rows >= T are out of bounds and arrive as zeros (the padding the MMA tiles need), rows land densely (2*D bytes)
+// under the hardware swizzle (64B for D = 32, 128B for D = 64) so ldmatrix is conflict-free without padding.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {  // a protocol bug traps instead of hanging the GPU
+      printf("vitb attention: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
   }
 }
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// asynchronous version: rows < T only (the padding rows are zeroed once per kernel and never written again)
-template <int D, int TP>
-__device__ __forceinline__ void load_head_tile_async(bf16* dst, const bf16* src, int64_t row_stride, int T, int tid, int nthr) {
-  constexpr int LD = D + 8, CH = D / 8;
-  for (int idx = tid; idx < T * CH; idx += nthr) {
-    const int r = idx / CH, c = idx % CH;
-    cp_async16(dst + r * LD + c * 8, src + (int64_t)r * row_stride + c * 8);
+// byte offset of 16-byte chunk `chunk` of row `row` inside a swizzled (rows x D) bf16 tile
+template <int D>
+__device__ __forceinline__ uint32_t swz(int row) { return D == 32 ? (uint32_t)((row >> 1) & 3) : (uint32_t)(row & 7); }
+template <int D>
+__device__ __forceinline__ uint32_t tile_off(int row, uint32_t chunk) { return (uint32_t)row * (2 * D) + ((chunk ^ swz<D>(row)) << 4); }
+
+// per-lane pieces of the three ldmatrix address patterns (all row offsets added later are multiples of 8: the swizzle term of a
+// lane never changes, so an address is  base + (row0 + lane_row) * 2D + ((chunk0 ^ lane_x) << 4)  with chunk0 a constant)
+template <int D>
+struct LaneAddr {
+  uint32_t a_row, a_x;  // A fragments (16 rows x 16 k):   row = lane & 15,                       chunk = 2 kk + (lane >> 4)
+  uint32_t b_row, b_x;  // B fragments (8 keys x 32 k):    row = lane & 7,                        chunk = 4 k2 + (lane >> 3)
+  uint32_t t_row, t_x;  // transposed B (16 k-rows x 16):  row = (lane & 7) + 8 ((lane >> 3) & 1), chunk = 2 jp + (lane >> 4)
+  __device__ __forceinline__ LaneAddr(int lane) {
+    a_row = lane & 15; a_x = (uint32_t)(lane >> 4) ^ swz<D>(a_row);
+    b_row = lane & 7;  b_x = (uint32_t)(lane >> 3) ^ swz<D>(b_row);
+    t_row = (lane & 7) + ((lane >> 3) & 1) * 8; t_x = (uint32_t)(lane >> 4) ^ swz<D>(t_row);
   }
+  __device__ __forceinline__ uint32_t a(int row0, int kk) const { return (row0 + a_row) * (2 * D) + (((uint32_t)(2 * kk) ^ a_x) << 4); }
+  __device__ __forceinline__ uint32_t b(int row0, int k2) const { return (row0 + b_row) * (2 * D) + (((uint32_t)(4 * k2) ^ b_x) << 4); }
+  __device__ __forceinline__ uint32_t t(int row0, int jp) const { return (row0 + t_row) * (2 * D) + (((uint32_t)(2 * jp) ^ t_x) << 4); }
+};
+__device__ __forceinline__ void ldsm_x4_s(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-template <int D, int TP>
-__device__ __forceinline__ void zero_pad_rows(bf16* dst, int T, int tid, int nthr) {
-  constexpr int LD = D + 8;
-  for (int idx = tid; idx < (TP - T) * LD / 2; idx += nthr) reinterpret_cast<uint32_t*>(dst + T * LD)[idx] = 0u;
+__device__ __forceinline__ void ldsm_x4_t_s(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
-// S[16 x TP] = Q_rows(16w..) · Kᵀ   (raw, unscaled) -> s[j][4], j = key tile of 8
+// S[16 x TP] = Q_rows(16w..) · Kᵀ   (raw, unscaled; masked key columns = -inf) -> s[j][4], j = key tile of 8
 template <int D, int NT16>
-__device__ __forceinline__ void qk_tile(float (&s)[2 * NT16][4], const bf16* sA, const bf16* sB, int warp, int lane) {
-  constexpr int LD = D + 8;
+__device__ __forceinline__ void qk_tile(float (&s)[2 * NT16][4], uint32_t sA, uint32_t sB, int warp, const LaneAddr<D>& la, const KeyMask& km) {
   uint32_t a[D / 16][4];
 #pragma unroll
-  for (int kk = 0; kk < D / 16; ++kk) ldsm_x4(a[kk], sA + (16 * warp + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+  for (int kk = 0; kk < D / 16; ++kk) ldsm_x4_s(a[kk], sA + la.a(16 * warp, kk));
 #pragma unroll
   for (int j = 0; j < 2 * NT16; ++j) {
-    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    if (j < km.nfull || (j == km.nfull && km.rem != 0)) {  // warp-uniform
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
-    for (int k2 = 0; k2 < D / 32; ++k2) {
-      uint32_t b[4];
-      ldsm_x4(b, sB + (8 * j + (lane & 7)) * LD + k2 * 32 + (lane >> 3) * 8);
-      mma_bf16(s[j], a[2 * k2], b[0], b[1]);
-      mma_bf16(s[j], a[2 * k2 + 1], b[2], b[3]);
+      for (int k2 = 0; k2 < D / 32; ++k2) {
+        uint32_t b[4];
+        ldsm_x4_s(b, sB + la.b(8 * j, k2));
+        mma_bf16(s[j], a[2 * k2], b[0], b[1]);
+        mma_bf16(s[j], a[2 * k2 + 1], b[2], b[3]);
+      }
+      if (j == km.nfull) {
+        s[j][0] += km.pm0; s[j][2] += km.pm0;
+        s[j][1] += km.pm1; s[j][3] += km.pm1;
+      }
+    } else {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY;
     }
   }
 }
 
 // acc[16 x D] += P(regs, 16 x TP) · B(TP x D) with B rows = reduction index (ldmatrix.trans)
 template <int D, int NT16>
-__device__ __forceinline__ void pv_tile(float (&acc)[D / 8][4], const float (&p)[2 * NT16][4], const bf16* sB, int lane) {
-  constexpr int LD = D + 8;
+__device__ __forceinline__ void pv_tile(float (&acc)[D / 8][4], const float (&p)[2 * NT16][4], uint32_t sB, const LaneAddr<D>& la) {
 #pragma unroll
   for (int kk = 0; kk < NT16; ++kk) {
     uint32_t a[4];
@@ -115,92 +175,93 @@ __device__ __forceinline__ void pv_tile(float (&acc)[D / 8][4], const float (&p)
 #pragma unroll
     for (int jp = 0; jp < D / 16; ++jp) {
       uint32_t b[4];
-      ldsm_x4_t(b, sB + (16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + jp * 16 + (lane >> 4) * 8);
+      ldsm_x4_t_s(b, sB + la.t(16 * kk, jp));
       mma_bf16(acc[2 * jp], a, b[0], b[1]);
       mma_bf16(acc[2 * jp + 1], a, b[2], b[3]);
     }
   }
 }
 
-// write a warp's 16 x D fp32 fragment tile as bf16 into its own 16 smem rows, then stream it out coalesced
+// write a warp's 16 x D fp32 fragment tile as bf16 into rows row0.. of a swizzled tile (a later TMA store moves the tile out)
 template <int D>
-__device__ __forceinline__ void store_rows16(const float (&acc)[D / 8][4], bf16* sTile /* row 0 of this warp */, bf16* gdst,
-                                             int64_t g_row_stride, int rows_valid, int lane) {
-  constexpr int LD = D + 8, CH = D / 8;
+__device__ __forceinline__ void stage_rows16(const float (&acc)[D / 8][4], uint32_t sTile, int row0, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int jn = 0; jn < D / 8; ++jn) {
-    *reinterpret_cast<uint32_t*>(sTile + g * LD + jn * 8 + 2 * t) = pack_bf16x2(acc[jn][0], acc[jn][1]);
-    *reinterpret_cast<uint32_t*>(sTile + (g + 8) * LD + jn * 8 + 2 * t) = pack_bf16x2(acc[jn][2], acc[jn][3]);
-  }
-  __syncwarp();
-  for (int idx = lane; idx < 16 * CH; idx += 32) {
-    const int r = idx / CH, c = idx % CH;
-    if (r < rows_valid) *reinterpret_cast<uint4*>(gdst + (int64_t)r * g_row_stride + c * 8) = *reinterpret_cast<const uint4*>(sTile + r * LD + c * 8);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sTile + tile_off<D>(row0 + g, jn) + 4 * t), "r"(pack_bf16x2(acc[jn][0], acc[jn][1])) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sTile + tile_off<D>(row0 + g + 8, jn) + 4 * t), "r"(pack_bf16x2(acc[jn][2], acc[jn][3])) : "memory");
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// bf16 forward: persistent CTAs walk (image, head) items; the next item's Q/K/V tiles stream in with cp.async
-// (double buffer) while the current one is computed
+// bf16 forward: persistent CTAs walk (image, head) items; one thread streams the next item's Q/K/V tiles in with TMA
+// (double buffer, mbarrier) while the CTA computes the current one; the output tile leaves through a TMA store
 // ---------------------------------------------------------------------------------------------
 template <int D, int NT16>
 __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1)))
-    attn_fwd_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, float* __restrict__ attn_map,
-                         int n_items, int T, int heads, float scale) {
-  constexpr int TP = 16 * NT16, LD = D + 8, TILE = TP * LD;
-  extern __shared__ __align__(16) uint8_t smem_attn[];
-  bf16* sbuf = reinterpret_cast<bf16*>(smem_attn);  // [2][3][TILE]
+    attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap m_qkv, const __grid_constant__ CUtensorMap m_o, float* __restrict__ lse,
+                         float* __restrict__ attn_map, int n_items, int T, int heads, float scale) {
+  constexpr int TP = 16 * NT16;
+  constexpr uint32_t TILE_B = TP * D * 2;
+  extern __shared__ uint8_t smem_attn_raw[];
+  const uint32_t sbase = (smem_u32(smem_attn_raw) + 1023u) & ~1023u;  // [2][3] input tiles, output tile, 2 barriers
+  const uint32_t sO = sbase + 6 * TILE_B;
+  const uint32_t bars = sO + TILE_B;
   const int Hd = heads * D;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-  for (int i = 0; i < 6; ++i) zero_pad_rows<D, TP>(sbuf + i * TILE, T, tid, nthr);
-
-  auto issue = [&](int item, int buf) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qkv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_o) : "memory");
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int item, int buf) {  // one thread
     const int b = item / heads, h = item % heads;
-    const bf16* base = qkv + (int64_t)b * T * 3 * Hd + h * D;
-    bf16* dst = sbuf + buf * 3 * TILE;
-    load_head_tile_async<D, TP>(dst, base, 3 * Hd, T, tid, nthr);
-    load_head_tile_async<D, TP>(dst + TILE, base + Hd, 3 * Hd, T, tid, nthr);
-    load_head_tile_async<D, TP>(dst + 2 * TILE, base + 2 * Hd, 3 * Hd, T, tid, nthr);
+    const uint32_t dst = sbase + (uint32_t)buf * 3 * TILE_B, bar = bars + 8 * buf;
+    mbar_arrive_expect_tx(bar, 3 * TILE_B);
+    tma_load_3d(dst, &m_qkv, bar, h * D, 0, b);
+    tma_load_3d(dst + TILE_B, &m_qkv, bar, Hd + h * D, 0, b);
+    tma_load_3d(dst + 2 * TILE_B, &m_qkv, bar, 2 * Hd + h * D, 0, b);
   };
-
   int item = blockIdx.x;
-  if (item < n_items) issue(item, 0);
-  cp_async_commit();
+  if (tid == 0 && item < n_items) issue(item, 0);
   const int g = lane >> 2, t = lane & 3;
   const float sl2 = scale * kLog2e;
+  const KeyMask km = make_key_mask(T, lane);
+  const LaneAddr<D> la(lane);
   for (int it = 0; item < n_items; item += gridDim.x, ++it) {
     const int cur = it & 1;
-    const int nxt = item + gridDim.x;
-    if (nxt < n_items) issue(nxt, cur ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    bf16* sQ = sbuf + cur * 3 * TILE;
-    bf16* sK = sQ + TILE;
-    bf16* sV = sK + TILE;
+    // every warp has finished with the other buffer and with the output tile of the previous item (barrier at the loop end)
+    if (tid == 0) {
+      const int nxt = item + gridDim.x;
+      if (nxt < n_items) issue(nxt, cur ^ 1);
+    }
+    mbar_wait(bars + 8 * cur, (uint32_t)(it >> 1) & 1u);
+    const uint32_t sQ = sbase + (uint32_t)cur * 3 * TILE_B, sK = sQ + TILE_B, sV = sK + TILE_B;
     const int b = item / heads, h = item % heads;
 
     float s[2 * NT16][4];
-    qk_tile<D, NT16>(s, sQ, sK, warp, lane);
+    qk_tile<D, NT16>(s, sQ, sK, warp, la, km);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 2 * NT16; ++j) {
-      const int c = 8 * j + 2 * t;
-      if (c >= T) s[j][0] = s[j][2] = -INFINITY;
-      if (c + 1 >= T) s[j][1] = s[j][3] = -INFINITY;
       m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
       m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
     }
     m0 = quad_max(m0);
     m1 = quad_max(m1);
+    // p = 2^(s * scale*log2e - max * scale*log2e): one FFMA + one MUFU per element; P stays unnormalised through the PV
+    // product (its largest entry is exactly 1) and the 16 x D output is scaled by 1 / rowsum instead
+    const float ms0 = m0 * sl2, ms1 = m1 * sl2;
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 2 * NT16; ++j) {
-      s[j][0] = exp2f((s[j][0] - m0) * sl2);
-      s[j][1] = exp2f((s[j][1] - m0) * sl2);
-      s[j][2] = exp2f((s[j][2] - m1) * sl2);
-      s[j][3] = exp2f((s[j][3] - m1) * sl2);
+      s[j][0] = ex2_fast(fmaf(s[j][0], sl2, -ms0));
+      s[j][1] = ex2_fast(fmaf(s[j][1], sl2, -ms0));
+      s[j][2] = ex2_fast(fmaf(s[j][2], sl2, -ms1));
+      s[j][3] = ex2_fast(fmaf(s[j][3], sl2, -ms1));
       sum0 += s[j][0] + s[j][1];
       sum1 += s[j][2] + s[j][3];
     }
@@ -213,40 +274,42 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
       if (r0 < T) l[r0] = m0 * scale + logf(sum0);
       if (r1 < T) l[r1] = m1 * scale + logf(sum1);
     }
-#pragma unroll
-    for (int j = 0; j < 2 * NT16; ++j) {
-      s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;
-    }
     if (attn_map != nullptr) {  // save_attn_map protocol (layers.py:99-100)
       float* am = attn_map + ((int64_t)b * heads + h) * T * T;
 #pragma unroll
       for (int j = 0; j < 2 * NT16; ++j) {
         const int c = 8 * j + 2 * t;
-        if (r0 < T) { if (c < T) am[(int64_t)r0 * T + c] = s[j][0]; if (c + 1 < T) am[(int64_t)r0 * T + c + 1] = s[j][1]; }
-        if (r1 < T) { if (c < T) am[(int64_t)r1 * T + c] = s[j][2]; if (c + 1 < T) am[(int64_t)r1 * T + c + 1] = s[j][3]; }
+        if (r0 < T) { if (c < T) am[(int64_t)r0 * T + c] = s[j][0] * inv0; if (c + 1 < T) am[(int64_t)r0 * T + c + 1] = s[j][1] * inv0; }
+        if (r1 < T) { if (c < T) am[(int64_t)r1 * T + c] = s[j][2] * inv1; if (c + 1 < T) am[(int64_t)r1 * T + c + 1] = s[j][3] * inv1; }
       }
     }
     float acc[D / 8][4];
 #pragma unroll
     for (int jn = 0; jn < D / 8; ++jn) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0.f;
-    pv_tile<D, NT16>(acc, s, sV, lane);
-    // this warp's Q rows are dead (fragments already in registers, nobody else reads them): reuse as staging.
-    // (padding rows of Q may now hold garbage: they only feed score rows >= T, which are never stored)
-    const int rows_valid = min(16, T - 16 * warp);
-    if (rows_valid > 0)
-      store_rows16<D>(acc, sQ + 16 * warp * LD, o + ((int64_t)b * T + 16 * warp) * Hd + h * D, Hd, rows_valid, lane);
-    __syncthreads();  // everyone is done with this buffer before the next iteration refills it
+    pv_tile<D, NT16>(acc, s, sV, la);
+#pragma unroll
+    for (int jn = 0; jn < D / 8; ++jn) {
+      acc[jn][0] *= inv0; acc[jn][1] *= inv0; acc[jn][2] *= inv1; acc[jn][3] *= inv1;
+    }
+    stage_rows16<D>(acc, sO, 16 * warp, lane);
+    fence_async_smem();  // generic-proxy writes of the output tile -> visible to the TMA store
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&m_o, sO, h * D, 0, b);  // token rows >= T are clipped by the tensor map
+      tma_store_commit();
+      tma_store_wait_read();                 // the tile is rewritten in the next iteration
+    }
+    __syncthreads();
   }
-  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
 // bf16 backward
 // ---------------------------------------------------------------------------------------------
-// acc[16 keys x D] += Aᵀ-tile from sPS (stored [query][key]) · sB (stored [query][D]); reduction over queries
+// acc[16 keys x D] += Aᵀ-tile from sPS (stored [query][key], padded rows) · sB (swizzled [query][D] tile); reduction over queries
 template <int D, int NT16>
-__device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS, const bf16* sB, int warp, int lane) {
-  constexpr int LD = D + 8, LP = 16 * NT16 + 8;
+__device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS, uint32_t sB, int warp, int lane, const LaneAddr<D>& la) {
+  constexpr int LP = 16 * NT16 + 8;
 #pragma unroll
   for (int kq = 0; kq < NT16; ++kq) {
     uint32_t a[4];
@@ -254,7 +317,7 @@ __device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS,
 #pragma unroll
     for (int jp = 0; jp < D / 16; ++jp) {
       uint32_t b[4];
-      ldsm_x4_t(b, sB + (16 * kq + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + jp * 16 + (lane >> 4) * 8);
+      ldsm_x4_t_s(b, sB + la.t(16 * kq, jp));
       mma_bf16(acc[2 * jp], a, b[0], b[1]);
       mma_bf16(acc[2 * jp + 1], a, b[2], b[3]);
     }
@@ -264,65 +327,66 @@ __device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS,
 // One CTA per (image, head); low register count (scores are processed in 16-key chunks) so that 4 CTAs share an SM.
 //   D_i = sum_d dO_id * O_id  (= rowsum(P ∘ dP), flash-attention identity) from the saved forward output, so a chunk's
 //   dS can be formed without holding the whole score row.
+// Q, K, V, dO and O tiles arrive through five TMA loads (zero rows beyond T included), dQ/dK/dV leave through three TMA stores.
 template <int D, int NT16>
 __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1)) : (NT16 <= 2 ? 4 : (NT16 <= 5 ? 2 : 1))))
-    attn_bwd_bf16_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
-                         const float* __restrict__ lse, bf16* __restrict__ dqkv, int T, int heads, float scale) {
-  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8, TILE = TP * LD, CH = D / 8;
-  extern __shared__ __align__(16) uint8_t smem_attn[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
-  bf16* sK = sQ + TILE;
-  bf16* sV = sK + TILE;
-  bf16* sdO = sV + TILE;
-  bf16* sP = sdO + TILE;     // [TP][LP]
-  bf16* sdS = sP + TP * LP;  // [TP][LP]
-  float* sD = reinterpret_cast<float*>(sdS + TP * LP);  // [TP]
-  float* sL = sD + TP;                                   // [TP] lse * log2(e)
+    attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap m_qkv, const __grid_constant__ CUtensorMap m_o, const __grid_constant__ CUtensorMap m_do,
+                         const __grid_constant__ CUtensorMap m_dqkv, const float* __restrict__ lse, int T, int heads, float scale) {
+  constexpr int TP = 16 * NT16, LP = TP + 8, CH = D / 8;
+  constexpr uint32_t TILE_B = TP * D * 2;
+  extern __shared__ uint8_t smem_attn_raw[];
+  const uint32_t sbase = (smem_u32(smem_attn_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_attn_raw + (sbase - smem_u32(smem_attn_raw));
+  const uint32_t sQ = sbase, sK = sQ + TILE_B, sV = sK + TILE_B, sdO = sV + TILE_B, sO = sdO + TILE_B;
+  bf16* sP = reinterpret_cast<bf16*>(gen + 5 * TILE_B);  // [TP][LP]
+  bf16* sdS = sP + TP * LP;                               // [TP][LP]
+  float* sD = reinterpret_cast<float*>(sdS + TP * LP);    // [TP]
+  float* sL = sD + TP;                                    // [TP] lse * log2(e)
+  const uint32_t bar = smem_u32(sL + TP);
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int Hd = heads * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-  const bf16* base = qkv + (int64_t)b * T * 3 * Hd + h * D;
-  const int64_t orow = (int64_t)b * T * Hd + h * D;
-  // all tile loads are asynchronous (one round trip); the other CTAs resident on the SM compute meanwhile
-  load_head_tile_async<D, TP>(sQ, base, 3 * Hd, T, tid, nthr);
-  load_head_tile_async<D, TP>(sK, base + Hd, 3 * Hd, T, tid, nthr);
-  load_head_tile_async<D, TP>(sV, base + 2 * Hd, 3 * Hd, T, tid, nthr);
-  load_head_tile_async<D, TP>(sdO, d_o + orow, Hd, T, tid, nthr);
-  cp_async_commit();
-  zero_pad_rows<D, TP>(sQ, T, tid, nthr);
-  zero_pad_rows<D, TP>(sK, T, tid, nthr);
-  zero_pad_rows<D, TP>(sV, T, tid, nthr);
-  zero_pad_rows<D, TP>(sdO, T, tid, nthr);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(bar, 5 * TILE_B);
+    tma_load_3d(sQ, &m_qkv, bar, h * D, 0, b);
+    tma_load_3d(sK, &m_qkv, bar, Hd + h * D, 0, b);
+    tma_load_3d(sV, &m_qkv, bar, 2 * Hd + h * D, 0, b);
+    tma_load_3d(sdO, &m_do, bar, h * D, 0, b);
+    tma_load_3d(sO, &m_o, bar, h * D, 0, b);
+  }
   for (int r = tid; r < TP; r += nthr) sL[r] = r < T ? lse[((int64_t)b * heads + h) * T + r] * kLog2e : 0.f;
-  // D_i = sum_d dO_id * O_id straight from global memory: CH threads per row, 8 elements each
+  __syncthreads();  // barrier initialised (and sL written) before anyone waits
+  mbar_wait(bar, 0);
+  // D_i = sum_d dO_id * O_id from the two tiles: CH threads per row, 8 elements each (zero rows give D = 0)
   for (int idx = tid; idx < TP * CH; idx += nthr) {
     const int r = idx / CH, c = idx % CH;
-    float v = 0.f;
-    if (r < T) {
-      const uint4 a = *reinterpret_cast<const uint4*>(d_o + orow + (int64_t)r * Hd + c * 8);
-      const uint4 q = *reinterpret_cast<const uint4*>(o + orow + (int64_t)r * Hd + c * 8);
-      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-      const float2 q0 = unpack_bf16x2(q.x), q1 = unpack_bf16x2(q.y), q2 = unpack_bf16x2(q.z), q3 = unpack_bf16x2(q.w);
-      v = (a0.x * q0.x + a0.y * q0.y) + (a1.x * q1.x + a1.y * q1.y) + (a2.x * q2.x + a2.y * q2.y) + (a3.x * q3.x + a3.y * q3.y);
-    }
+    uint32_t a0, a1, a2, a3, q0, q1, q2, q3;
+    const uint32_t off = tile_off<D>(r, c);
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sdO + off));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(sO + off));
+    const float2 x0 = unpack_bf16x2(a0), x1 = unpack_bf16x2(a1), x2 = unpack_bf16x2(a2), x3 = unpack_bf16x2(a3);
+    const float2 y0 = unpack_bf16x2(q0), y1 = unpack_bf16x2(q1), y2 = unpack_bf16x2(q2), y3 = unpack_bf16x2(q3);
+    float v = (x0.x * y0.x + x0.y * y0.y) + (x1.x * y1.x + x1.y * y1.y) + (x2.x * y2.x + x2.y * y2.y) + (x3.x * y3.x + x3.y * y3.y);
 #pragma unroll
-    for (int off = CH / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);  // CH (4 or 8) adjacent lanes share a row
+    for (int off2 = CH / 2; off2 > 0; off2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off2);  // CH (4 or 8) adjacent lanes share a row
     if (c == 0) sD[r] = v;
   }
-  cp_async_wait<0>();
   __syncthreads();
 
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2;
   const int r0 = 16 * warp + g, r1 = r0 + 8;
   const float sl2 = scale * kLog2e;
   const float l0 = sL[r0], l1 = sL[r1];
   const float d0 = sD[r0], d1 = sD[r1];
-  const bool rv0 = r0 < T, rv1 = r1 < T;
+  const KeyMask km = make_key_mask(T, lane);
+  const LaneAddr<D> la(lane);
   uint32_t aq[D / 16][4], ado[D / 16][4];
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
-    ldsm_x4(aq[kk], sQ + (16 * warp + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
-    ldsm_x4(ado[kk], sdO + (16 * warp + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+    ldsm_x4_s(aq[kk], sQ + la.a(16 * warp, kk));
+    ldsm_x4_s(ado[kk], sdO + la.a(16 * warp, kk));
   }
   float dq[D / 8][4];
 #pragma unroll
@@ -335,27 +399,33 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
       const int j = 2 * jc + u;
       s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f;
       dp[u][0] = dp[u][1] = dp[u][2] = dp[u][3] = 0.f;
+      if (j < km.nfull || (j == km.nfull && km.rem != 0)) {  // warp-uniform: key tiles beyond T contribute P = dS = 0
 #pragma unroll
-      for (int k2 = 0; k2 < D / 32; ++k2) {
-        uint32_t bk[4], bv[4];
-        ldsm_x4(bk, sK + (8 * j + (lane & 7)) * LD + k2 * 32 + (lane >> 3) * 8);
-        ldsm_x4(bv, sV + (8 * j + (lane & 7)) * LD + k2 * 32 + (lane >> 3) * 8);
-        mma_bf16(s[u], aq[2 * k2], bk[0], bk[1]);
-        mma_bf16(s[u], aq[2 * k2 + 1], bk[2], bk[3]);
-        mma_bf16(dp[u], ado[2 * k2], bv[0], bv[1]);
-        mma_bf16(dp[u], ado[2 * k2 + 1], bv[2], bv[3]);
+        for (int k2 = 0; k2 < D / 32; ++k2) {
+          uint32_t bk[4], bv[4];
+          ldsm_x4_s(bk, sK + la.b(8 * j, k2));
+          ldsm_x4_s(bv, sV + la.b(8 * j, k2));
+          mma_bf16(s[u], aq[2 * k2], bk[0], bk[1]);
+          mma_bf16(s[u], aq[2 * k2 + 1], bk[2], bk[3]);
+          mma_bf16(dp[u], ado[2 * k2], bv[0], bv[1]);
+          mma_bf16(dp[u], ado[2 * k2 + 1], bv[2], bv[3]);
+        }
+        if (j == km.nfull) {  // partial tile: masked key columns get score -inf -> P = 0
+          s[u][0] += km.pm0; s[u][2] += km.pm0;
+          s[u][1] += km.pm1; s[u][3] += km.pm1;
+        }
+        // Query rows >= T need no mask: their Q and dO rows are zero padding and D = lse = 0 there, so P = 1, dP = 0, dS = 0 and
+        // P only multiplies zero dO rows in dV.
+        s[u][0] = ex2_fast(fmaf(s[u][0], sl2, -l0));
+        s[u][1] = ex2_fast(fmaf(s[u][1], sl2, -l0));
+        s[u][2] = ex2_fast(fmaf(s[u][2], sl2, -l1));
+        s[u][3] = ex2_fast(fmaf(s[u][3], sl2, -l1));
+        // dS = P ∘ (dP − D) / sqrt(features)
+        dp[u][0] = s[u][0] * (dp[u][0] - d0) * scale;
+        dp[u][1] = s[u][1] * (dp[u][1] - d0) * scale;
+        dp[u][2] = s[u][2] * (dp[u][2] - d1) * scale;
+        dp[u][3] = s[u][3] * (dp[u][3] - d1) * scale;
       }
-      const int c = 8 * j + 2 * t;
-      const bool v0 = c < T, v1 = c + 1 < T;
-      s[u][0] = (v0 && rv0) ? exp2f(s[u][0] * sl2 - l0) : 0.f;
-      s[u][1] = (v1 && rv0) ? exp2f(s[u][1] * sl2 - l0) : 0.f;
-      s[u][2] = (v0 && rv1) ? exp2f(s[u][2] * sl2 - l1) : 0.f;
-      s[u][3] = (v1 && rv1) ? exp2f(s[u][3] * sl2 - l1) : 0.f;
-      // dS = P ∘ (dP − D) / sqrt(features)
-      dp[u][0] = s[u][0] * (dp[u][0] - d0) * scale;
-      dp[u][1] = s[u][1] * (dp[u][1] - d0) * scale;
-      dp[u][2] = s[u][2] * (dp[u][2] - d1) * scale;
-      dp[u][3] = s[u][3] * (dp[u][3] - d1) * scale;
     }
     uint32_t pa[4], da[4];  // A-operand fragments of this 16 x 16 chunk (also exactly what stmatrix stores)
     pa[0] = pack_bf16x2(s[0][0], s[0][1]); pa[1] = pack_bf16x2(s[0][2], s[0][3]);
@@ -370,7 +440,7 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
 #pragma unroll
     for (int jp = 0; jp < D / 16; ++jp) {
       uint32_t bb[4];
-      ldsm_x4_t(bb, sK + (16 * jc + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + jp * 16 + (lane >> 4) * 8);
+      ldsm_x4_t_s(bb, sK + la.t(16 * jc, jp));
       mma_bf16(dq[2 * jp], da, bb[0], bb[1]);
       mma_bf16(dq[2 * jp + 1], da, bb[2], bb[3]);
     }
@@ -384,16 +454,21 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
     dv[jn][0] = dv[jn][1] = dv[jn][2] = dv[jn][3] = 0.f;
     dk[jn][0] = dk[jn][1] = dk[jn][2] = dk[jn][3] = 0.f;
   }
-  tn_tile<D, NT16>(dv, sP, sdO, warp, lane);
-  tn_tile<D, NT16>(dk, sdS, sQ, warp, lane);
-  __syncthreads();  // everyone is done reading sQ/sK/sV/sdO: reuse own rows as staging
+  tn_tile<D, NT16>(dv, sP, sdO, warp, lane, la);
+  tn_tile<D, NT16>(dk, sdS, sQ, warp, lane, la);
+  __syncthreads();  // everyone is done reading sQ/sK/sV/sdO: the Q/K/V tiles become the staging tiles of dQ/dK/dV
 
-  const int rows_valid = min(16, T - 16 * warp);
-  if (rows_valid > 0) {
-    bf16* gd = dqkv + ((int64_t)b * T + 16 * warp) * 3 * Hd + h * D;
-    store_rows16<D>(dq, sQ + 16 * warp * LD, gd, 3 * Hd, rows_valid, lane);
-    store_rows16<D>(dk, sK + 16 * warp * LD, gd + Hd, 3 * Hd, rows_valid, lane);
-    store_rows16<D>(dv, sV + 16 * warp * LD, gd + 2 * Hd, 3 * Hd, rows_valid, lane);
+  stage_rows16<D>(dq, sQ, 16 * warp, lane);
+  stage_rows16<D>(dk, sK, 16 * warp, lane);
+  stage_rows16<D>(dv, sV, 16 * warp, lane);
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&m_dqkv, sQ, h * D, 0, b);  // token rows >= T are clipped by the tensor map
+    tma_store_3d(&m_dqkv, sK, Hd + h * D, 0, b);
+    tma_store_3d(&m_dqkv, sV, 2 * Hd + h * D, 0, b);
+    tma_store_commit();
+    tma_store_wait_read();  // shared memory must stay alive until the stores have read it
   }
 }
 
@@ -506,10 +581,16 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// tensor maps of one head tile: box = (D columns, 16*NT16 token rows, 1 image) of a (columns, T, B) view
+template <int D, int NT16>
+static int head_tile_map(CUtensorMap* map, const void* ptr, int cols, int T, int B) {
+  return make_tma_map_3d_bf16(map, ptr, (uint64_t)cols, (uint64_t)T, (uint64_t)B, (uint64_t)cols * 2, (uint64_t)T * cols * 2, D, 16 * NT16, 1, D == 32 ? 64 : 128);
+}
+
 template <int D, int NT16>
 static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int B, int T, int heads, float scale, cudaStream_t st) {
-  constexpr int TP = 16 * NT16, LD = D + 8;
-  constexpr size_t smem = (size_t)6 * TP * LD * sizeof(bf16);
+  constexpr int TP = 16 * NT16;
+  constexpr size_t smem = (size_t)7 * TP * D * 2 + 16 + 1024;
   constexpr int per_sm = NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1);
   auto kern = attn_fwd_bf16_kernel<D, NT16>;
   static bool configured = false;
@@ -517,24 +598,34 @@ static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int 
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  const int Hd = heads * D;
+  CUtensorMap m_qkv, m_o;
+  if (head_tile_map<D, NT16>(&m_qkv, qkv, 3 * Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
   const int items = B * heads;
   const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-  kern<<<grid, 32 * NT16, smem, st>>>((const bf16*)qkv, (bf16*)o, lse, am, items, T, heads, scale);
+  kern<<<grid, 32 * NT16, smem, st>>>(m_qkv, m_o, lse, am, items, T, heads, scale);
   VITB_LAUNCH_OK();
   return 0;
 }
 template <int D, int NT16>
 static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, float scale,
                            cudaStream_t st) {
-  constexpr int TP = 16 * NT16, LD = D + 8, LP = TP + 8, TILE = TP * LD;
-  constexpr size_t smem = ((size_t)4 * TILE + (size_t)2 * TP * LP) * sizeof(bf16) + (size_t)2 * TP * sizeof(float);
+  constexpr int TP = 16 * NT16, LP = TP + 8;
+  constexpr size_t smem = (size_t)5 * TP * D * 2 + (size_t)2 * TP * LP * 2 + (size_t)2 * TP * sizeof(float) + 16 + 1024;
   auto kern = attn_bwd_bf16_kernel<D, NT16>;
   static bool configured = false;
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<B * heads, 32 * NT16, smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, T, heads, scale);
+  const int Hd = heads * D;
+  CUtensorMap m_qkv, m_o, m_do, m_dqkv;
+  if (head_tile_map<D, NT16>(&m_qkv, qkv, 3 * Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_do, d_o, Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_dqkv, dqkv, 3 * Hd, T, B)) return -1;
+  kern<<<B * heads, 32 * NT16, smem, st>>>(m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale);
   VITB_LAUNCH_OK();
   return 0;
 }

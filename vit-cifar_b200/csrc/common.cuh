@@ -133,18 +133,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // fixed-order reduction of per-block partials: out_k[c] = sum_p ws[k][p][c]   (k = blockIdx.y < 3)
 // (template so that every translation unit can instantiate it without relocatable device code)
 // ---------------------------------------------------------------------------------------------
-// launch with block (32, 8) and grid (ceil(cols / 128), number of outputs): x = 4-column lane, y = slice of the partials
-template <int kUnused = 0>
-__global__ void __launch_bounds__(256) partials_finalize_kernel(const float* __restrict__ ws, int nparts, int64_t cols,
-                                                                float* out0, float* out1, float* out2) {
+// block (32, 8): x = 4-column lane, y = slice of the partials.  `bx` of `nbx` blocks cover `cols` columns.
+__device__ __forceinline__ void finalize_block_cols(const float* __restrict__ base, int nparts, int64_t cols, float* __restrict__ out, int bx, int nbx) {
   __shared__ float4 red[8][32];
-  const int k = blockIdx.y;
-  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
-  if (out == nullptr) return;
-  const float* base = ws + (size_t)k * nparts * cols;
   const int tx = threadIdx.x, ty = threadIdx.y;
   if ((cols & 3) == 0) {
-    const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 4;
+    const int64_t c = ((int64_t)bx * 32 + tx) * 4;
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
     if (c < cols) {
       const float* p = base + c;
@@ -173,13 +167,32 @@ __global__ void __launch_bounds__(256) partials_finalize_kernel(const float* __r
     }
     return;
   }
-  // generic (cols not a multiple of 4): one thread per column, strided over the grid
+  // generic (cols not a multiple of 4): one thread per column, strided over the blocks
   const int tid = ty * 32 + tx;
-  for (int64_t c = (int64_t)blockIdx.x * 256 + tid; c < cols; c += (int64_t)gridDim.x * 256) {
+  for (int64_t c = (int64_t)bx * 256 + tid; c < cols; c += (int64_t)nbx * 256) {
     float s = 0.f;
     for (int i = 0; i < nparts; ++i) s += base[(size_t)i * cols + c];
     out[c] = s;
   }
+}
+
+// launch with block (32, 8) and grid (ceil(cols / 128), number of outputs)
+template <int kUnused = 0>
+__global__ void __launch_bounds__(256) partials_finalize_kernel(const float* __restrict__ ws, int nparts, int64_t cols,
+                                                                float* out0, float* out1, float* out2) {
+  const int k = blockIdx.y;
+  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+  if (out == nullptr) return;
+  finalize_block_cols(ws + (size_t)k * nparts * cols, nparts, cols, out, blockIdx.x, gridDim.x);
+}
+
+// two partial sets with different widths in one launch (wgrad: dW and the bias gradient): grid = blocks(cols0) + blocks(cols1)
+template <int kUnused = 0>
+__global__ void __launch_bounds__(256) partials_finalize2_kernel(const float* __restrict__ ws0, int64_t cols0, float* out0, const float* __restrict__ ws1,
+                                                                 int64_t cols1, float* out1, int nparts) {
+  const int nb0 = (int)((cols0 + 127) / 128);
+  if ((int)blockIdx.x < nb0) finalize_block_cols(ws0, nparts, cols0, out0, blockIdx.x, nb0);
+  else finalize_block_cols(ws1, nparts, cols1, out1, blockIdx.x - nb0, gridDim.x - nb0);
 }
 
 inline dim3 finalize_grid(int64_t cols, int nout) { return dim3((unsigned)((cols + 127) / 128), (unsigned)nout); }

@@ -1,5 +1,7 @@
 // gemm_internal.h — host-side interfaces shared between gemm_simt.cu and gemm_tc.cu (not part of the C ABI).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vitb {
@@ -25,6 +27,16 @@ struct SimtGemmArgs {
 
 int simt_gemm_launch(const SimtGemmArgs& g, int a_dt, int b_dt, int o_dt, int splits, cudaStream_t st);
 int simt_pick_splits(int tiles, int K);
+// 3-D bf16 tensor map {d0 (contiguous), d1, d2} with byte strides of d1 / d2, box {box0, box1, box2}, swizzle_bytes in {0, 32, 64, 128}
+// (implemented in gemm_tc.cu, which owns the driver entry point)
+int make_tma_map_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                         uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes);
+
+// classifier head (head.cu): N = num_classes <= 128, fp32 logits / dlogits, activations and weight in `dt`
+bool head_shape_ok(int M, int N, int K);
+int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st);
+int head_dgrad_launch(const float* dy, const void* w, void* dx, int M, int N, int K, int dt, cudaStream_t st);
+int head_wgrad_launch(const float* dy, const void* x, float* dw, float* dbias, int M, int N, int K, int dt, cudaStream_t st);
 int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t ld, int x_dt, cudaStream_t st);
 
 // tensor-core pieces of the patch embedding (gemm_tc.cu), bf16 only

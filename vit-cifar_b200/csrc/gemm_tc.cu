@@ -672,6 +672,24 @@ static int make_map3(CUtensorMap* map, const void* ptr, uint64_t H, uint64_t Tn,
   return 0;
 }
 
+int make_tma_map_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                         uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  VITB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  VITB_REQUIRE(((uintptr_t)ptr % 16 == 0) && stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "tensor map: operand must be 16-byte aligned with 16-byte multiple strides");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstr[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VITB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (dims %llu %llu %llu box %u %u %u)", (int)r, (unsigned long long)d0,
+               (unsigned long long)d1, (unsigned long long)d2, box0, box1, box2);
+  return 0;
+}
+
 struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
@@ -812,9 +830,8 @@ int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias,
   int rc = launch_tc<kBN, true, true>(m, t, st);
   if (rc) return rc;
   const int64_t n = (int64_t)H * K;
-  partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
-  VITB_LAUNCH_OK();
-  partials_finalize_kernel<0><<<finalize_grid(H, 1), finalize_block(), 0, st>>>(bpart, splits, H, dbias, nullptr, nullptr);
+  const unsigned nb = (unsigned)((n + 127) / 128 + (H + 127) / 128);
+  partials_finalize2_kernel<0><<<nb, finalize_block(), 0, st>>>(part, n, dw, bpart, H, dbias, splits);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -863,6 +880,7 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
     return launch_tc<kBN, false, false>(m, t, st);
   }
+  if (e.out_f32 && !e.gelu && !residual && !preact && head_shape_ok(M, N, K)) return head_fwd_launch(a, w, bias, (float*)c, M, N, K, dt, st);
   SimtGemmArgs g = {};
   g.a = a; g.b = w; g.M = M; g.N = N; g.K = K;
   g.a_sm = K; g.a_sk = 1; g.b_sk = 1; g.b_sn = K; g.e = e;
@@ -891,6 +909,7 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     t.has_in = z != nullptr;
     return launch_tc<kBN, false, true>(m, t, st);
   }
+  if (dy_f32 && !z && head_shape_ok(M, N, K)) return head_dgrad_launch((const float*)dy, w, dx, M, N, K, dt, st);
   SimtGemmArgs g = {};
   g.a = dy; g.b = w; g.M = M; g.N = K; g.K = N;
   g.a_sm = N; g.a_sk = 1; g.b_sk = K; g.b_sn = 1; g.e = e;
@@ -901,7 +920,9 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
 static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* kb_per) {
   const int tiles = (N / BM) * (K / kBN);
   const int total = ceil_div(M, BK);
-  int s = (kNumSMs * g_tc_streams) / (tiles > 0 ? tiles : 1);  // one work item per stream of every CTA
+  // one work item per stream of every CTA when the output is wide (QKV: 27 tiles); narrow outputs (9 tiles) keep one item per
+  // CTA, where twice the fp32 partials to write and re-read cost more than the second stream gains
+  int s = (kNumSMs * (tiles >= 18 ? g_tc_streams : 1)) / (tiles > 0 ? tiles : 1);
   if (s < 1) s = 1;
   if (s > total) s = total;
   const int per = ceil_div(total, s);
@@ -961,15 +982,17 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
     if (rc) return rc;
     if (splits > 1) {
       const int64_t n = (int64_t)N * K;
-      partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
-      VITB_LAUNCH_OK();
-      if (dbias) {
-        partials_finalize_kernel<0><<<finalize_grid(N, 1), finalize_block(), 0, st>>>(bpart, splits, N, dbias, nullptr, nullptr);
-        VITB_LAUNCH_OK();
+      if (dbias) {  // dW and the bias gradient in one launch
+        const unsigned nb = (unsigned)((n + 127) / 128 + (N + 127) / 128);
+        partials_finalize2_kernel<0><<<nb, finalize_block(), 0, st>>>(part, n, dw, bpart, N, dbias, splits);
+      } else {
+        partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
       }
+      VITB_LAUNCH_OK();
     }
     return 0;
   }
+  if ((flags & VITB_GEMM_DY_F32) && head_shape_ok(M, N, K)) return head_wgrad_launch((const float*)dy, x, dw, dbias, M, N, K, dt, st);
   splits = wgrad_simt_splits(M, N, K);
   const size_t part_bytes = align_up((size_t)(splits > 1 ? splits : 0) * N * K * sizeof(float), 256);
   {

@@ -1,0 +1,141 @@
+// head.cu — the classifier head `fc[1] = nn.Linear(hidden, num_classes)` (vit.py:63, 76) and its backward.
+//
+// N = num_classes is 10 or 100: far too narrow for a 128-wide tensor-core tile and, as a 64x64 SIMT tile, a 16-CTA
+// latency-bound launch.  These kernels are plain FFMA with fixed-order reductions (bit-reproducible, used by both the bf16
+// path and the fp32 check mode), shaped so that every SM has work:
+//   fwd    logits[b, c] = bias[c] + sum_k a[b, k] w[c, k]          one warp per image
+//   dgrad  da[b, k]     = sum_c dlogits[b, c] w[c, k]              one thread per (image, 4 columns)
+//   wgrad  dw[c, k]     = sum_b dlogits[b, c] a[b, k],  dbias[c] = sum_b dlogits[b, c]
+//                                                                  32 columns x 8 batch slices per CTA, slices combined in order
+#include "common.cuh"
+#include "gemm_internal.h"
+
+namespace vitb {
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, const T* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ out, int M, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T* ar = a + (size_t)row * K;
+  for (int c = 0; c < N; ++c) {
+    const T* wr = w + (size_t)c * K;
+    float acc = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 x = ld4(ar + k), y = ld4(wr + k);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+      acc = fmaf(x.z, y.z, acc);
+      acc = fmaf(x.w, y.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)row * N + c] = acc + (bias ? bias[c] : 0.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx, int M, int N,
+                                                         int K) {
+  const int k4 = K >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * k4) return;
+  const int row = (int)(i / k4), k = (int)(i % k4) * 4;
+  const float* d = dy + (size_t)row * N;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < N; ++c) {
+    const float g = d[c];
+    const float4 y = ld4(w + (size_t)c * K + k);
+    acc.x = fmaf(g, y.x, acc.x);
+    acc.y = fmaf(g, y.y, acc.y);
+    acc.z = fmaf(g, y.z, acc.z);
+    acc.w = fmaf(g, y.w, acc.w);
+  }
+  st4(dx + (size_t)row * K + k, acc);
+}
+
+constexpr int kHeadCC = 16;     // classes per register pass
+constexpr int kHeadSlices = 8;  // batch slices per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
+                                                                      float* __restrict__ dbias, int M, int N, int K) {
+  __shared__ float red[kHeadSlices][kHeadCC][32];
+  const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += kHeadCC) {
+    float acc[kHeadCC];
+#pragma unroll
+    for (int j = 0; j < kHeadCC; ++j) acc[j] = 0.f;
+    if (k < K) {
+      for (int b = s; b < M; b += kHeadSlices) {
+        const float xv = Act<T>::ld(x + (size_t)b * K + k);
+        const float* d = dy + (size_t)b * N + c0;
+#pragma unroll
+        for (int j = 0; j < kHeadCC; ++j)
+          if (c0 + j < N) acc[j] = fmaf(d[j], xv, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadCC; ++j) red[s][j][lane] = acc[j];
+    __syncthreads();
+    // thread (s, lane) combines classes s, s + 8 of this pass for column `lane`, slices in fixed order
+    for (int j = s; j < kHeadCC; j += kHeadSlices) {
+      if (c0 + j < N && k < K) {
+        float t = red[0][j][lane];
+#pragma unroll
+        for (int q = 1; q < kHeadSlices; ++q) t += red[q][j][lane];
+        dw[(size_t)(c0 + j) * K + k] = t;
+      }
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && dbias != nullptr) {
+    // dbias: lane = class (strided), slice = batch slice
+    float* r2 = &red[0][0][0];  // [kHeadSlices][32]
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      const int c = c0 + lane;
+      float t = 0.f;
+      if (c < N)
+        for (int b = s; b < M; b += kHeadSlices) t += dy[(size_t)b * N + c];
+      r2[s * 32 + lane] = t;
+      __syncthreads();
+      if (s == 0 && c < N) {
+        float u = r2[lane];
+#pragma unroll
+        for (int q = 1; q < kHeadSlices; ++q) u += r2[q * 32 + lane];
+        dbias[c] = u;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+bool head_shape_ok(int M, int N, int K) { return N <= 128 && K % 4 == 0 && M > 0; }
+
+int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st) {
+  const int wpb = 8;
+  if (dt == VITB_BF16) head_fwd_kernel<bf16><<<ceil_div(M, wpb), 32 * wpb, 0, st>>>((const bf16*)a, (const bf16*)w, bias, out, M, N, K);
+  else head_fwd_kernel<float><<<ceil_div(M, wpb), 32 * wpb, 0, st>>>((const float*)a, (const float*)w, bias, out, M, N, K);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+int head_dgrad_launch(const float* dy, const void* w, void* dx, int M, int N, int K, int dt, cudaStream_t st) {
+  const int64_t n = (int64_t)M * (K / 4);
+  const int blocks = (int)ceil_div64(n, 256);
+  if (dt == VITB_BF16) head_dgrad_kernel<bf16><<<blocks, 256, 0, st>>>(dy, (const bf16*)w, (bf16*)dx, M, N, K);
+  else head_dgrad_kernel<float><<<blocks, 256, 0, st>>>(dy, (const float*)w, (float*)dx, M, N, K);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+int head_wgrad_launch(const float* dy, const void* x, float* dw, float* dbias, int M, int N, int K, int dt, cudaStream_t st) {
+  const int blocks = ceil_div(K, 32);
+  if (dt == VITB_BF16) head_wgrad_kernel<bf16><<<blocks, 32 * kHeadSlices, 0, st>>>(dy, (const bf16*)x, dw, dbias, M, N, K);
+  else head_wgrad_kernel<float><<<blocks, 32 * kHeadSlices, 0, st>>>(dy, (const float*)x, dw, dbias, M, N, K);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace vitb

@@ -4,7 +4,8 @@
 namespace vitb {
 
 // ---------------------------------------------------------------------------------------------
-// LS-CE: criterions.py:13-19.  One CTA; each warp walks rows w, w+32, ...; fixed-order reduction.
+// LS-CE: criterions.py:13-19.  One CTA, one thread per image (C is 10 or 100: a row is a few cache lines), rows r, r + 1024, ...;
+// the batch mean is reduced in a fixed order (lane shuffles, then the 32 warp sums serially) -> bit-reproducible.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
     ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss,
@@ -15,33 +16,30 @@ __global__ void __launch_bounds__(1024)
   const float conf = 1.0f - smoothing;
   const float gs = grad_scale / (float)B;
   float acc = 0.f;
-  for (int r = warp; r < B; r += nwarps) {
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
     const float* z = logits + (size_t)r * C;
     const int y = (int)labels[r];
     float mx = -INFINITY, sz = 0.f;
-    for (int j = lane; j < C; j += 32) {
+    for (int j = 0; j < C; ++j) {
       const float v = z[j];
       mx = fmaxf(mx, v);
       sz += v;
     }
-    mx = warp_max(mx);
-    sz = warp_sum(sz);
     float se = 0.f;
-    for (int j = lane; j < C; j += 32) se += expf(z[j] - mx);
-    se = warp_sum(se);
+    for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
     const float lse = mx + logf(se);
     const float zy = z[y];
     // sum_j -q_j (z_j - lse)
-    const float li = -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
-    acc += li;
+    acc += -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
     if (dlogits != nullptr) {
       float* d = dlogits + (size_t)r * C;
-      for (int j = lane; j < C; j += 32) {
+      for (int j = 0; j < C; ++j) {
         const float p = expf(z[j] - lse);
         d[j] = (p - (j == y ? conf : off)) * gs;
       }
     }
   }
+  acc = warp_sum(acc);
   if (lane == 0) part[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
