@@ -97,6 +97,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1),
                "r"(c2)
@@ -182,14 +185,18 @@ __device__ __forceinline__ void pv_tile(float (&acc)[D / 8][4], const float (&p)
   }
 }
 
-// write a warp's 16 x D fp32 fragment tile as bf16 into rows row0.. of a swizzled tile (a later TMA store moves the tile out)
+// write a warp's 16 x D fp32 fragment tile as bf16 into rows row0.. (a multiple of 16) of a swizzled tile; a later TMA store
+// moves the tile out.  Rows g and g + 8 share their swizzle term, so an address is base + ((chunk ^ x) << 4).
 template <int D>
 __device__ __forceinline__ void stage_rows16(const float (&acc)[D / 8][4], uint32_t sTile, int row0, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  const uint32_t x = swz<D>(g);
+  const uint32_t base = sTile + (uint32_t)(row0 + g) * (2 * D) + 4 * t;
 #pragma unroll
   for (int jn = 0; jn < D / 8; ++jn) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sTile + tile_off<D>(row0 + g, jn) + 4 * t), "r"(pack_bf16x2(acc[jn][0], acc[jn][1])) : "memory");
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sTile + tile_off<D>(row0 + g + 8, jn) + 4 * t), "r"(pack_bf16x2(acc[jn][2], acc[jn][3])) : "memory");
+    const uint32_t a = base + (((uint32_t)jn ^ x) << 4);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(pack_bf16x2(acc[jn][0], acc[jn][1])) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + 8 * 2 * D), "r"(pack_bf16x2(acc[jn][2], acc[jn][3])) : "memory");
   }
 }
 
@@ -204,9 +211,9 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
   constexpr int TP = 16 * NT16;
   constexpr uint32_t TILE_B = TP * D * 2;
   extern __shared__ uint8_t smem_attn_raw[];
-  const uint32_t sbase = (smem_u32(smem_attn_raw) + 1023u) & ~1023u;  // [2][3] input tiles, output tile, 2 barriers
-  const uint32_t sO = sbase + 6 * TILE_B;
-  const uint32_t bars = sO + TILE_B;
+  const uint32_t sbase = (smem_u32(smem_attn_raw) + 1023u) & ~1023u;  // [2][3] input tiles, [2] output tiles, 2 barriers
+  const uint32_t sO0 = sbase + 6 * TILE_B;
+  const uint32_t bars = sO0 + 2 * TILE_B;
   const int Hd = heads * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -233,7 +240,8 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
   const LaneAddr<D> la(lane);
   for (int it = 0; item < n_items; item += gridDim.x, ++it) {
     const int cur = it & 1;
-    // every warp has finished with the other buffer and with the output tile of the previous item (barrier at the loop end)
+    const uint32_t sO = sO0 + (uint32_t)cur * TILE_B;
+    // every warp has finished with the other input buffer (the barrier of the previous iteration comes after its compute)
     if (tid == 0) {
       const int nxt = item + gridDim.x;
       if (nxt < n_items) issue(nxt, cur ^ 1);
@@ -293,14 +301,16 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
     }
     stage_rows16<D>(acc, sO, 16 * warp, lane);
     fence_async_smem();  // generic-proxy writes of the output tile -> visible to the TMA store
+    // The store of the previous item (other output tile, issued a whole iteration ago) must have read its tile before the barrier
+    // releases the warps into the iteration that rewrites it.
+    if (tid == 0) tma_store_wait_read();
     __syncthreads();
     if (tid == 0) {
       tma_store_3d(&m_o, sO, h * D, 0, b);  // token rows >= T are clipped by the tensor map
       tma_store_commit();
-      tma_store_wait_read();                 // the tile is rewritten in the next iteration
     }
-    __syncthreads();
   }
+  if (tid == 0) tma_store_wait_read();  // shared memory must stay alive until the last store has read it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,7 +341,7 @@ __device__ __forceinline__ void tn_tile(float (&acc)[D / 8][4], const bf16* sPS,
 template <int D, int NT16>
 __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1)) : (NT16 <= 2 ? 4 : (NT16 <= 5 ? 2 : 1))))
     attn_bwd_bf16_kernel(const __grid_constant__ CUtensorMap m_qkv, const __grid_constant__ CUtensorMap m_o, const __grid_constant__ CUtensorMap m_do,
-                         const __grid_constant__ CUtensorMap m_dqkv, const float* __restrict__ lse, int T, int heads, float scale) {
+                         const __grid_constant__ CUtensorMap m_dqkv, const float* __restrict__ lse, int T, int heads, float scale, int pf_dist) {
   constexpr int TP = 16 * NT16, LP = TP + 8, CH = D / 8;
   constexpr uint32_t TILE_B = TP * D * 2;
   extern __shared__ uint8_t smem_attn_raw[];
@@ -341,11 +351,10 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
   bf16* sP = reinterpret_cast<bf16*>(gen + 5 * TILE_B);  // [TP][LP]
   bf16* sdS = sP + TP * LP;                               // [TP][LP]
   float* sD = reinterpret_cast<float*>(sdS + TP * LP);    // [TP]
-  float* sL = sD + TP;                                    // [TP] lse * log2(e)
-  const uint32_t bar = smem_u32(sL + TP);
+  const uint32_t bar = smem_u32(sD + 2 * TP);
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int Hd = heads * D;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -355,13 +364,29 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
     tma_load_3d(sV, &m_qkv, bar, 2 * Hd + h * D, 0, b);
     tma_load_3d(sdO, &m_do, bar, h * D, 0, b);
     tma_load_3d(sO, &m_o, bar, h * D, 0, b);
+    // CTAs are not persistent here: ask L2 for the tiles of the item that takes this CTA's place about one wave later, so its
+    // loads do not pay the full HBM latency with nothing else to do
+    const int nxt = (int)blockIdx.x + pf_dist;
+    if (nxt < (int)gridDim.x) {
+      const int nb = nxt / heads, nh = nxt % heads;
+      tma_prefetch_3d(&m_qkv, nh * D, 0, nb);
+      tma_prefetch_3d(&m_qkv, Hd + nh * D, 0, nb);
+      tma_prefetch_3d(&m_qkv, 2 * Hd + nh * D, 0, nb);
+      tma_prefetch_3d(&m_do, nh * D, 0, nb);
+      tma_prefetch_3d(&m_o, nh * D, 0, nb);
+    }
   }
-  for (int r = tid; r < TP; r += nthr) sL[r] = r < T ? lse[((int64_t)b * heads + h) * T + r] * kLog2e : 0.f;
-  __syncthreads();  // barrier initialised (and sL written) before anyone waits
+  const int g = lane >> 2;
+  const int r0 = 16 * warp + g, r1 = r0 + 8;
+  // lse * log2(e) of this thread's two query rows (0 beyond T)
+  const float* lrow = lse + ((int64_t)b * heads + h) * T;
+  const float l0 = r0 < T ? lrow[r0] * kLog2e : 0.f, l1 = r1 < T ? lrow[r1] * kLog2e : 0.f;
+  __syncthreads();  // barrier initialised before anyone waits
   mbar_wait(bar, 0);
-  // D_i = sum_d dO_id * O_id from the two tiles: CH threads per row, 8 elements each (zero rows give D = 0)
-  for (int idx = tid; idx < TP * CH; idx += nthr) {
-    const int r = idx / CH, c = idx % CH;
+  // D_i = sum_d dO_id * O_id from the two tiles, each warp for its own 16 query rows: CH lanes per row, 8 elements each
+  // (zero rows give D = 0)
+  for (int idx = lane; idx < 16 * CH; idx += 32) {
+    const int r = 16 * warp + idx / CH, c = idx % CH;
     uint32_t a0, a1, a2, a3, q0, q1, q2, q3;
     const uint32_t off = tile_off<D>(r, c);
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sdO + off));
@@ -373,12 +398,9 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
     for (int off2 = CH / 2; off2 > 0; off2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off2);  // CH (4 or 8) adjacent lanes share a row
     if (c == 0) sD[r] = v;
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int g = lane >> 2;
-  const int r0 = 16 * warp + g, r1 = r0 + 8;
   const float sl2 = scale * kLog2e;
-  const float l0 = sL[r0], l1 = sL[r1];
   const float d0 = sD[r0], d1 = sD[r1];
   const KeyMask km = make_key_mask(T, lane);
   const LaneAddr<D> la(lane);
@@ -590,7 +612,7 @@ static int head_tile_map(CUtensorMap* map, const void* ptr, int cols, int T, int
 template <int D, int NT16>
 static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int B, int T, int heads, float scale, cudaStream_t st) {
   constexpr int TP = 16 * NT16;
-  constexpr size_t smem = (size_t)7 * TP * D * 2 + 16 + 1024;
+  constexpr size_t smem = (size_t)8 * TP * D * 2 + 16 + 1024;
   constexpr int per_sm = NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1);
   auto kern = attn_fwd_bf16_kernel<D, NT16>;
   static bool configured = false;
@@ -625,7 +647,9 @@ static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, cons
   if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
   if (head_tile_map<D, NT16>(&m_do, d_o, Hd, T, B)) return -1;
   if (head_tile_map<D, NT16>(&m_dqkv, dqkv, 3 * Hd, T, B)) return -1;
-  kern<<<B * heads, 32 * NT16, smem, st>>>(m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale);
+  int per_sm = 1;
+  VITB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NT16, smem));
+  kern<<<B * heads, 32 * NT16, smem, st>>>(m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale, kNumSMs * (per_sm > 0 ? per_sm : 1));
   VITB_LAUNCH_OK();
   return 0;
 }
