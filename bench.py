@@ -298,8 +298,12 @@ def run_ours(args):
         sampler.start()
     ms_dev = timed(lambda i: eng.step(), args.steps, W)
     # ---- end-to-end arm: pinned host -> device every step, loss read back every step ----------
+    # Public API as a training loop uses it: step() on the batch prefetched during the previous step, then prefetch() of the
+    # next pinned host batch (its PCIe transfer overlaps this step's kernels).  One H2D batch copy and one D2H loss read per step.
+    eng.prefetch(host_x[0], host_y[0])
     def e2e_step(i):
-        loss = eng.step(host_x[i % nbuf], host_y[i % nbuf])
+        loss = eng.step()
+        eng.prefetch(host_x[(i + 1) % nbuf], host_y[(i + 1) % nbuf])
         loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)
     ms_e2e = timed(e2e_step, args.steps, W)
     clocks = sampler.stop() if rank == 0 else None

@@ -88,6 +88,14 @@ class TrainEngine:
         self.img = torch.zeros((self.B, 3, S, S), dtype=torch.float32, device=self.dev)
         self.labels = torch.zeros((self.B,), dtype=torch.int64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        # input staging for `prefetch`: the next batch crosses PCIe on a copy stream while the current step computes
+        self._img_stage = torch.zeros_like(self.img)
+        self._labels_stage = torch.zeros_like(self.labels)
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
+        self._staged = torch.cuda.Event()
+        self._consumed = torch.cuda.Event()
+        self._consumed.record()
+        self._pending = False
         self.dlogits = torch.zeros((self.B, model.num_classes), dtype=torch.float32, device=self.dev)
         self.logits: Optional[torch.Tensor] = None
         self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=self.dev)
@@ -171,10 +179,29 @@ class TrainEngine:
         self.img.copy_(img, non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
 
+    def prefetch(self, img: torch.Tensor, labels: torch.Tensor) -> None:
+        """Start copying the NEXT batch (pinned host tensors) to the device on a side stream; the following `step()` (called
+        without arguments) trains on it.  Called right after `step()` returns, the host-to-device transfer overlaps that step's
+        kernels — the role the DataLoader's pinned-memory prefetch plays for the reference (main.py:175)."""
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)  # the previously staged batch has been moved into the input buffers
+        with torch.cuda.stream(cs):
+            self._img_stage.copy_(img, non_blocking=True)
+            self._labels_stage.copy_(labels, non_blocking=True)
+            self._staged.record(cs)
+        self._pending = True
+
     def step(self, img: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step.  Returns the (device) loss tensor of this step; no host synchronisation."""
         if img is not None:
             self.load_batch(img, labels)
+        elif self._pending:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged)
+            self.img.copy_(self._img_stage, non_blocking=True)
+            self.labels.copy_(self._labels_stage, non_blocking=True)
+            self._consumed.record(cur)
+            self._pending = False
         self.step_count += 1
         h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
