@@ -138,6 +138,26 @@ def test_gemm_wgrad_dbias(ops, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,C,H", [(1024, 10, 384), (130, 100, 384), (9, 128, 768)])
+def test_classifier_head_kernels(ops, dtype, B, C, H):
+    """fc[1] (vit.py:63,76) forward / dgrad / wgrad+dbias through the small-N kernels (head.cu), at CIFAR-10 and -100 widths."""
+    hn = rnd((B, H), dtype, 1); w = rnd((C, H), dtype, 2, 0.05); bias = rnd((C,), torch.float32, 3)
+    dl = rnd((B, C), torch.float32, 4, 1.0 / B)
+    logits = torch.empty((B, C), device="cuda")
+    ops.gemm_fwd(cu(hn), cu(w), cu(bias), None, logits, None, B, C, H, out_f32=True)
+    assert rel(logits, hn.float() @ w.float().t() + bias) < 1e-4
+    dw = torch.empty((C, H), device="cuda"); db = torch.empty((C,), device="cuda")
+    ops.gemm_wgrad(cu(dl), cu(hn), dw, db, B, C, H, dy_f32=True)
+    assert rel(dw, dl.t() @ hn.float()) < 1e-4 and rel(db, dl.sum(0)) < 1e-4
+    dw2 = torch.empty_like(dw); db2 = torch.empty_like(db)
+    ops.gemm_wgrad(cu(dl), cu(hn), dw2, db2, B, C, H, dy_f32=True)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)  # fixed-order reductions
+    dx = torch.empty((B, H), dtype=dtype, device="cuda")
+    ops.gemm_dgrad(cu(dl), cu(w), None, dx, B, C, H, dy_f32=True)
+    assert rel(dx, dl @ w.float()) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_gemm_head_backward_f32_dy(ops, dtype):
     B, C, H = 5, 10, 128
     dl = rnd((B, C), torch.float32, 1); hn = rnd((B, H), dtype, 2); w = rnd((C, H), dtype, 3)

@@ -264,3 +264,30 @@ def test_full_size_properties_b1024(vb):
     assert loss1 == loss2
     for k, v in eb.grads().items():
         assert torch.equal(v, gb[k]), k
+
+
+def test_prefetch_pipeline_equals_direct_steps(vb):
+    """TrainEngine.prefetch() (next batch copied on a side stream while the current step runs) feeds step() the same
+    batches, in the same order, as passing them to step() directly: identical losses and parameters after 4 steps."""
+    cfg, _ = CASES["tiny65"]
+    batches = [oracle.hash_inputs(cfg, 8, seed=s) for s in range(4)]
+    pinned = [(x.pin_memory(), y.pin_memory()) for x, y in batches]
+    out = []
+    for mode in ("direct", "prefetch"):
+        model = build(vb, cfg, "bf16")
+        eng = vb.TrainEngine(model, 8, use_graph=True)
+        losses = []
+        if mode == "direct":
+            for x, y in pinned:
+                losses.append(eng.step(x, y).clone())
+        else:
+            eng.prefetch(*pinned[0])
+            for i in range(4):
+                loss = eng.step()
+                if i + 1 < 4:
+                    eng.prefetch(*pinned[i + 1])
+                losses.append(loss.clone())
+        torch.cuda.synchronize()
+        out.append((torch.stack(losses).cpu(), eng.P.clone().cpu()))
+    assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])

@@ -66,14 +66,14 @@ def run(kind, M, N, K, mode, extra="", flags=0):
 
 if __name__ == "__main__":
     M = 66560
-    for pf_t, pf_k, ns1 in ((0, 0, 0), (1, 4, 0), (2, 8, 0), (4, 16, 0), (2, 8, 0x10)):
-        lib.vitb_debug_gemm_prefetch(pf_t, pf_k)
-        print(f"prefetch distance: {pf_t} tiles / {pf_k} k-blocks; " + ("single stream" if ns1 else "dual stream"))
-        run("fwd", M, 384, 384, 2 | ns1)
-        run("fwd", M, 1152, 384, 2 | ns1)
-        run("fwd", M, 384, 384, 2 | ns1, "res")
-        run("fwd", M, 384, 384, 2 | ns1, "gelu pre")
-        run("dgrad", M, 384, 384, 2 | ns1)
-        run("dgrad", M, 1152, 384, 1 | ns1)
-        run("wgrad", M, 384, 384, 0 | ns1)
-        run("wgrad", M, 1152, 384, 0 | ns1)
+    lib.vitb_debug_gemm_prefetch(2, 8)
+    for bn128 in (0x20, 0):
+        print("wgrad BN=128" if bn128 else "wgrad BN=192")
+        run("wgrad", M, 384, 384, 0 | bn128)
+        run("wgrad", M, 1152, 384, 0 | bn128)
+    run("fwd", M, 384, 384, 2)
+    run("fwd", M, 1152, 384, 2)
+    run("fwd", M, 384, 384, 2, "res")
+    run("fwd", M, 384, 384, 2, "gelu pre")
+    run("dgrad", M, 384, 384, 2)
+    run("dgrad", M, 1152, 384, 1)

@@ -17,6 +17,7 @@
 //   dgrad dX[M,K] = dY[M,N]  · W[N,K]  : A K-major,  B MN-major (reduction runs over W's rows)
 //   wgrad dW[N,K] = dY[M,N]ᵀ · X[M,K]  : A MN-major, B MN-major (reduction runs over the rows of both)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_internal.h"
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES>;
   constexpr int ACC = S::kAcc;
   static_assert(NS * ACC * BN + NS * 16 <= (int)kTmemCols || NSLAB > 0, "TMEM plan");
-  static_assert(BN == 128, "epilogue slabs assume two 64-column halves");
+  static_assert(BN == 128 || (NSLAB == 0 && BN % 64 == 0 && BN <= 256), "the slab epilogue assumes two 64-column halves; the fp32 direct-store epilogue takes any BN = 64 j");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       const int st_ = it % NS, jt = it / NS;           // stream, and the tile's index inside the stream
       const int acc = jt % ACC;
       const uint32_t acc_phase = (uint32_t)(jt / ACC) & 1u;
-      const int n0 = nb0 + half * 64;
+      const int n0 = nb0 + half * (BN / 2);
       const int grow = m0 + row_in_tile;
       if (p.has_in) {  // fetch this warp's residual / z slab while the MMAs of the tile run
         if (lane == 0) {
@@ -532,13 +533,38 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
         continue;
       }
       if (p.dbg && ew == 0 && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] += clock64() - e0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col(st_, acc) + (uint32_t)(half * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col(st_, acc) + (uint32_t)(half * (BN / 2));
+      if constexpr (NSLAB == 0) {
+        // fp32 split-K partials straight from registers: this warp owns 32 rows x BN/2 columns, drained 32 columns at a time
+        const bool do_bias = want_dbias && nblk == 0 && half == 0;
+        float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + n0;
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t raw[32];
+          tc_ld32(taddr + 32u * c, raw);
+          tc_wait_ld();
+          if (grow < p.M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n0 + 32 * c + 4 * j + 3 < p.valid_n)
+                reinterpret_cast<float4*>(o + 32 * c)[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+          }
+        }
+        if (do_bias) {
+          uint32_t rawb[16];
+          tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + bias_col(st_, acc), rawb);
+          tc_wait_ld();
+          if (grow < p.M) p.dbias_part[(size_t)split * p.M + grow] = __uint_as_float(rawb[0]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(st_, acc));
+        continue;
+      }
       uint32_t raw0[32], raw1[32];
       tc_ld32(taddr, raw0);
       tc_ld32(taddr + 32u, raw1);
-      uint32_t rawb[16];
-      const bool do_bias = want_dbias && nblk == 0 && half == 0;
-      if (do_bias) tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + bias_col(st_, acc), rawb);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -549,16 +575,6 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       for (int j = 0; j < 32; ++j) {
         v[j] = __uint_as_float(raw0[j]);
         v[32 + j] = __uint_as_float(raw1[j]);
-      }
-      if (e.mode == EPI_RAW_F32) {
-        if (grow < p.M) {
-          float* o = (float*)e.out + (size_t)split * p.M * e.ldc + (size_t)grow * e.ldc + n0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + 4 * j + 3 < p.valid_n) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (do_bias) p.dbias_part[(size_t)split * p.M + grow] = __uint_as_float(rawb[0]);
-        }
-        continue;
       }
       if (stores_pending) {  // the previous tile's TMA stores must have finished reading the slabs
         if (lane == 0 && !p.has_in) tma_store_wait_read();  // (with an input operand lane 0 already waited before refilling the slab)
@@ -736,6 +752,7 @@ static bool use_resident_weights(const TcArgs& a) {
 //   <NS, STAGES, KPS> dual stream: wgrad 2 x 3 x 32 KB;  resident 2 x 3 x 16 KB (2 x 2 with a pre-activation slab);
 //   streaming 2 x 3 x 32 KB (2 x 2 x 32 KB).   g_tc_streams = 1 (tools) selects the single-stream plans.
 static int g_tc_streams = 2;
+static int g_tc_wgrad_bn = 192;  // wgrad tile width; tools can force 128
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
@@ -744,6 +761,11 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   args.dbg_flags = g_tc_dbg_flags;
   args.pf_tiles = g_tc_pf_tiles;
   args.pf_kblocks = g_tc_pf_kblocks;
+  if constexpr (BN != 128) {
+    // wide wgrad tiles (BN = 192): a 128x192x16 MMA holds the pipe for 96 cycles, which one issuing thread can sustain, and the
+    // operand bytes per FLOP drop by a sixth; single stream, 5 stages x 40 KB
+    return launch_tc_impl<BN, A_MN, B_MN, 1, 5, 1, 0, false>(m, args, st);
+  } else {
   const bool res = !A_MN && use_resident_weights(args);
   if (g_tc_streams == 1) {
     if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 0, false>(m, args, st);
@@ -761,6 +783,7 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   }
   if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 2, 1, 2, false>(m, args, st);
   return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, false>(m, args, st);
+  }
 }
 
 // K needs only a 16-byte row pitch: a partial last k-block is zero-filled by TMA
@@ -853,6 +876,7 @@ int vitb_debug_gemm_timeline(long long* dbg, int mode) {
   g_tc_dbg = dbg;
   g_tc_force_mode = mode & 0xf;
   g_tc_streams = (mode & 0x10) ? 1 : 2;
+  g_tc_wgrad_bn = (mode & 0x20) ? 128 : 192;
   g_tc_dbg_flags = mode >> 8;
   return 0;
 }
@@ -917,12 +941,21 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
 }
 
 // split plan for wgrad on the tensor-core path
+// 192-wide tiles (single stream) win on narrow outputs, where they save a third of the fp32 partials' column blocks and a sixth of
+// the operand traffic; wide outputs (QKV: 9 row blocks) do better with 128-wide tiles on both streams (measured 68 vs 74 us)
+static int wgrad_bn(int N, int K) {
+  static const int max_rows = getenv("VITB_WGRAD_WIDE_MAX_ROWBLOCKS") ? atoi(getenv("VITB_WGRAD_WIDE_MAX_ROWBLOCKS")) : 4;  // tuning hook
+  return (g_tc_wgrad_bn == 192 && K % 192 == 0 && N / BM <= max_rows) ? 192 : kBN;
+}
+
 static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* kb_per) {
-  const int tiles = (N / BM) * (K / kBN);
+  const int bn = wgrad_bn(N, K);
+  const int tiles = (N / BM) * (K / bn);
   const int total = ceil_div(M, BK);
-  // one work item per stream of every CTA when the output is wide (QKV: 27 tiles); narrow outputs (9 tiles) keep one item per
-  // CTA, where twice the fp32 partials to write and re-read cost more than the second stream gains
-  int s = (kNumSMs * (tiles >= 18 ? g_tc_streams : 1)) / (tiles > 0 ? tiles : 1);
+  // 192-wide tiles run single-stream: one work item per CTA.  128-wide tiles: one item per stream of every CTA when the output is
+  // wide (QKV: 27 tiles); narrow outputs (9 tiles) keep one item per CTA, where twice the fp32 partials cost more than the second
+  // stream gains
+  int s = (kNumSMs * ((bn == 128 && tiles >= 18) ? g_tc_streams : 1)) / (tiles > 0 ? tiles : 1);
   if (s < 1) s = 1;
   if (s > total) s = total;
   const int per = ceil_div(total, s);
@@ -974,11 +1007,12 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
     if (make_map(&m.b, x, K, M, K, 64)) return -1;
     m.out = m.a; m.pre = m.a; m.in = m.a;  // unused in RAW mode
     TcArgs t = {};
-    t.M = N; t.N = K; t.num_m_blocks = N / BM; t.num_n_blocks = K / kBN; t.splits = splits;
+    const int bn = wgrad_bn(N, K);
+    t.M = N; t.N = K; t.num_m_blocks = N / BM; t.num_n_blocks = K / bn; t.splits = splits;
     t.kblocks_total = kb_total; t.kblocks_per_split = kb_per;
     t.e.mode = EPI_RAW_F32; t.e.ldc = K; t.e.out = splits > 1 ? part : dw; t.valid_n = K;
     t.dbias_part = dbias ? (splits > 1 ? bpart : dbias) : nullptr;  // bias gradient rides on the tensor pipe (ones-operand MMA)
-    int rc = launch_tc<kBN, true, true>(m, t, st);
+    int rc = bn == 192 ? launch_tc<192, true, true>(m, t, st) : launch_tc<kBN, true, true>(m, t, st);
     if (rc) return rc;
     if (splits > 1) {
       const int64_t n = (int64_t)N * K;
