@@ -249,6 +249,77 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// bf16 GELU backward, 16-byte accesses: a thread owns 8 consecutive columns of a few rows.  block = (cols / 8, TY), rows strided
+// over the grid.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__global__ void __launch_bounds__(512)
+    gelu_bwd_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z, bf16* __restrict__ out, float* __restrict__ ws, int rows, int cols) {
+  extern __shared__ float red8[];  // [TY][cols]
+  const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int c = tx * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int step = gridDim.x * TY;
+  auto one = [&](const uint4& av, const uint4& zv) -> uint4 {
+    float x[8], g[8];
+    unpack8(av, x);
+    unpack8(zv, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] *= gelu_grad_f(g[i]);
+      acc[i] += x[i];
+    }
+    return make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+  };
+  int r = blockIdx.x * TY + ty;
+  for (; r + 3 * step < rows; r += 4 * step) {
+    // all eight loads first, all four stores last: no store sits between the loads, so they issue back to back
+    uint4 av[4], zv[4], ov[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t off = (size_t)(r + k * step) * cols + c;
+      av[k] = __ldg(reinterpret_cast<const uint4*>(a + off));
+      zv[k] = __ldg(reinterpret_cast<const uint4*>(z + off));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ov[k] = one(av[k], zv[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + (size_t)(r + k * step) * cols + c) = ov[k];
+  }
+  for (; r < rows; r += step) {
+    const size_t off = (size_t)r * cols + c;
+    *reinterpret_cast<uint4*>(out + off) = one(__ldg(reinterpret_cast<const uint4*>(a + off)), __ldg(reinterpret_cast<const uint4*>(z + off)));
+  }
+  if (ws == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red8[ty * cols + c + i] = acc[i];
+  __syncthreads();
+  for (int j = ty * blockDim.x + tx; j < cols; j += blockDim.x * TY) {
+    float sum = 0.f;
+    for (int y = 0; y < TY; ++y) sum += red8[y * cols + j];
+    ws[(size_t)blockIdx.x * cols + j] = sum;
+  }
+}
+static bool gelu8_geom(int rows, int cols, int* ty, int* gx) {
+  if (cols % 8 != 0 || cols / 8 > 128 || cols / 8 < 16) return false;
+  const int tx = cols / 8;
+  int y = 512 / tx;
+  if (y > 8) y = 8;
+  if (y < 1) return false;
+  // ptxas sinks every load to its use, so the bytes in flight come from resident threads, not from per-thread unrolling: fill
+  // the SMs (5 blocks of <= 512 threads each at 32 registers)
+  int g = ceil_div(rows, y * 4);
+  if (g > 5 * kNumSMs) g = 5 * kNumSMs;
+  if (g < 1) g = 1;
+  *ty = y;
+  *gx = g;
+  return true;
+}
+
 struct RowsGeom {
   int tx, ty, gx, gy;
 };
@@ -274,6 +345,18 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
                               void* ws, size_t ws_bytes, int rows, int cols, cudaStream_t st) {
   RowsGeom g;
   VITB_REQUIRE(rows_geom(rows, cols, &g), "colsum: cols=%d must be a multiple of 128", cols);
+  int ty8 = 0, gx8 = 0;
+  if (gelu && sizeof(T) == 2 && gelu8_geom(rows, cols, &ty8, &gx8) && ((uintptr_t)a | (uintptr_t)z | (uintptr_t)out) % 16 == 0 &&
+      (colsum == nullptr || (ws != nullptr && ws_bytes >= (size_t)gx8 * cols * sizeof(float)))) {
+    float* w8 = colsum != nullptr ? (float*)ws : nullptr;
+    gelu_bwd_bf16x8_kernel<<<gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st>>>((const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
+    VITB_LAUNCH_OK();
+    if (colsum != nullptr) {
+      partials_finalize_kernel<0><<<finalize_grid(cols, 1), finalize_block(), 0, st>>>(w8, gx8, cols, colsum, nullptr, nullptr);
+      VITB_LAUNCH_OK();
+    }
+    return 0;
+  }
   float* wsf = nullptr;
   if (colsum != nullptr) {
     VITB_REQUIRE(ws != nullptr && ws_bytes >= (size_t)g.gx * cols * sizeof(float),
@@ -426,7 +509,9 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
 size_t vitb_colsum_ws_bytes(int rows, int cols) {
   RowsGeom g;
   if (!rows_geom(rows, cols, &g)) return 0;
-  return (size_t)g.gx * cols * sizeof(float);
+  int ty8 = 0, gx8 = 0;
+  if (!gelu8_geom(rows, cols, &ty8, &gx8)) gx8 = 0;
+  return (size_t)(g.gx > gx8 ? g.gx : gx8) * cols * sizeof(float);
 }
 
 int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes,
