@@ -183,8 +183,11 @@ def probe_kernels(eng, steps=3):
     try:
         saved_graph, eng.use_graph = eng.use_graph, False
         for _ in range(steps):
+            # Park the GPU (~25 ms spin) while the host enqueues the whole eager step: every kernel then starts the moment
+            # its predecessor ends, so an event pair brackets device time only, not host launch latency.
+            torch.cuda._sleep(50_000_000)
             eng.step()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         eng.use_graph = saved_graph
     finally:
         for n in names:
@@ -203,7 +206,24 @@ def probe_kernels(eng, steps=3):
     return table
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch", {}).get(kernel_name)
+    except (OSError, ValueError):
+        return None
+
+
 def kernel_roofline(row, pk, B, T, H):
+    r = _kernel_roofline(row, pk, B, T, H)
+    if r is not None:
+        r["traffic"] = ncu_traffic(r["kernel"])
+    return r
+
+
+def _kernel_roofline(row, pk, B, T, H):
     """Algorithmic FLOPs / bytes of one call against the measured peaks."""
     op, sh = row["op"], row["shape"]
     sec = row["ms_per_call"] * 1e-3

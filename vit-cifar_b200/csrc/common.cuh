@@ -99,6 +99,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 //   Phi(-u) = 0.5*erfc(u/sqrt2) = exp2(r(u)),  r = degree-6 polynomial fitted on u in [0,10]  (max abs error of
 //   Phi 2.0e-7, of gelu 1.8e-7, of gelu' 2.0e-7 over R: below fp32 rounding of the surrounding arithmetic)
 //   Phi(x) = x >= 0 ? 1 - Phi(-x) : Phi(-|x|).     6 FMA + 1 MUFU.EX2 instead of erff's two polynomial branches.
+// 2^x as ONE MUFU.EX2 (ex2.approx.ftz: relative error 2^-22, denormal results flush to 0).  exp2f() wraps the same instruction in
+// range guards (compare, scale by 0.5, square) that triple the instruction count of the GELU epilogues, which are ALU-bound.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float normal_cdf_f(float x) {
   const float u = fminf(fabsf(x), 10.0f);
   float r = 2.641155697e-05f;
@@ -108,13 +115,13 @@ __device__ __forceinline__ float normal_cdf_f(float x) {
   r = fmaf(r, u, -4.589958787e-01f);
   r = fmaf(r, u, -1.151131988e+00f);
   r = fmaf(r, u, -9.999994636e-01f);
-  const float e = exp2f(r);
+  const float e = ex2_approx(r);
   return x >= 0.0f ? 1.0f - e : e;
 }
 __device__ __forceinline__ float gelu_f(float x) { return x * normal_cdf_f(x); }
 // d/dx [x Phi(x)] = Phi(x) + x phi(x),  phi(x) = exp2(-x^2 * log2(e)/2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+  const float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x * x);
   return fmaf(x, pdf, normal_cdf_f(x));
 }
 

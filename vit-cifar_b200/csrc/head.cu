@@ -6,7 +6,7 @@
 //   fwd    logits[b, c] = bias[c] + sum_k a[b, k] w[c, k]          one warp per image
 //   dgrad  da[b, k]     = sum_c dlogits[b, c] w[c, k]              one thread per (image, 4 columns)
 //   wgrad  dw[c, k]     = sum_b dlogits[b, c] a[b, k],  dbias[c] = sum_b dlogits[b, c]
-//                                                                  32 columns x 8 batch slices per CTA, slices combined in order
+//                                                                  32 columns x 32 batch slices per CTA, slices combined in order
 #include "common.cuh"
 #include "gemm_internal.h"
 
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict
   st4(dx + (size_t)row * K + k, acc);
 }
 
-constexpr int kHeadCC = 16;     // classes per register pass
-constexpr int kHeadSlices = 8;  // batch slices per CTA
+constexpr int kHeadCC = 8;       // classes per register pass
+constexpr int kHeadSlices = 32;  // batch slices per CTA (the loop over the batch is latency-bound: 32 images per thread at B = 1024)
 
 template <typename T>
 __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const floa
 #pragma unroll
     for (int j = 0; j < kHeadCC; ++j) red[s][j][lane] = acc[j];
     __syncthreads();
-    // thread (s, lane) combines classes s, s + 8 of this pass for column `lane`, slices in fixed order
+    // thread (s, lane) with s < kHeadCC combines class s of this pass for column `lane`, slices in fixed order
     for (int j = s; j < kHeadCC; j += kHeadSlices) {
       if (c0 + j < N && k < K) {
         float t = red[0][j][lane];
