@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
   const uint32_t bars = sO0 + 2 * TILE_B;
   const int Hd = heads * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qkv) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_o) : "memory");
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();  // inputs come from the preceding kernel
   auto issue = [&](int item, int buf) {  // one thread
     const int b = item / heads, h = item % heads;
     const uint32_t dst = sbase + (uint32_t)buf * 3 * TILE_B, bar = bars + 8 * buf;
@@ -355,6 +357,8 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int Hd = heads * D;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();  // inputs come from the preceding kernels
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -500,6 +504,8 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
 __global__ void __launch_bounds__(128)
     attn_fwd_f32_kernel(const float* __restrict__ qkv, float* __restrict__ o, float* __restrict__ lse, float* __restrict__ attn_map,
                         int T, int heads, int D, float scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   float* sQ = reinterpret_cast<float*>(smem_attn);
   float* sK = sQ + T * D;
@@ -549,6 +555,8 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(128)
     attn_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, const float* __restrict__ lse,
                         float* __restrict__ dqkv, int T, int heads, int D, float scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_attn[];
   float* sQ = reinterpret_cast<float*>(smem_attn);
   float* sK = sQ + T * D;
@@ -626,7 +634,7 @@ static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int 
   if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
   const int items = B * heads;
   const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-  kern<<<grid, 32 * NT16, smem, st>>>(m_qkv, m_o, lse, am, items, T, heads, scale);
+  VITB_LAUNCH((kern), grid, 32 * NT16, smem, st, m_qkv, m_o, lse, am, items, T, heads, scale);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -649,7 +657,7 @@ static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, cons
   if (head_tile_map<D, NT16>(&m_dqkv, dqkv, 3 * Hd, T, B)) return -1;
   int per_sm = 1;
   VITB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NT16, smem));
-  kern<<<B * heads, 32 * NT16, smem, st>>>(m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale, kNumSMs * (per_sm > 0 ? per_sm : 1));
+  VITB_LAUNCH((kern), B * heads, 32 * NT16, smem, st, m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale, kNumSMs * (per_sm > 0 ? per_sm : 1));
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -692,7 +700,7 @@ int vitb_attn_fwd(const void* qkv, void* o, float* lse, float* attn_map, int B, 
   }
   const size_t smem = ((size_t)3 * T * d + (size_t)T * T) * sizeof(float);
   if (set_dyn_smem((const void*)attn_fwd_f32_kernel, smem)) return -1;
-  attn_fwd_f32_kernel<<<B * heads, 128, smem, st>>>((const float*)qkv, (float*)o, lse, attn_map, T, heads, d, scale);
+  VITB_LAUNCH((attn_fwd_f32_kernel), B * heads, 128, smem, st, (const float*)qkv, (float*)o, lse, attn_map, T, heads, d, scale);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -707,7 +715,7 @@ int vitb_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* 
   }
   const size_t smem = ((size_t)4 * T * d + (size_t)2 * T * T) * sizeof(float);
   if (set_dyn_smem((const void*)attn_bwd_f32_kernel, smem)) return -1;
-  attn_bwd_f32_kernel<<<B * heads, 128, smem, st>>>((const float*)qkv, (const float*)d_o, lse, (float*)dqkv, T, heads, d, scale);
+  VITB_LAUNCH((attn_bwd_f32_kernel), B * heads, 128, smem, st, (const float*)qkv, (const float*)d_o, lse, (float*)dqkv, T, heads, d, scale);
   VITB_LAUNCH_OK();
   return 0;
 }

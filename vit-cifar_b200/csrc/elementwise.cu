@@ -3,6 +3,8 @@
 // All are one-pass, 8/16-byte vectorised, warp-shuffle reductions, fp32 math on bf16/fp32 storage.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vitb {
@@ -15,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("VITB_PDL") && atoi(getenv("VITB_PDL")) != 0;
+  return on;
+}
 static unsigned long long g_launches = 0;  // host-side, single launching thread per process
 void count_launch() { ++g_launches; }
 
@@ -22,6 +28,8 @@ void count_launch() { ++g_launches; }
 // cast
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
@@ -41,6 +49,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, in
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      int rows, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int H = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -103,6 +113,8 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32)
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
                   int64_t dxs, float* __restrict__ ws, int rows) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int H = VEC * 128;
   __shared__ float red[kLnBwdWarps][H];
   const int lane = threadIdx.x & 31;
@@ -209,6 +221,8 @@ template <typename T, bool GELU_BWD>
 __global__ void __launch_bounds__(256)
     rows_colsum_kernel(const T* __restrict__ a, const T* __restrict__ z, T* __restrict__ out,
                        float* __restrict__ ws, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[256];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int c = (blockIdx.y * TX + tx) * 4;
@@ -257,6 +271,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 __global__ void __launch_bounds__(512)
     gelu_bwd_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z, bf16* __restrict__ out, float* __restrict__ ws, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red8[];  // [TY][cols]
   const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
   const int c = tx * 8;
@@ -349,10 +365,10 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
   if (gelu && sizeof(T) == 2 && gelu8_geom(rows, cols, &ty8, &gx8) && ((uintptr_t)a | (uintptr_t)z | (uintptr_t)out) % 16 == 0 &&
       (colsum == nullptr || (ws != nullptr && ws_bytes >= (size_t)gx8 * cols * sizeof(float)))) {
     float* w8 = colsum != nullptr ? (float*)ws : nullptr;
-    gelu_bwd_bf16x8_kernel<<<gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st>>>((const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
+    VITB_LAUNCH((gelu_bwd_bf16x8_kernel), gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st, (const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
     VITB_LAUNCH_OK();
     if (colsum != nullptr) {
-      partials_finalize_kernel<0><<<finalize_grid(cols, 1), finalize_block(), 0, st>>>(w8, gx8, cols, colsum, nullptr, nullptr);
+      VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(cols, 1), finalize_block(), 0, st, w8, gx8, cols, colsum, nullptr, nullptr);
       VITB_LAUNCH_OK();
     }
     return 0;
@@ -365,12 +381,12 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
   }
   dim3 grid(g.gx, g.gy), block(g.tx, g.ty);
   if (gelu)
-    rows_colsum_kernel<T, true><<<grid, block, 0, st>>>((const T*)a, (const T*)z, (T*)out, wsf, rows, cols);
+    VITB_LAUNCH((rows_colsum_kernel<T, true>), grid, block, 0, st, (const T*)a, (const T*)z, (T*)out, wsf, rows, cols);
   else
-    rows_colsum_kernel<T, false><<<grid, block, 0, st>>>((const T*)a, nullptr, nullptr, wsf, rows, cols);
+    VITB_LAUNCH((rows_colsum_kernel<T, false>), grid, block, 0, st, (const T*)a, nullptr, nullptr, wsf, rows, cols);
   VITB_LAUNCH_OK();
   if (colsum != nullptr) {
-    partials_finalize_kernel<0><<<finalize_grid(cols, 1), finalize_block(), 0, st>>>(wsf, g.gx, cols, colsum, nullptr, nullptr);
+    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(cols, 1), finalize_block(), 0, st, wsf, g.gx, cols, colsum, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   return 0;
@@ -381,6 +397,8 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn, int H, int mode) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     float4 acc = ld4(x + ((size_t)b * Tn) * H + c);
@@ -398,6 +416,8 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 
 template <typename T>
 __global__ void pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Tn, int H, int mode) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total4 = (size_t)B * Tn * H / 4;
   const float inv = 1.0f / Tn;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
@@ -443,7 +463,7 @@ int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) 
   VITB_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "cast: buffers must be 16/8-byte aligned");
   int blocks = (int)ceil_div64(n / 4 + 1, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  VITB_LAUNCH((cast_f32_bf16_kernel), blocks, 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -467,9 +487,9 @@ int vitb_layernorm_fwd(const void* x, int64_t xs, const float* gamma, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = ceil_div(rows, 8);
   if (dt == VITB_BF16) {
-    VITB_DISPATCH_VEC(H, (ln_fwd_kernel<bf16, VEC><<<blocks, 256, 0, st>>>((const bf16*)x, xs, gamma, beta, (bf16*)y, mean, rstd, rows, eps)));
+    VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_fwd_kernel<bf16, VEC>), blocks, 256, 0, st, (const bf16*)x, xs, gamma, beta, (bf16*)y, mean, rstd, rows, eps)));
   } else {
-    VITB_DISPATCH_VEC(H, (ln_fwd_kernel<float, VEC><<<blocks, 256, 0, st>>>((const float*)x, xs, gamma, beta, (float*)y, mean, rstd, rows, eps)));
+    VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_fwd_kernel<float, VEC>), blocks, 256, 0, st, (const float*)x, xs, gamma, beta, (float*)y, mean, rstd, rows, eps)));
   }
   VITB_LAUNCH_OK();
   return 0;
@@ -490,7 +510,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   const int blocks = ln_bwd_blocks(rows);
   const bool res = dres != nullptr, cs = dx_colsum != nullptr;
 #define VITB_LN_BWD(T, RES, CS)                                                                                              \
-  VITB_DISPATCH_VEC(H, (ln_bwd_kernel<T, VEC, RES, CS><<<blocks, kLnBwdWarps * 32, 0, st>>>((const T*)dy, (const T*)x, xs, gamma, mean, rstd, \
+  VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_bwd_kernel<T, VEC, RES, CS>), blocks, kLnBwdWarps * 32, 0, st, (const T*)dy, (const T*)x, xs, gamma, mean, rstd, \
                                                                                          (const T*)dres, (T*)dx, dxs, (float*)ws, rows)))
   if (dt == VITB_BF16) {
     if (res && cs) { VITB_LN_BWD(bf16, true, true); } else if (res) { VITB_LN_BWD(bf16, true, false); }
@@ -501,7 +521,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   }
 #undef VITB_LN_BWD
   VITB_LAUNCH_OK();
-  partials_finalize_kernel<0><<<finalize_grid(H, 3), finalize_block(), 0, st>>>((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
+  VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(H, 3), finalize_block(), 0, st, (const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -530,8 +550,8 @@ int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int row
 int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream) {
   VITB_REQUIRE(x && y && B > 0 && T > 0 && H % 4 == 0 && (mode == 0 || mode == 1), "pool_fwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dt == VITB_BF16) pool_fwd_kernel<bf16><<<B, 128, 0, st>>>((const bf16*)x, (bf16*)y, B, T, H, mode);
-  else pool_fwd_kernel<float><<<B, 128, 0, st>>>((const float*)x, (float*)y, B, T, H, mode);
+  if (dt == VITB_BF16) VITB_LAUNCH((pool_fwd_kernel<bf16>), B, 128, 0, st, (const bf16*)x, (bf16*)y, B, T, H, mode);
+  else VITB_LAUNCH((pool_fwd_kernel<float>), B, 128, 0, st, (const float*)x, (float*)y, B, T, H, mode);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -541,8 +561,8 @@ int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int d
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)ceil_div64((int64_t)B * T * H / 4, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  if (dt == VITB_BF16) pool_bwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dy, (bf16*)dx, B, T, H, mode);
-  else pool_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (float*)dx, B, T, H, mode);
+  if (dt == VITB_BF16) VITB_LAUNCH((pool_bwd_kernel<bf16>), blocks, 256, 0, st, (const bf16*)dy, (bf16*)dx, B, T, H, mode);
+  else VITB_LAUNCH((pool_bwd_kernel<float>), blocks, 256, 0, st, (const float*)dy, (float*)dx, B, T, H, mode);
   VITB_LAUNCH_OK();
   return 0;
 }

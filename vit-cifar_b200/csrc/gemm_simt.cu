@@ -52,6 +52,8 @@ constexpr int SK = 16;   // k tile
 
 template <typename TA, typename TB, typename TO>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[SK][SB + 4];
   __shared__ float Bs[SK][SB + 4];
   const int tid = threadIdx.x;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g) {
 int simt_gemm_launch(const SimtGemmArgs& g, int a_dt, int b_dt, int o_dt, int splits, cudaStream_t st) {
   VITB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "simt gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   dim3 grid(ceil_div(g.N, SB), ceil_div(g.M, SB), splits);
-#define L(TA, TB, TO) gemm_simt_kernel<TA, TB, TO><<<grid, 256, 0, st>>>(g)
+#define L(TA, TB, TO) VITB_LAUNCH((gemm_simt_kernel<TA, TB, TO>), grid, 256, 0, st, g)
   const int key = a_dt * 4 + b_dt * 2 + o_dt;
   switch (key) {
     case 0: L(float, float, float); break;
@@ -169,6 +171,8 @@ int simt_gemm_launch(const SimtGemmArgs& g, int a_dt, int b_dt, int o_dt, int sp
 // small column sum (any cols): out[c] = sum_r x[r*ld + c]; one thread per column, fixed order
 template <typename T>
 __global__ void colsum_small_kernel(const T* __restrict__ x, float* __restrict__ out, int rows, int cols, int64_t ld) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -177,8 +181,8 @@ __global__ void colsum_small_kernel(const T* __restrict__ x, float* __restrict__
 }
 
 int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t ld, int x_dt, cudaStream_t st) {
-  if (x_dt == VITB_BF16) colsum_small_kernel<bf16><<<ceil_div(cols, 128), 128, 0, st>>>((const bf16*)x, out, rows, cols, ld);
-  else colsum_small_kernel<float><<<ceil_div(cols, 128), 128, 0, st>>>((const float*)x, out, rows, cols, ld);
+  if (x_dt == VITB_BF16) VITB_LAUNCH((colsum_small_kernel<bf16>), ceil_div(cols, 128), 128, 0, st, (const bf16*)x, out, rows, cols, ld);
+  else VITB_LAUNCH((colsum_small_kernel<float>), ceil_div(cols, 128), 128, 0, st, (const float*)x, out, rows, cols, ld);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -200,6 +204,8 @@ int simt_pick_splits(int tiles, int K) {
 template <typename T>
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, T* __restrict__ out,
                                 int B, int Tn, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < H; c += blockDim.x) Act<T>::st(out + (size_t)b * Tn * H + c, cls[c] + pos[c]);
 }
@@ -207,6 +213,8 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 // dcls = dpos[0]; dbias[c] = sum_{t >= has_cls} dpos[t][c]
 __global__ void patch_bias_cls_kernel(const float* __restrict__ dpos, float* __restrict__ dbias, float* __restrict__ dcls,
                                       int Tn, int H, int has_cls) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= H) return;
   float s = 0.f;
@@ -218,6 +226,8 @@ __global__ void patch_bias_cls_kernel(const float* __restrict__ dpos, float* __r
 // part[s][j] = sum over the s-th slice of the batch of dout[b][j], j over T*H (fixed order; finalize sums the slices)
 template <typename T>
 __global__ void batch_sum_kernel(const T* __restrict__ x, float* __restrict__ part, int B, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t j4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j4 >= n) return;
   const int per = (B + gridDim.y - 1) / gridDim.y;
@@ -241,6 +251,8 @@ static int batch_sum_slices(int B) { return B >= 256 ? 16 : (B >= 32 ? 4 : 1); }
 
 // words[m][f..f+7] (bf16) for the tensor-core path: 8 consecutive features per thread (vit.py:79-89)
 __global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restrict__ words, int B, int S, int P) {
+  pdl_trigger();
+  pdl_wait();
   const int ps = S / P;
   const int K = ps * ps * 3, K8 = K / 8;
   const int64_t total = (int64_t)B * P * P * K8;
@@ -259,6 +271,8 @@ __global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restric
 // out[b, off+n, :] = tmp[b*PP+n, :] + pos[off+n, :];  out[b, 0, :] = cls + pos[0, :]   (vit.py:68-70), 8 columns per thread
 __global__ void patch_assemble_kernel(const bf16* __restrict__ tmp, const float* __restrict__ cls, const float* __restrict__ pos,
                                       bf16* __restrict__ out, int B, int PP, int Tn, int H, int has_cls) {
+  pdl_trigger();
+  pdl_wait();
   const int H8 = H / 8;
   const int64_t total = (int64_t)B * Tn * H8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -312,13 +326,13 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
     // tensor-core path: words (bf16) -> tcgen05 GEMM (+bias) -> assemble with cls / pos_emb
     int blocks = (int)ceil_div64((int64_t)B * PP * (K / 8), 256);
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-    words_bf16_kernel<<<blocks, 256, 0, st>>>(img, (bf16*)words, B, S, P);
+    VITB_LAUNCH((words_bf16_kernel), blocks, 256, 0, st, img, (bf16*)words, B, S, P);
     VITB_LAUNCH_OK();
     int rc = tc_patch_fwd(words, w_act, bias, ws, B * PP, H, K, st);
     if (rc) return rc;
     blocks = (int)ceil_div64((int64_t)B * Tn * (H / 8), 256);
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-    patch_assemble_kernel<<<blocks, 256, 0, st>>>((const bf16*)ws, cls, pos, (bf16*)out, B, PP, Tn, H, has_cls ? 1 : 0);
+    VITB_LAUNCH((patch_assemble_kernel), blocks, 256, 0, st, (const bf16*)ws, cls, pos, (bf16*)out, B, PP, Tn, H, has_cls ? 1 : 0);
     VITB_LAUNCH_OK();
     return 0;
   }
@@ -332,8 +346,8 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
   int rc = simt_gemm_launch(g, VITB_F32, VITB_F32, dt, 1, st);
   if (rc) return rc;
   if (has_cls) {
-    if (dt == VITB_BF16) cls_rows_kernel<bf16><<<B, 128, 0, st>>>(cls, pos, (bf16*)out, B, Tn, H);
-    else cls_rows_kernel<float><<<B, 128, 0, st>>>(cls, pos, (float*)out, B, Tn, H);
+    if (dt == VITB_BF16) VITB_LAUNCH((cls_rows_kernel<bf16>), B, 128, 0, st, cls, pos, (bf16*)out, B, Tn, H);
+    else VITB_LAUNCH((cls_rows_kernel<float>), B, 128, 0, st, cls, pos, (float*)out, B, Tn, H);
     VITB_LAUNCH_OK();
   }
   return 0;
@@ -371,14 +385,14 @@ int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, 
     const int slices = batch_sum_slices(B);
     float* bpart = slices > 1 ? (float*)((char*)ws + wg_bytes) : dpos;
     const dim3 grid((unsigned)ceil_div64(n / 4, 128), slices);
-    if (dt == VITB_BF16) batch_sum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)dout, bpart, B, n);
-    else batch_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)dout, bpart, B, n);
+    if (dt == VITB_BF16) VITB_LAUNCH((batch_sum_kernel<bf16>), grid, 128, 0, st, (const bf16*)dout, bpart, B, n);
+    else VITB_LAUNCH((batch_sum_kernel<float>), grid, 128, 0, st, (const float*)dout, bpart, B, n);
     VITB_LAUNCH_OK();
     if (slices > 1) {
-      partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(bpart, slices, n, dpos, nullptr, nullptr);
+      VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, bpart, slices, n, dpos, nullptr, nullptr);
       VITB_LAUNCH_OK();
     }
-    patch_bias_cls_kernel<<<ceil_div(H, 128), 128, 0, st>>>(dpos, dbias, dcls, Tn, H, has_cls ? 1 : 0);
+    VITB_LAUNCH((patch_bias_cls_kernel), ceil_div(H, 128), 128, 0, st, dpos, dbias, dcls, Tn, H, has_cls ? 1 : 0);
     VITB_LAUNCH_OK();
   }
   // 2) dW[h][k] = sum_m dout[phys(m)][h] * words(m,k)
@@ -396,7 +410,7 @@ int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, 
   if (rc) return rc;
   if (splits > 1) {
     const int64_t n = (int64_t)H * K;
-    partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   return 0;

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   // st = stream, s = ring stage, j = k-block inside the stage
   auto a_stage = [&](int st, int s, int j) {
@@ -294,6 +295,9 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // everything above (barriers, TMEM allocation, tensor-map prefetch, the ones operand) overlapped the previous kernel's tail;
+  // operands, residuals and outputs may belong to it: wait for it here
+  pdl_wait();
 
   const int tiles_per_split = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_per_split * p.splits;
@@ -727,7 +731,7 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
     const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
     grid = tiles < kNumSMs ? tiles : kNumSMs;
   }
-  kern<<<grid, tc_threads(NS), S::kDynBytes, st>>>(m.a, m.b, m.out, m.pre, m.in, args);
+  VITB_LAUNCH((kern), grid, tc_threads(NS), S::kDynBytes, st, m.a, m.b, m.out, m.pre, m.in, args);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -854,7 +858,7 @@ int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias,
   if (rc) return rc;
   const int64_t n = (int64_t)H * K;
   const unsigned nb = (unsigned)((n + 127) / 128 + (H + 127) / 128);
-  partials_finalize2_kernel<0><<<nb, finalize_block(), 0, st>>>(part, n, dw, bpart, H, dbias, splits);
+  VITB_LAUNCH((partials_finalize2_kernel<0>), nb, finalize_block(), 0, st, part, n, dw, bpart, H, dbias, splits);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -1018,9 +1022,9 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
       const int64_t n = (int64_t)N * K;
       if (dbias) {  // dW and the bias gradient in one launch
         const unsigned nb = (unsigned)((n + 127) / 128 + (N + 127) / 128);
-        partials_finalize2_kernel<0><<<nb, finalize_block(), 0, st>>>(part, n, dw, bpart, N, dbias, splits);
+        VITB_LAUNCH((partials_finalize2_kernel<0>), nb, finalize_block(), 0, st, part, n, dw, bpart, N, dbias, splits);
       } else {
-        partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+        VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
       }
       VITB_LAUNCH_OK();
     }
@@ -1039,7 +1043,7 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   }
   if (splits > 1) {
     const int64_t n = (int64_t)N * K;
-    partials_finalize_kernel<0><<<finalize_grid(n, 1), finalize_block(), 0, st>>>(part, splits, n, dw, nullptr, nullptr);
+    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
     VITB_LAUNCH_OK();
   }
   if (dbias != nullptr) {

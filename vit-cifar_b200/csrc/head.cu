@@ -15,6 +15,8 @@ namespace vitb {
 template <typename T>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, const T* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ out, int M, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
 template <typename T>
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx, int M, int N,
                                                          int K) {
+  pdl_trigger();
+  pdl_wait();
   const int k4 = K >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * k4) return;
@@ -60,6 +64,8 @@ constexpr int kHeadSlices = 32;  // batch slices per CTA (the loop over the batc
 template <typename T>
 __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
                                                                       float* __restrict__ dbias, int M, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[kHeadSlices][kHeadCC][32];
   const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
@@ -115,8 +121,8 @@ bool head_shape_ok(int M, int N, int K) { return N <= 128 && K % 4 == 0 && M > 0
 
 int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st) {
   const int wpb = 8;
-  if (dt == VITB_BF16) head_fwd_kernel<bf16><<<ceil_div(M, wpb), 32 * wpb, 0, st>>>((const bf16*)a, (const bf16*)w, bias, out, M, N, K);
-  else head_fwd_kernel<float><<<ceil_div(M, wpb), 32 * wpb, 0, st>>>((const float*)a, (const float*)w, bias, out, M, N, K);
+  if (dt == VITB_BF16) VITB_LAUNCH((head_fwd_kernel<bf16>), ceil_div(M, wpb), 32 * wpb, 0, st, (const bf16*)a, (const bf16*)w, bias, out, M, N, K);
+  else VITB_LAUNCH((head_fwd_kernel<float>), ceil_div(M, wpb), 32 * wpb, 0, st, (const float*)a, (const float*)w, bias, out, M, N, K);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -124,16 +130,16 @@ int head_fwd_launch(const void* a, const void* w, const float* bias, float* out,
 int head_dgrad_launch(const float* dy, const void* w, void* dx, int M, int N, int K, int dt, cudaStream_t st) {
   const int64_t n = (int64_t)M * (K / 4);
   const int blocks = (int)ceil_div64(n, 256);
-  if (dt == VITB_BF16) head_dgrad_kernel<bf16><<<blocks, 256, 0, st>>>(dy, (const bf16*)w, (bf16*)dx, M, N, K);
-  else head_dgrad_kernel<float><<<blocks, 256, 0, st>>>(dy, (const float*)w, (float*)dx, M, N, K);
+  if (dt == VITB_BF16) VITB_LAUNCH((head_dgrad_kernel<bf16>), blocks, 256, 0, st, dy, (const bf16*)w, (bf16*)dx, M, N, K);
+  else VITB_LAUNCH((head_dgrad_kernel<float>), blocks, 256, 0, st, dy, (const float*)w, (float*)dx, M, N, K);
   VITB_LAUNCH_OK();
   return 0;
 }
 
 int head_wgrad_launch(const float* dy, const void* x, float* dw, float* dbias, int M, int N, int K, int dt, cudaStream_t st) {
   const int blocks = ceil_div(K, 32);
-  if (dt == VITB_BF16) head_wgrad_kernel<bf16><<<blocks, 32 * kHeadSlices, 0, st>>>(dy, (const bf16*)x, dw, dbias, M, N, K);
-  else head_wgrad_kernel<float><<<blocks, 32 * kHeadSlices, 0, st>>>(dy, (const float*)x, dw, dbias, M, N, K);
+  if (dt == VITB_BF16) VITB_LAUNCH((head_wgrad_kernel<bf16>), blocks, 32 * kHeadSlices, 0, st, dy, (const bf16*)x, dw, dbias, M, N, K);
+  else VITB_LAUNCH((head_wgrad_kernel<float>), blocks, 32 * kHeadSlices, 0, st, dy, (const float*)x, dw, dbias, M, N, K);
   VITB_LAUNCH_OK();
   return 0;
 }

@@ -10,6 +10,8 @@ namespace vitb {
 __global__ void __launch_bounds__(1024)
     ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss,
                  float* __restrict__ dlogits, int B, int C, float smoothing, float grad_scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float off = smoothing / (float)(C - 1);
@@ -67,6 +69,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 bf16* __restrict__ shadow, int64_t n, AdamHyper hv, const float* __restrict__ hyper_dev) {
+  pdl_trigger();
+  pdl_wait();
   AdamHyper h = hv;
   if (hyper_dev != nullptr) {
     h.step_size = hyper_dev[0]; h.bc2_sqrt = hyper_dev[1]; h.beta1 = hyper_dev[2]; h.beta2 = hyper_dev[3];
@@ -105,7 +109,7 @@ int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, 
                        float smoothing, float grad_scale, void* stream) {
   VITB_REQUIRE(logits && labels && loss, "ls_ce: null pointer");
   VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
-  ls_ce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, B, C, smoothing, grad_scale);
+  VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels, loss, dlogits, B, C, smoothing, grad_scale);
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -125,7 +129,7 @@ int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow
   }
   int blocks = (int)ceil_div64(n / 4 + 1, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)w_shadow, n, h, hyper_dev);
+  VITB_LAUNCH((adam_kernel), blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)w_shadow, n, h, hyper_dev);
   VITB_LAUNCH_OK();
   return 0;
 }
