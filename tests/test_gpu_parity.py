@@ -61,6 +61,9 @@ CASES = {
                               is_cls_token=False, encoder_mlp=False), 2),
     "full65": (ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 4),
     "full17c100": (ViTConfig(num_classes=100, patch=4, num_layers=7, hidden=384, mlp_hidden=384, head=12), 4),
+    # BASELINE.json configs[4] (scaled ViT: hidden 768, MLP 3072, 12 heads -> head_dim 64) at 2 layers, both token counts
+    "scaled17": (ViTConfig(num_classes=10, patch=4, num_layers=2, hidden=768, mlp_hidden=3072, head=12), 3),
+    "scaled65": (ViTConfig(num_classes=100, patch=8, num_layers=2, hidden=768, mlp_hidden=3072, head=12), 2),
 }
 
 
