@@ -67,13 +67,11 @@ def run(kind, M, N, K, mode, extra="", flags=0):
 if __name__ == "__main__":
     M = 66560
     lib.vitb_debug_gemm_prefetch(2, 8)
-    for bn128 in (0x20, 0):
-        print("wgrad BN=128" if bn128 else "wgrad BN=192")
-        run("wgrad", M, 384, 384, 0 | bn128)
-        run("wgrad", M, 1152, 384, 0 | bn128)
-    run("fwd", M, 384, 384, 2)
-    run("fwd", M, 1152, 384, 2)
-    run("fwd", M, 384, 384, 2, "res")
-    run("fwd", M, 384, 384, 2, "gelu pre")
-    run("dgrad", M, 384, 384, 2)
-    run("dgrad", M, 1152, 384, 1)
+    for nopair in (0, 0x40):   # 0x40 switches the experimental cta_group::2 pair mode ON
+        print("cta_group::2 pairs (experimental)" if nopair else "single-CTA tiles")
+        run("fwd", M, 384, 384, 2 | nopair)
+        run("fwd", M, 1152, 384, 2 | nopair)
+        run("fwd", M, 384, 384, 2 | nopair, "res")
+        run("fwd", M, 384, 384, 2 | nopair, "gelu pre")
+        run("fwd", M, 384, 384, 2 | nopair, "gelu pre res")
+        run("dgrad", M, 384, 384, 2 | nopair)

@@ -73,6 +73,25 @@ inline cudaError_t launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, 
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
 }
+// same, as thread-block clusters of `cluster` consecutive CTAs (cta_group::2 GEMM pairs)
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_kernel_cluster(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
 // kernel expression in parentheses (template arguments contain commas)
 #define VITB_LAUNCH(kernel, grid, block, smem, stream, ...) (void)::vitb::launch_kernel(kernel, grid, block, smem, stream, __VA_ARGS__)
 

@@ -44,6 +44,7 @@ struct TcArgs {
   int a3_pp;         // > 0: the MN-major A operand is a (B, T, H) tensor read through a 3-D map, a3_pp token rows per image
   int a3_off;        //      first token row used (1 when a cls row is skipped)
   long long* dbg;    // optional per-CTA cycle counters (tools/gemm_timeline.py); null in production
+  int pair;          // resident fwd/dgrad launched as cta_group::2 pairs (num_m_blocks then counts 256-row blocks, tma_b boxes are half tiles)
   int pf_tiles;      // fwd/dgrad: prefetch the A tile this many tiles (per stream) ahead into L2; 0 = off
   int pf_kblocks;    // wgrad: prefetch operands this many k-blocks ahead into L2; 0 = off
   int dbg_flags;     // tools only: 1 = epilogue skips its work (accumulator handed straight back), 2 = producer loads nothing
@@ -114,6 +115,43 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (a pair of CTAs on adjacent SMs computes one 256-row tile; only the leader issues MMAs) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {  // the same shared-memory offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory that signals an mbarrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\n"
@@ -176,11 +214,11 @@ constexpr int kMaxResKB = 6;  // resident-B mode keeps up to 6 k-blocks (K <= 38
 // shared-memory plan: [resident B slab (W_RES)] [ring: STAGES x KPS x (A | B) tiles] [epilogue slabs / ones operand] [barriers] [tmem slot]
 // A ring stage holds KPS consecutive k-blocks behind ONE full/empty barrier pair: the MMA-issuing thread pays its
 // wait + commit round trip (which the tensor pipe cannot hide: tools/mma_bench.cu) once per 4*KPS MMAs.
-template <int BN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
+template <int BN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG = 1>
 struct TcSmem {
   static constexpr int kAcc = (NS == 2 && NSLAB == 0) ? 1 : 2;  // TMEM accumulator stages per stream (wgrad items are long: 1 is enough)
   static constexpr uint32_t kABytes = BM * BK * 2;
-  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;  // a CTA of a pair holds half of the B tile
   static constexpr uint32_t kSubBytes = W_RES ? kABytes : kABytes + kBBytes;  // one k-block
   static constexpr uint32_t kStageBytes = KPS * kSubBytes;
   static constexpr uint32_t kResBytes = W_RES ? kMaxResKB * kBBytes : 0;
@@ -224,13 +262,22 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // W_RES ("resident weights", fwd / dgrad with K <= 384): the CTA owns ONE 128-column block of the output, loads that
 // block's B operand (all k-blocks) into shared memory once, and streams only A tiles for its share of the m-blocks —
 // half the L2->SM traffic per tile of the streaming mode, which is what bounds these 384-wide GEMMs.
-template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
+// CG = 2 ("pair", resident fwd / dgrad only): two CTAs on adjacent SMs form a cluster and compute one 256-row tile with
+// tcgen05.mma.cta_group::2 — each loads its own 128 rows of A and keeps HALF of the weight block (48 KB instead of 96 KB), which
+// buys every stream a fourth ring stage (ring depth is what bounds these kernels).  The leader CTA issues the MMAs
+// for both; full / accumulator-empty barriers live in the leader (the peer's TMA loads and epilogue warps signal them remotely),
+// empty / accumulator-full barriers exist in both CTAs and are signalled by multicast tcgen05.commit.
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG>
 __global__ void __launch_bounds__(tc_threads(NS), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                    const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
-  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES>;
+  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
   constexpr int ACC = S::kAcc;
+  constexpr bool PAIR = CG == 2;
+  static_assert(!PAIR || (W_RES && !A_MN && NSLAB > 0 && KPS == 1), "pair mode: resident-weight fwd / dgrad kernels only");
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   static_assert(NS * ACC * BN + NS * 16 <= (int)kTmemCols || NSLAB > 0, "TMEM plan");
   static_assert(BN == 128 || (NSLAB == 0 && BN % 64 == 0 && BN <= 256), "the slab epilogue assumes two 64-column halves; the fp32 direct-store epilogue takes any BN = 64 j");
   extern __shared__ uint8_t smem_raw[];
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(st, a), 1);
-        mbar_init(tempty_bar(st, a), kEpiWarps);  // one arrival per epilogue warp
+        mbar_init(tempty_bar(st, a), kEpiWarps * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
       }
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(in_bar(w), 1);
@@ -282,8 +329,13 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (want_dbias && warp >= 2 * NS) {
     // all-ones bf16 operand (16 rows x 128 B, any layout reads ones); overlays the unused epilogue slabs
@@ -293,6 +345,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // everything above (barriers, TMEM allocation, tensor-map prefetch, the ones operand) overlapped the previous kernel's tail;
@@ -303,16 +356,18 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   const int num_tiles = tiles_per_split * p.splits;
   // work decomposition.  streaming: tile = blockIdx.x + it * gridDim.x over (split, m-block, n-block), n fastest.
   // W_RES: CTA = (n-block group, member); member walks m-blocks member, member + members, ...
+  // (pair mode: the unit is the CTA pair, p.num_m_blocks counts 256-row blocks)
   const int res_groups = p.num_n_blocks;
-  const int res_members = W_RES ? (int)gridDim.x / res_groups : 1;
-  const int res_group = W_RES ? (int)blockIdx.x % res_groups : 0;
-  const int res_member = W_RES ? (int)blockIdx.x / res_groups : 0;
+  const int unit = (int)blockIdx.x / CG, units = (int)gridDim.x / CG;
+  const int res_members = W_RES ? units / res_groups : 1;
+  const int res_group = W_RES ? unit % res_groups : 0;
+  const int res_member = W_RES ? unit / res_groups : 0;
   const bool res_active = !W_RES || res_member < res_members;
   auto get_tile = [&](int it, int& m0, int& n0, int& nblk, int& split) -> bool {
     if (W_RES) {
       const int mb = res_member + it * res_members;
       if (!res_active || mb >= p.num_m_blocks) return false;
-      m0 = mb * BM; nblk = res_group; n0 = nblk * BN; split = 0;
+      m0 = (mb * CG + (int)cta_rank) * BM; nblk = res_group; n0 = nblk * BN; split = 0;
       return true;
     }
     const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -331,15 +386,20 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    if (W_RES && res_active && leader && st_ == 0) {  // the weight block of this CTA: every k-block, once
-      const int n0 = res_group * BN;
-      mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.kblocks_total * S::kBBytes);
+    if (W_RES && res_active && leader && st_ == 0) {  // the weight block of this CTA (its half, in a pair): every k-block, once
+      const int n0 = res_group * BN + (int)cta_rank * (BN / CG);
+      const uint32_t wbar = PAIR ? mapa_rank(wfull_bar, 0) : wfull_bar;  // the leader's barrier collects both halves
+      if (is_leader) mbar_arrive_expect_tx(wfull_bar, (uint32_t)p.kblocks_total * S::kBBytes * CG);
       for (int kb = 0; kb < p.kblocks_total; ++kb) {
         if (!B_MN) {
-          tma_load_2d(b_res(kb), &tma_b, wfull_bar, kb * BK, n0);
+          if (PAIR) tma_load_2d_pair(b_res(kb), &tma_b, wbar, kb * BK, n0);
+          else tma_load_2d(b_res(kb), &tma_b, wfull_bar, kb * BK, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_res(kb) + j * (64 * BK * 2), &tma_b, wfull_bar, n0 + j * 64, kb * BK);
+          for (int j = 0; j < BN / CG / 64; ++j) {
+            if (PAIR) tma_load_2d_pair(b_res(kb) + j * (64 * BK * 2), &tma_b, wbar, n0 + j * 64, kb * BK);
+            else tma_load_2d(b_res(kb) + j * (64 * BK * 2), &tma_b, wfull_bar, n0 + j * 64, kb * BK);
+          }
         }
       }
     }
@@ -380,18 +440,20 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
           }
         }
         mbar_wait(empty_bar(st_, stage), phase ^ 1u);
-        const uint32_t fbar = full_bar(st_, stage);
+        // pair mode: the full barrier of the LEADER counts the bytes of both CTAs; the leader arms it, both load
+        const uint32_t fbar = PAIR ? mapa_rank(full_bar(st_, stage), 0) : full_bar(st_, stage);
         if (leader && (p.dbg_flags & 2)) {
           mbar_arrive(fbar);
         } else if (leader) {
-          mbar_arrive_expect_tx(fbar, (uint32_t)nsub * S::kSubBytes);
+          if (is_leader) mbar_arrive_expect_tx(full_bar(st_, stage), (uint32_t)nsub * S::kSubBytes * CG);
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
             if (j < nsub) {
               const int k0 = (kb + j) * BK;
               const uint32_t sa = a_stage(st_, stage, j), sb = b_stage(st_, stage, j);
               if (!A_MN) {
-                tma_load_2d(sa, &tma_a, fbar, k0, m0);
+                if (PAIR) tma_load_2d_pair(sa, &tma_a, fbar, k0, m0);
+                else tma_load_2d(sa, &tma_a, fbar, k0, m0);
               } else if (p.a3_pp > 0) {
                 // 64 reduction rows = token rows [a3_off + k0 % pp, +64) of image k0 / pp  (pp >= 64), or all pp token rows of
                 // 64 / pp consecutive images (pp < 64); the box of the 3-D map has exactly that shape
@@ -419,11 +481,12 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     }
   } else if (warp < 2 * NS) {
     // ================= MMA issuer of stream `warp - NS`: the whole warp walks the loop, one elected lane issues =================
+    // (pair mode: only the leader CTA's issuers run; their MMAs drive the tensor cores and TMEM of both SMs)
     const int st_ = warp - NS;
-    const bool leader = elect_one();
+    const bool leader = elect_one() && is_leader;
     // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     // bias-gradient MMA: same A, B = all-ones K-major tile, N = 16
     const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | (0u << 16) |
                                 ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -439,14 +502,14 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     long long t_full = 0, t_tempty = 0, t_issue = 0, t_commit = 0, t_begin = clock64();
-    if (W_RES && res_active) {
+    if (W_RES && res_active && is_leader) {
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
     }
     const long long t_w = clock64() - t_begin;
     int m0, n0, nblk, split;
     int ntiles = 0;
-    for (int it = st_; get_tile(it, m0, n0, nblk, split); it += NS) {
+    for (int it = st_; is_leader && get_tile(it, m0, n0, nblk, split); it += NS) {
       ++ntiles;
       const bool do_bias = want_dbias && nblk == 0;
       const int kb0 = split * p.kblocks_per_split;
@@ -471,7 +534,11 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
               const uint32_t a_lo = a_lo0 + (uint32_t)(stage * KPS + j) * (S::kSubBytes >> 4);
               const uint32_t b_lo = b_lo0 + (W_RES ? (uint32_t)(kb + j) * (S::kBBytes >> 4) : (uint32_t)(stage * KPS + j) * (S::kSubBytes >> 4));
               const uint32_t first = (kb + j) > kb0 ? 1u : 0u;
-              if (!do_bias) {
+              if (PAIR) {
+#pragma unroll
+                for (int kk = 0; kk < BK / UK; ++kk)
+                  tc_mma_bf16_pair(d_tmem, desc_from_lo(a_lo + kk * kAStep), desc_from_lo(b_lo + kk * kBStep), idesc, kk > 0 ? 1u : first);
+              } else if (!do_bias) {
 #pragma unroll
                 for (int kk = 0; kk < BK / UK; ++kk)
                   tc_mma_bf16(d_tmem, desc_from_lo(a_lo + kk * kAStep), desc_from_lo(b_lo + kk * kBStep), idesc, kk > 0 ? 1u : first);
@@ -485,13 +552,17 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
             }
           }
           const long long ti1 = p.dbg ? clock64() : 0;
-          tc_commit(empty_bar(st_, stage));  // frees the smem slot once these MMAs have read it
+          if (PAIR) tc_commit_pair(empty_bar(st_, stage));  // frees the slot in both CTAs
+          else tc_commit(empty_bar(st_, stage));             // frees the smem slot once these MMAs have read it
           if (p.dbg) { t_issue += ti1 - ti0; t_commit += clock64() - ti1; }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (leader) tc_commit(tfull_bar(st_, acc));  // accumulator complete
+      if (leader) {  // accumulator complete
+        if (PAIR) tc_commit_pair(tfull_bar(st_, acc));
+        else tc_commit(tfull_bar(st_, acc));
+      }
       __syncwarp();
       if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
@@ -572,7 +643,10 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(st_, acc));  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
+      if (lane == 0) {  // accumulator drained into registers: hand the TMEM stage back to the (leader's) MMA warp
+        if (PAIR && !is_leader) mbar_arrive_remote(mapa_rank(tempty_bar(st_, acc), 0));
+        else mbar_arrive(tempty_bar(st_, acc));
+      }
 
       float v[64];
 #pragma unroll
@@ -635,12 +709,14 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     if (stores_pending && lane == 0) tma_store_wait_all();
   }
 
-  // teardown: everyone done with TMEM before the owning warp frees it
+  // teardown: everyone (of both CTAs of a pair) done with TMEM and with remote barriers before the owning warp frees it
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == NS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -714,11 +790,11 @@ struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
 
-template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES>
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG = 1>
 static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
-  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES>;
+  using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
   static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NS, STAGES, KPS, NSLAB, W_RES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
@@ -726,12 +802,37 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
   }
   int grid;
   if (W_RES) {
-    grid = (kNumSMs / args.num_n_blocks) * args.num_n_blocks;  // (members per column block) x (column blocks)
+    int units = kNumSMs / CG;
+    if (CG == 2) {
+      // every pair must be resident at once (persistent kernel): ask the driver how many 2-CTA clusters of this kernel fit
+      static int max_clusters = -1;
+      if (max_clusters < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kNumSMs / 2 * 2);
+        cfg.blockDim = dim3(tc_threads(NS));
+        cfg.dynamicSmemBytes = S::kDynBytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        VITB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        max_clusters = n;
+        if (getenv("VITB_DEBUG")) fprintf(stderr, "vitb gemm_tc: max active 2-CTA clusters = %d\n", n);
+      }
+      if (units > max_clusters) units = max_clusters;
+      VITB_REQUIRE(units >= args.num_n_blocks, "gemm_tc pair mode: only %d clusters fit", units);
+    }
+    grid = CG * (units / args.num_n_blocks) * args.num_n_blocks;  // (members per column block) x (column blocks) [x 2 CTAs per pair]
   } else {
     const int tiles = args.num_m_blocks * args.num_n_blocks * args.splits;
     grid = tiles < kNumSMs ? tiles : kNumSMs;
   }
-  VITB_LAUNCH((kern), grid, tc_threads(NS), S::kDynBytes, st, m.a, m.b, m.out, m.pre, m.in, args);
+  if (CG == 2) {
+    VITB_CUDA_OK(::vitb::launch_kernel_cluster(kern, grid, tc_threads(NS), S::kDynBytes, st, 2, m.a, m.b, m.out, m.pre, m.in, args));
+  } else {
+    VITB_LAUNCH((kern), grid, tc_threads(NS), S::kDynBytes, st, m.a, m.b, m.out, m.pre, m.in, args);
+  }
   VITB_LAUNCH_OK();
   return 0;
 }
@@ -749,6 +850,18 @@ static bool use_resident_weights(const TcArgs& a) {
   if (g_tc_force_mode == 2) return true;
   const int members = kNumSMs / a.num_n_blocks;
   return a.num_m_blocks >= 2 * members;  // enough row blocks per CTA to amortise loading the weight block
+}
+
+// cta_group::2 pairs for the resident-weight kernels: EXPERIMENTAL, off unless tools switch it on.  Correct on 256-row-aligned M
+// (parity with the single-CTA path), but measured slower in round 1 (fwd 66560x384x384: 35.8 vs 25.4 us; 7.7k cycles per 256-row
+// tile per stream with large accumulator-release waits, plus ~6 us more fixed cost per cluster launch) and it still deadlocks when
+// the last pair's peer tile lies entirely beyond M — hence the M % 256 restriction.  profiles/r1_gemm_timeline_cta_pair_experiment.log
+static int g_tc_pair = 0;
+// pair mode needs the resident plan and at least two 256-row blocks per pair
+static bool use_pair(const TcArgs& a, int M) {
+  if (!g_tc_pair || M % (2 * BM) != 0 || !use_resident_weights(a) || a.num_n_blocks > kNumSMs / 2) return false;
+  const int members = (kNumSMs / 2) / a.num_n_blocks;
+  return ceil_div(M, 2 * BM) >= 2 * members;
 }
 
 // The smem rings get whatever the resident weights and the epilogue slabs leave free (227 KB per CTA):
@@ -781,6 +894,12 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
     return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, false>(m, args, st);
   }
   if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 0, false>(m, args, st);
+  if constexpr (!A_MN) {
+    if (res && args.pair) {  // cta_group::2 pairs: half the resident weights per CTA -> 4 ring stages per stream (3 with a pre-activation slab)
+      if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 2, true, 2>(m, args, st);
+      return launch_tc_impl<BN, A_MN, B_MN, 2, 4, 1, 1, true, 2>(m, args, st);
+    }
+  }
   if (res) {
     if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 2, 1, 2, true>(m, args, st);
     return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, true>(m, args, st);
@@ -881,6 +1000,7 @@ int vitb_debug_gemm_timeline(long long* dbg, int mode) {
   g_tc_force_mode = mode & 0xf;
   g_tc_streams = (mode & 0x10) ? 1 : 2;
   g_tc_wgrad_bn = (mode & 0x20) ? 128 : 192;
+  g_tc_pair = (mode & 0x40) ? 1 : 0;
   g_tc_dbg_flags = mode >> 8;
   return 0;
 }
@@ -906,6 +1026,11 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = N;
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
+    if (use_pair(t, M)) {
+      t.pair = 1;
+      t.num_m_blocks = ceil_div(M, 2 * BM);
+      if (make_map(&m.b, w, K, N, K, kBN / 2)) return -1;  // each CTA of a pair loads half of the weight block's rows
+    }
     return launch_tc<kBN, false, false>(m, t, st);
   }
   if (e.out_f32 && !e.gelu && !residual && !preact && head_shape_ok(M, N, K)) return head_fwd_launch(a, w, bias, (float*)c, M, N, K, dt, st);
@@ -935,6 +1060,10 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(N, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = K;
     t.has_in = z != nullptr;
+    if (use_pair(t, M)) {  // (the MN-major weight boxes are 64 columns wide already: one per CTA of a pair)
+      t.pair = 1;
+      t.num_m_blocks = ceil_div(M, 2 * BM);
+    }
     return launch_tc<kBN, false, true>(m, t, st);
   }
   if (dy_f32 && !z && head_shape_ok(M, N, K)) return head_dgrad_launch((const float*)dy, w, dx, M, N, K, dt, st);
