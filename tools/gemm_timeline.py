@@ -56,6 +56,10 @@ def run(kind, M, N, K, mode, extra="", flags=0):
     call(); torch.cuda.synchronize()
     lib.vitb_debug_gemm_timeline(None, 0)
     d = dbg.view(148, 8).double()
+    if mode & 0x40:  # pair mode: epilogue warp 0's accumulator-full wait, leaders (even CTAs) vs peers (odd CTAs), per stream-0 tile
+        lead, peer = d[0:144:2], d[1:144:2]
+        nt = lead[:, 4].clamp_min(1)
+        print(f"      pair mode epilogue wait_acc_full per tile: leader {(lead[:,5]/nt).mean().item():7.0f}  peer {(peer[:,5]/nt).mean().item():7.0f}")
     act = d[:, 4] > 0
     d = d[act]
     tiles = d[:, 4].mean().item()
@@ -67,11 +71,6 @@ def run(kind, M, N, K, mode, extra="", flags=0):
 if __name__ == "__main__":
     M = 66560
     lib.vitb_debug_gemm_prefetch(2, 8)
-    for nopair in (0, 0x40):   # 0x40 switches the experimental cta_group::2 pair mode ON
-        print("cta_group::2 pairs (experimental)" if nopair else "single-CTA tiles")
-        run("fwd", M, 384, 384, 2 | nopair)
-        run("fwd", M, 1152, 384, 2 | nopair)
-        run("fwd", M, 384, 384, 2 | nopair, "res")
-        run("fwd", M, 384, 384, 2 | nopair, "gelu pre")
-        run("fwd", M, 384, 384, 2 | nopair, "gelu pre res")
-        run("dgrad", M, 384, 384, 2 | nopair)
+    run("fwd", M, 384, 384, 2)
+    run("fwd", M, 384, 384, 2 | 0x40)
+    run("fwd", M, 1152, 384, 2 | 0x40)

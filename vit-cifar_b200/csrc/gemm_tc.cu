@@ -131,7 +131,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory that signals an mbarrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
@@ -853,9 +853,9 @@ static bool use_resident_weights(const TcArgs& a) {
 }
 
 // cta_group::2 pairs for the resident-weight kernels: EXPERIMENTAL, off unless tools switch it on.  Correct on 256-row-aligned M
-// (parity with the single-CTA path), but measured slower in round 1 (fwd 66560x384x384: 35.8 vs 25.4 us; 7.7k cycles per 256-row
-// tile per stream with large accumulator-release waits, plus ~6 us more fixed cost per cluster launch) and it still deadlocks when
-// the last pair's peer tile lies entirely beyond M — hence the M % 256 restriction.  profiles/r1_gemm_timeline_cta_pair_experiment.log
+// (parity with the single-CTA path) and as fast as it (fwd 66560x384x384: 26.1 vs 26.3 us) — the fourth ring stage it buys does not
+// help because these kernels are bound by L2->SM bandwidth, not ring latency.  It still deadlocks when the last
+// pair's peer tile lies entirely beyond M — hence the M % 256 restriction.  profiles/r1_gemm_timeline_cta_pair_experiment.log
 static int g_tc_pair = 0;
 // pair mode needs the resident plan and at least two 256-row blocks per pair
 static bool use_pair(const TcArgs& a, int M) {
