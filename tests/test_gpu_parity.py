@@ -294,3 +294,39 @@ def test_prefetch_pipeline_equals_direct_steps(vb):
         out.append((torch.stack(losses).cpu(), eng.P.clone().cpu()))
     assert torch.equal(out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1])
+
+
+def test_evaluate_matches_oracle_validation_step(vb):
+    """network.py:388-395 (val_loss, val_acc) through vb.evaluate on two batches vs the oracle's forward."""
+    cfg, _ = CASES["tiny17c100"]
+    model = build(vb, cfg, "fp32")
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    batches = [oracle.hash_inputs(cfg, 6, seed=s) for s in (5, 6)]
+    res = vb.evaluate(model, crit, batches)
+    params = oracle.init_params(cfg, 0)
+    loss_sum, correct, n = 0.0, 0, 0
+    for x, y in batches:
+        logits, loss, _ = oracle.train_step({k: v.clone() for k, v in params.items()}, x, y, cfg, 0.1)
+        loss_sum += float(loss) * x.shape[0]
+        correct += int((logits.argmax(-1) == y).sum())
+        n += x.shape[0]
+    assert res["n"] == n and res["val_acc"] == correct / n
+    assert abs(res["val_loss"] - loss_sum / n) < 1e-4 * abs(loss_sum / n)
+
+
+def test_module_trains_with_torch_sgd(vb):
+    """network.py:78-84: the SGD option works on the drop-in module (ordinary nn.Parameters + autograd.Functions)."""
+    cfg, B = CASES["tiny65"]
+    model = build(vb, cfg, "bf16")
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5)
+    x, y = oracle.hash_inputs(cfg, 16, seed=2)
+    x, y = x.cuda(), y.cuda()
+    losses = []
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] * 0.9

@@ -150,3 +150,85 @@ def test_bucket_allreduce_two_ranks_gloo():
     oracle.adam_step(a, {"p": gsum / 2}, z(), z(), 1)
     oracle.adam_step(b, {"p": gsum * 0.5}, z(), z(), 1)
     assert torch.equal(a["p"], b["p"])
+
+
+# ---------------------------------------------------------------------------------------------
+# LR schedule, checkpoint format
+# ---------------------------------------------------------------------------------------------
+class _GradualWarmupRestated(torch.optim.lr_scheduler._LRScheduler):
+    """Test-side restatement of ildoonet/pytorch-gradual-warmup-lr (git HEAD; the dependency the reference installs in
+    setup.sh:5 and calls at network.py:116-121; not vendored, no network here): warmup_scheduler/scheduler.py's published
+    algorithm, kept line by line so that torch's real CosineAnnealingLR is what runs after the warm-up."""
+
+    def __init__(self, optimizer, multiplier, total_epoch, after_scheduler=None):
+        self.multiplier = multiplier
+        self.total_epoch = total_epoch
+        self.after_scheduler = after_scheduler
+        self.finished = False
+        super().__init__(optimizer)
+
+    def get_lr(self):
+        if self.last_epoch > self.total_epoch:
+            if self.after_scheduler:
+                if not self.finished:
+                    self.after_scheduler.base_lrs = [base_lr * self.multiplier for base_lr in self.base_lrs]
+                    self.finished = True
+                return self.after_scheduler.get_last_lr()
+            return [base_lr * self.multiplier for base_lr in self.base_lrs]
+        if self.multiplier == 1.0:
+            return [base_lr * (float(self.last_epoch) / self.total_epoch) for base_lr in self.base_lrs]
+        return [base_lr * ((self.multiplier - 1.0) * self.last_epoch / self.total_epoch + 1.0) for base_lr in self.base_lrs]
+
+    def step(self, epoch=None, metrics=None):
+        if self.finished and self.after_scheduler:
+            self.after_scheduler.step(None)
+            self._last_lr = self.after_scheduler.get_last_lr()
+        else:
+            return super().step(epoch)
+
+
+@pytest.mark.parametrize("base_lr,min_lr,max_epochs,warmup", [(1e-3, 1e-5, 100, 5), (5e-4, 0.0, 30, 1), (1e-3, 1e-5, 12, 3)])
+def test_warmup_cosine_matches_the_reference_schedulers(base_lr, min_lr, max_epochs, warmup):
+    import warnings
+    import vit_cifar_b200 as vb
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=base_lr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=max_epochs, eta_min=min_lr)      # network.py:113-115
+        sched = _GradualWarmupRestated(opt, multiplier=1.0, total_epoch=warmup, after_scheduler=base)  # network.py:116-121
+        ours = vb.WarmupCosine(base_lr, min_lr, max_epochs, warmup)
+        for epoch in range(max_epochs):
+            lr_ref = opt.param_groups[0]["lr"]            # the LR Lightning trains epoch `epoch` with
+            assert ours(epoch) == pytest.approx(lr_ref, rel=1e-9, abs=1e-15), epoch
+            opt.step()
+            sched.step()                                  # Lightning: once per epoch
+
+
+def test_checkpoint_format_round_trip(tmp_path):
+    """main.py:234-237 writes {'state_dict': {'model.<name>': tensor}, 'hyper_parameters': {...}}; run_model.py:12-37 reads it
+    with strict=False.  Same keys as the reference model -> interchangeable both ways."""
+    import vit_cifar_b200 as vb
+    kw = dict(img_size=32, patch=4, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+    torch.manual_seed(3)
+    a = vb.ViT(3, 10, **kw)
+    hp = {"model_name": "vit", "lr": 1e-3, **kw}
+    path = tmp_path / "m.ckpt"
+    vb.save_checkpoint(a, str(path), hp)
+    raw = torch.load(str(path), map_location="cpu")
+    assert set(raw) == {"state_dict", "hyper_parameters"} and raw["hyper_parameters"] == hp
+    assert all(k.startswith("model.") for k in raw["state_dict"])
+    if reference_available():  # a reference ViT accepts the stripped keys, strictly
+        ref_vit, _, _ = import_reference()
+        ref = ref_vit.ViT(3, 10, **kw)
+        ref.load_state_dict({k[len("model."):]: v for k, v in raw["state_dict"].items()}, strict=True)
+    torch.manual_seed(4)
+    b = vb.ViT(3, 10, **kw)
+    res = vb.load_checkpoint(b, str(path))
+    assert not res.missing_keys and not res.unexpected_keys
+    for (ka, va), (kb, vb_) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb_)
+    # extra keys of a larger LightningModule (criterion buffers, ...) are ignored with strict=False
+    raw["state_dict"]["criterion.weight"] = torch.zeros(3)
+    res = vb.load_checkpoint(b, raw, strict=False)
+    assert res.unexpected_keys == ["criterion.weight"]

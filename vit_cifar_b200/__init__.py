@@ -9,6 +9,7 @@ Public surface (mirrors the reference's module/class names for this path):
   FusedAdam                                             (torch.optim.Adam as configured in network.py:71-77)
   TrainEngine                                           (the per-batch hot loop, CUDA-graphed, data-parallel)
   set_precision / get_precision                         ('bf16' tensor-core path or 'fp32' check mode)
+  WarmupCosine, evaluate, save_checkpoint, load_checkpoint   (network.py:113-122, 388-395; main.py:234-237, run_model.py:12-37)
 """
 import os as _os
 
@@ -20,3 +21,4 @@ from .vit import ViT  # noqa: E402,F401
 from .criterions import LabelSmoothingCrossEntropyLoss  # noqa: E402,F401
 from .optim import FusedAdam, adam_hyper  # noqa: E402,F401
 from .engine import TrainEngine  # noqa: E402,F401
+from .schedule import WarmupCosine, warmup_cosine_lr, evaluate, save_checkpoint, load_checkpoint, to_lightning_checkpoint  # noqa: E402,F401
