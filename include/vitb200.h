@@ -136,6 +136,13 @@ int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int d
 int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, float* dlogits,
                        int B, int C, float smoothing, float grad_scale, void* stream);
 
+/* ---- the same loss with two targets per image, network.py:149-167 (CutMix da.py:51-72, MixUp da.py:75-93):
+ * loss = lam * L(z, labels_a) + (1 - lam) * L(z, labels_b);  dlogits = (softmax(z) - (lam q_a + (1-lam) q_b)) * (grad_scale / B).
+ * labels_b NULL = plain loss.  lam_dev (device float, may be NULL) overrides lam, so a captured graph can change it per step. ---- */
+int vitb_ls_ce_mix_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam,
+                           const float* lam_dev, float* loss, float* dlogits, int B, int C, float smoothing,
+                           float grad_scale, void* stream);
+
 /* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77
  * (lr main.py:48, betas :51-52, weight_decay :56, eps 1e-8).  g is multiplied by grad_scale first
  * (1/world_size after a sum all-reduce).  hyper: 16 HOST floats {step_size = lr/(1-b1^t),

@@ -25,6 +25,7 @@ from .vit_oracle import (  # noqa: F401
     encoder_forward,
     ls_ce_loss,
     ls_ce_dlogits,
+    mixed_ls_ce_loss,
     adam_step,
     train_step,
     OracleViT,

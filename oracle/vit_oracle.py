@@ -216,6 +216,12 @@ def ls_ce_dlogits(logits: torch.Tensor, target: torch.Tensor, classes: int, smoo
     return (logits.softmax(-1) - q) / logits.shape[0]
 
 
+def mixed_ls_ce_loss(logits: torch.Tensor, target_a: torch.Tensor, target_b: torch.Tensor, lam: float, classes: int,
+                     smoothing: float) -> torch.Tensor:
+    """CutMix / MixUp objective, network.py:163-165: loss(out, label) * lambda + loss(out, rand_label) * (1 - lambda)."""
+    return ls_ce_loss(logits, target_a, classes, smoothing) * lam + ls_ce_loss(logits, target_b, classes, smoothing) * (1.0 - lam)
+
+
 # ---------------------------------------------------------------------------
 # Adam with coupled L2 (torch.optim.Adam as configured at network.py:71-77)
 # ---------------------------------------------------------------------------
@@ -244,11 +250,16 @@ def adam_step(params: Params, grads: Params, exp_avg: Params, exp_avg_sq: Params
             p.addcdiv_(exp_avg[k], denom, value=-step_size)
 
 
-def train_step(params: Params, x: torch.Tensor, y: torch.Tensor, cfg: ViTConfig, smoothing: float = 0.1):
-    """forward + LS-CE + backward on leaf copies of ``params``; returns (logits, loss, grads)."""
+def train_step(params: Params, x: torch.Tensor, y: torch.Tensor, cfg: ViTConfig, smoothing: float = 0.1,
+               y_b: Optional[torch.Tensor] = None, lam: float = 1.0):
+    """forward + LS-CE (two-target form when y_b is given, network.py:149-167) + backward on leaf copies of ``params``;
+    returns (logits, loss, grads)."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     logits = vit_forward(leaf, x, cfg)
-    loss = ls_ce_loss(logits, y, cfg.num_classes, smoothing)
+    if y_b is None:
+        loss = ls_ce_loss(logits, y, cfg.num_classes, smoothing)
+    else:
+        loss = mixed_ls_ce_loss(logits, y, y_b, lam, cfg.num_classes, smoothing)
     loss.backward()
     # tensors the forward never touches (la2 when encoder_mlp=False) keep grad None, as in the reference
     grads = {k: (v.grad.detach() if v.grad is not None else None) for k, v in leaf.items()}

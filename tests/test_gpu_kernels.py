@@ -320,3 +320,26 @@ def test_bad_arguments_raise(ops):
         ops.attn_fwd(x, x, x, None, 1, 200, 2, 32, 1.0)  # T > 128
     with pytest.raises(VitbError):
         ops.cast_f32_to_bf16(torch.zeros(4), torch.zeros(4, dtype=torch.bfloat16))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("B,C,lam", [(64, 10, 0.3), (1000, 100, 0.85), (5, 10, 1.0), (7, 10, 0.0)])
+def test_ls_ce_two_targets(ops, B, C, lam):
+    """CutMix / MixUp objective (network.py:149-167) in the fused loss kernel vs the oracle and its autograd gradient;
+    lam from the host argument and from device memory; lam = 1 reproduces the plain loss bit for bit."""
+    import oracle
+    g = torch.Generator().manual_seed(B + C)
+    z = torch.randn(B, C, generator=g) * 3
+    ya = torch.randint(0, C, (B,), generator=g); yb = torch.randint(0, C, (B,), generator=g)
+    zr = z.clone().requires_grad_(True)
+    ref = oracle.mixed_ls_ce_loss(zr, ya, yb, lam, C, 0.1)
+    ref.backward()
+    for use_dev in (False, True):
+        loss = torch.zeros((), device="cuda"); dl = torch.empty((B, C), device="cuda")
+        lam_dev = torch.tensor([lam], device="cuda") if use_dev else None
+        ops.ls_ce(cu(z), cu(ya), loss, dl, 0.1, 1.0, labels_b=cu(yb), lam=(0.5 if use_dev else lam), lam_dev=lam_dev)
+        assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+        assert rel(dl, zr.grad) < 1e-5
+    if lam == 1.0:
+        loss1 = torch.zeros((), device="cuda"); dl1 = torch.empty((B, C), device="cuda")
+        ops.ls_ce(cu(z), cu(ya), loss1, dl1, 0.1, 1.0)
+        assert loss1.item() == loss.item() and torch.equal(dl1, dl)

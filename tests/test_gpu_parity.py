@@ -330,3 +330,26 @@ def test_module_trains_with_torch_sgd(vb):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0] * 0.9
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_two_target_batches_match_oracle(vb, use_graph):
+    """CutMix / MixUp batches: TrainEngine(mixed_targets=True).step(img, y, y_b, lam) vs the oracle's training step with
+    loss = lam * L(out, y) + (1 - lam) * L(out, y_b) (network.py:149-167); lam changes every step (also under the graph)."""
+    cfg, _ = CASES["tiny65"]
+    vb.set_precision("fp32")
+    model = build(vb, cfg, "fp32")
+    eng = vb.TrainEngine(model, 8, use_graph=use_graph, lr=0.0, weight_decay=0.0, mixed_targets=True)
+    params = oracle.init_params(cfg, 0)
+    for step, lam in enumerate([0.25, 0.7, 1.0]):
+        x, y = oracle.hash_inputs(cfg, 8, seed=10 + step)
+        yb = y.flip(0)
+        loss = eng.step(x.cuda(), y.cuda(), yb.cuda(), lam).item()
+        _, loss_ref, grads_ref = oracle.train_step(params, x, y, cfg, 0.1, y_b=yb, lam=lam)
+        assert abs(loss - loss_ref.item()) < 1e-4 * abs(loss_ref.item()), (step, loss, loss_ref.item())
+        gs = grad_scale_of(grads_ref)
+        for k, g in eng.grads().items():
+            e = rel(g, grads_ref[k]) if "Wk.bias" not in k else grad_err(g, grads_ref[k], gs)
+            assert e < 1e-4, (step, k, e)
+    with pytest.raises(ValueError):
+        vb.TrainEngine(build(vb, cfg, "fp32"), 8, use_graph=False).step(x.cuda(), y.cuda(), yb.cuda(), 0.5)

@@ -136,3 +136,17 @@ def test_oracle_matches_live_reference(kw):
     assert loss.item() == pytest.approx(loss_ref.item(), rel=1e-6)
     for k, p in model.named_parameters():
         torch.testing.assert_close(grads[k], p.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_two_target_loss_is_the_reference_expression():
+    """network.py:163-165: loss(out, label) * lambda + loss(out, rand_label) * (1 - lambda), with the reference criterion when mounted."""
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(9, 10, generator=g); ya = torch.randint(0, 10, (9,), generator=g); yb = torch.randint(0, 10, (9,), generator=g)
+    lam = 0.37
+    ours = oracle.mixed_ls_ce_loss(z, ya, yb, lam, 10, 0.1)
+    manual = oracle.ls_ce_loss(z, ya, 10, 0.1) * lam + oracle.ls_ce_loss(z, yb, 10, 0.1) * (1 - lam)
+    torch.testing.assert_close(ours, manual)
+    if reference_available():
+        _, _, ref_crit = import_reference()
+        crit = ref_crit.LabelSmoothingCrossEntropyLoss(10, smoothing=0.1)
+        torch.testing.assert_close(ours, crit(z, ya) * lam + crit(z, yb) * (1 - lam), rtol=1e-6, atol=1e-7)

@@ -7,9 +7,13 @@ namespace vitb {
 // LS-CE: criterions.py:13-19.  One CTA, one thread per image (C is 10 or 100: a row is a few cache lines), rows r, r + 1024, ...;
 // the batch mean is reduced in a fixed order (lane shuffles, then the 32 warp sums serially) -> bit-reproducible.
 // ---------------------------------------------------------------------------------------------
+// Two-target form (CutMix / MixUp, network.py:149-167): loss = lam * L(z, a) + (1 - lam) * L(z, b), i.e. the smoothed target
+// distribution is q = lam * q_a + (1 - lam) * q_b.  labels_b == nullptr is the plain loss.  lam comes from device memory when
+// lam_dev != nullptr (so a captured CUDA graph sees a new value every step).
 __global__ void __launch_bounds__(1024)
-    ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss,
-                 float* __restrict__ dlogits, int B, int C, float smoothing, float grad_scale) {
+    ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const int64_t* __restrict__ labels_b, float lam_host,
+                 const float* __restrict__ lam_dev, float* __restrict__ loss, float* __restrict__ dlogits, int B, int C, float smoothing,
+                 float grad_scale) {
   pdl_trigger();
   pdl_wait();
   __shared__ float part[32];
@@ -17,10 +21,12 @@ __global__ void __launch_bounds__(1024)
   const float off = smoothing / (float)(C - 1);
   const float conf = 1.0f - smoothing;
   const float gs = grad_scale / (float)B;
+  const float lam = labels_b == nullptr ? 1.0f : (lam_dev != nullptr ? *lam_dev : lam_host);
   float acc = 0.f;
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
     const float* z = logits + (size_t)r * C;
     const int y = (int)labels[r];
+    const int yb = labels_b != nullptr ? (int)labels_b[r] : y;
     float mx = -INFINITY, sz = 0.f;
     for (int j = 0; j < C; ++j) {
       const float v = z[j];
@@ -30,14 +36,17 @@ __global__ void __launch_bounds__(1024)
     float se = 0.f;
     for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
     const float lse = mx + logf(se);
-    const float zy = z[y];
-    // sum_j -q_j (z_j - lse)
-    acc += -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
+    const float zy = z[y], zb = z[yb];
+    // sum_j -q_j (z_j - lse) for each target, then the lam mix (criterions.py:13-19 applied twice, network.py:163-165)
+    const float la = -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
+    const float lb = -(conf * (zb - lse) + off * ((sz - zb) - (float)(C - 1) * lse));
+    acc += lam * la + (1.0f - lam) * lb;
     if (dlogits != nullptr) {
       float* d = dlogits + (size_t)r * C;
       for (int j = 0; j < C; ++j) {
         const float p = expf(z[j] - lse);
-        d[j] = (p - (j == y ? conf : off)) * gs;
+        const float q = lam * (j == y ? conf : off) + (1.0f - lam) * (j == yb ? conf : off);
+        d[j] = (p - q) * gs;
       }
     }
   }
@@ -107,9 +116,15 @@ extern "C" {
 
 int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, float* dlogits, int B, int C,
                        float smoothing, float grad_scale, void* stream) {
-  VITB_REQUIRE(logits && labels && loss, "ls_ce: null pointer");
+  return vitb_ls_ce_mix_fwd_bwd(logits, labels, nullptr, 1.0f, nullptr, loss, dlogits, B, C, smoothing, grad_scale, stream);
+}
+
+int vitb_ls_ce_mix_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam, const float* lam_dev, float* loss,
+                           float* dlogits, int B, int C, float smoothing, float grad_scale, void* stream) {
+  VITB_REQUIRE(logits && labels_a && loss, "ls_ce: null pointer");
   VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
-  VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels, loss, dlogits, B, C, smoothing, grad_scale);
+  VITB_REQUIRE(lam_dev != nullptr || (lam >= 0.0f && lam <= 1.0f), "ls_ce: lam=%f outside [0, 1]", lam);
+  VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels_a, labels_b, lam, lam_dev, loss, dlogits, B, C, smoothing, grad_scale);
   VITB_LAUNCH_OK();
   return 0;
 }

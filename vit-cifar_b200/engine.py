@@ -26,7 +26,7 @@ from .vit import ViT
 class TrainEngine:
     def __init__(self, model: ViT, batch_size: int, smoothing: float = 0.1, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 5e-5, process_group=None, use_graph: bool = True,
-                 overlap_comm: bool = False):
+                 overlap_comm: bool = False, mixed_targets: bool = False):
         ops.require_device()
         self.model = model
         self.B = int(batch_size)
@@ -38,6 +38,11 @@ class TrainEngine:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.use_graph = use_graph
+        # two-target loss lam*L(out,y) + (1-lam)*L(out,y') for CutMix / MixUp batches (network.py:149-167); lam travels in the
+        # per-step hyper-parameter block so the captured graph reads a fresh value every step
+        self.mixed_targets = bool(mixed_targets)
+        self._lam = 1.0
+        self._next_lam = 1.0
         # "overlap": per-layer buckets on a side stream while backward continues; "single": one all-reduce of the whole flat
         # gradient buffer after backward (no SM contention between NCCL's CTAs and the persistent GEMM kernels)
         mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "single")
@@ -87,6 +92,8 @@ class TrainEngine:
         S = model.img_size
         self.img = torch.zeros((self.B, 3, S, S), dtype=torch.float32, device=self.dev)
         self.labels = torch.zeros((self.B,), dtype=torch.int64, device=self.dev)
+        self.labels_b = torch.zeros_like(self.labels)
+        self._labels_b_stage = torch.zeros_like(self.labels)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         # input staging for `prefetch`: the next batch crosses PCIe on a copy stream while the current step computes
         self._img_stage = torch.zeros_like(self.img)
@@ -144,7 +151,10 @@ class TrainEngine:
             saved.append(sv)
         ln_w, ln_b, fc_w_c, fc_b = self.head_p
         self.logits, hsaved = Fn.head_fwd(x, ln_w, ln_b, fc_w_c, fc_b, B, T, H, Cn, m.is_cls_token, self._alloc("head"))
-        ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0)
+        if self.mixed_targets:
+            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, labels_b=self.labels_b, lam_dev=self.hyper_dev[9:10])
+        else:
+            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0)
 
         g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
         dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
@@ -174,12 +184,16 @@ class TrainEngine:
     def set_lr(self, lr: float) -> None:
         self.lr = float(lr)
 
-    def load_batch(self, img: torch.Tensor, labels: torch.Tensor) -> None:
+    def load_batch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor] = None) -> None:
         """Copy a batch (pinned host or device tensors) into the static input buffers on the current stream."""
         self.img.copy_(img, non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
+        if self.mixed_targets:
+            self.labels_b.copy_(labels if labels_b is None else labels_b, non_blocking=True)
+        elif labels_b is not None:
+            raise ValueError("construct the engine with mixed_targets=True to train on (label, rand_label, lambda) batches")
 
-    def prefetch(self, img: torch.Tensor, labels: torch.Tensor) -> None:
+    def prefetch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> None:
         """Start copying the NEXT batch (pinned host tensors) to the device on a side stream; the following `step()` (called
         without arguments) trains on it.  Called right after `step()` returns, the host-to-device transfer overlaps that step's
         kernels — the role the DataLoader's pinned-memory prefetch plays for the reference (main.py:175)."""
@@ -188,24 +202,36 @@ class TrainEngine:
         with torch.cuda.stream(cs):
             self._img_stage.copy_(img, non_blocking=True)
             self._labels_stage.copy_(labels, non_blocking=True)
+            if self.mixed_targets:
+                self._labels_b_stage.copy_(labels if labels_b is None else labels_b, non_blocking=True)
+            elif labels_b is not None:
+                raise ValueError("construct the engine with mixed_targets=True to train on (label, rand_label, lambda) batches")
             self._staged.record(cs)
+        self._next_lam = float(lam) if labels_b is not None else 1.0
         self._pending = True
 
-    def step(self, img: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One optimisation step.  Returns the (device) loss tensor of this step; no host synchronisation."""
+    def step(self, img: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, labels_b: Optional[torch.Tensor] = None,
+             lam: float = 1.0) -> torch.Tensor:
+        """One optimisation step.  Returns the (device) loss tensor of this step; no host synchronisation.
+        `labels_b`, `lam`: the second targets and the mixing weight of a CutMix / MixUp batch (engine built with mixed_targets)."""
         if img is not None:
-            self.load_batch(img, labels)
+            self.load_batch(img, labels, labels_b)
+            self._lam = float(lam) if labels_b is not None else 1.0
         elif self._pending:
             cur = torch.cuda.current_stream()
             cur.wait_event(self._staged)
             self.img.copy_(self._img_stage, non_blocking=True)
             self.labels.copy_(self._labels_stage, non_blocking=True)
+            if self.mixed_targets:
+                self.labels_b.copy_(self._labels_b_stage, non_blocking=True)
+            self._lam = self._next_lam
             self._consumed.record(cur)
             self._pending = False
         self.step_count += 1
         h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
         slot[:9] = torch.tensor(h, dtype=torch.float32)
+        slot[9] = self._lam
         self.hyper_dev.copy_(slot, non_blocking=True)
         if not self.use_graph:
             n0 = ops.launch_count()

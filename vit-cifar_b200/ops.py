@@ -176,12 +176,20 @@ def pool_bwd(dy, dx, B: int, T: int, H: int, mode: int) -> None:
     check(_lib.load().vitb_pool_bwd(_ptr(dy), _ptr(dx), B, T, H, mode, dt_of(dx), _stream()), "pool_bwd")
 
 
-def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0) -> None:
+def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None) -> None:
+    """LS-CE forward + dlogits.  With `labels_b`: the two-target CutMix / MixUp loss lam*L(a) + (1-lam)*L(b) (network.py:149-167);
+    `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step."""
     B, Cn = logits.shape
     assert logits.dtype == torch.float32 and labels.dtype == torch.int64
     _contig(logits, labels, dlogits)
-    check(_lib.load().vitb_ls_ce_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(loss), _ptr(dlogits), B, Cn, smoothing, grad_scale, _stream()),
-          "ls_ce_fwd_bwd")
+    if labels_b is None:
+        check(_lib.load().vitb_ls_ce_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(loss), _ptr(dlogits), B, Cn, smoothing, grad_scale, _stream()),
+              "ls_ce_fwd_bwd")
+        return
+    assert labels_b.dtype == torch.int64 and labels_b.shape == labels.shape
+    _contig(labels_b)
+    check(_lib.load().vitb_ls_ce_mix_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(labels_b), float(lam), _ptr(lam_dev), _ptr(loss), _ptr(dlogits),
+                                             B, Cn, smoothing, grad_scale, _stream()), "ls_ce_mix_fwd_bwd")
 
 
 _HyperArr = C.c_float * 16
