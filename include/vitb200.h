@@ -125,6 +125,13 @@ int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum,
 int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int rows, int cols, int dt,
                 void* stream);
 
+/* ---- training input pipeline on the device, utils.py:337-355: RandomCrop(S, padding=pad) + RandomHorizontalFlip + ToTensor +
+ * Normalize(mean, std) as one gather.  img_u8 uint8 (B,S,S,3) HWC device; dx, dy int32 (B) crop offsets in [0, 2*pad] (NULL = centre);
+ * flip uint8 (B) (NULL = none); mean3 / std3: 3 HOST floats each; out fp32 (B,3,S,S).  Out-of-image pixels are black before
+ * normalisation, as torchvision pads.  The caller draws dx, dy, flip. ---- */
+int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip,
+                                     const float* mean3, const float* std3, float* out, int B, int S, int pad, void* stream);
+
 /* ---- token pooling for the head: vit.py:72-75.  mode 0: y[b] = x[b,0] (cls); mode 1: mean over T.
  * bwd: dx (B,T,H) fully written (zeros where no gradient flows). */
 int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream);

@@ -26,6 +26,7 @@ from .vit_oracle import (  # noqa: F401
     ls_ce_loss,
     ls_ce_dlogits,
     mixed_ls_ce_loss,
+    augment_crop_flip_normalize,
     adam_step,
     train_step,
     OracleViT,

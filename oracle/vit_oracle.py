@@ -216,6 +216,22 @@ def ls_ce_dlogits(logits: torch.Tensor, target: torch.Tensor, classes: int, smoo
     return (logits.softmax(-1) - q) / logits.shape[0]
 
 
+def augment_crop_flip_normalize(img_u8: torch.Tensor, dx: torch.Tensor, dy: torch.Tensor, flip: torch.Tensor, mean, std, pad: int) -> torch.Tensor:
+    """utils.py:337-355 for given random draws: RandomCrop(S, padding=pad) at offset (dy, dx) of the zero-padded image, horizontal
+    flip where flagged, ToTensor (/255, HWC -> CHW), Normalize(mean, std).  img_u8 (B,S,S,3) uint8 -> (B,3,S,S) fp32."""
+    B, S = img_u8.shape[0], img_u8.shape[1]
+    out = torch.empty((B, 3, S, S), dtype=torch.float32)
+    m = torch.tensor(mean, dtype=torch.float32).view(3, 1, 1)
+    sd = torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
+    for b in range(B):
+        padded = F.pad(img_u8[b].permute(2, 0, 1), (pad, pad, pad, pad))              # RandomCrop pads with 0 first
+        crop = padded[:, int(dy[b]):int(dy[b]) + S, int(dx[b]):int(dx[b]) + S]
+        if bool(flip[b]):
+            crop = crop.flip(-1)                                                       # RandomHorizontalFlip
+        out[b] = (crop.float() / 255.0 - m) / sd                                       # ToTensor, Normalize
+    return out
+
+
 def mixed_ls_ce_loss(logits: torch.Tensor, target_a: torch.Tensor, target_b: torch.Tensor, lam: float, classes: int,
                      smoothing: float) -> torch.Tensor:
     """CutMix / MixUp objective, network.py:163-165: loss(out, label) * lambda + loss(out, rand_label) * (1 - lambda)."""

@@ -343,3 +343,40 @@ def test_ls_ce_two_targets(ops, B, C, lam):
         loss1 = torch.zeros((), device="cuda"); dl1 = torch.empty((B, C), device="cuda")
         ops.ls_ce(cu(z), cu(ya), loss1, dl1, 0.1, 1.0)
         assert loss1.item() == loss.item() and torch.equal(dl1, dl)
+
+
+@pytest.mark.parametrize("B,S,pad", [(37, 32, 4), (4, 32, 0), (1024, 32, 4)])
+def test_augment_crop_flip_normalize(ops, B, S, pad):
+    """Device input pipeline (utils.py:337-355) vs the oracle for the same random draws; bit-exact up to one fp32 rounding."""
+    import oracle
+    g = torch.Generator().manual_seed(B)
+    img = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    dx = torch.randint(0, 2 * pad + 1, (B,), generator=g, dtype=torch.int32)
+    dy = torch.randint(0, 2 * pad + 1, (B,), generator=g, dtype=torch.int32)
+    fl = torch.randint(0, 2, (B,), generator=g, dtype=torch.uint8)
+    mean, std = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)
+    out = torch.empty((B, 3, S, S), device="cuda")
+    ops.augment(img.cuda(), dx.cuda(), dy.cuda(), fl.cuda(), mean, std, out, pad)
+    nb = min(B, 64)  # the oracle loops over images in Python
+    ref = oracle.augment_crop_flip_normalize(img[:nb], dx[:nb], dy[:nb], fl[:nb], mean, std, pad)
+    assert (out[:nb].cpu() - ref).abs().max().item() < 1e-6
+    out2 = torch.empty_like(out)
+    ops.augment(img.cuda(), None, None, None, mean, std, out2, pad)   # no draws = centre crop, no flip = plain ToTensor + Normalize
+    plain = (img.permute(0, 3, 1, 2).float() / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    assert (out2.cpu() - plain).abs().max().item() < 1e-6
+
+
+def test_gpu_augment_class_statistics(ops):
+    import vit_cifar_b200 as vb
+    aug = vb.GpuAugment(size=32, padding=4, seed=1)
+    img = torch.full((512, 32, 32, 3), 255, dtype=torch.uint8, device="cuda")
+    out = aug(img)
+    assert out.shape == (512, 3, 32, 32) and out.dtype == torch.float32
+    hi = [(1.0 - m) / s for m, s in zip(vb.schedule.CIFAR10_MEAN, vb.schedule.CIFAR10_STD)]
+    lo = [(0.0 - m) / s for m, s in zip(vb.schedule.CIFAR10_MEAN, vb.schedule.CIFAR10_STD)]
+    # every pixel is either white or padding-black after normalisation, and on average (1 - 2/8)^2-ish of the crop is image
+    for c in range(3):
+        ch = out[:, c]
+        assert torch.all(((ch - hi[c]).abs() < 1e-5) | ((ch - lo[c]).abs() < 1e-5))
+    frac = ((out[:, 0] - hi[0]).abs() < 1e-5).float().mean().item()
+    assert 0.85 < frac < 0.93   # E[(32 - |d|) / 32]^2 with d uniform in [-4, 4]: 0.879

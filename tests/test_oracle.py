@@ -150,3 +150,21 @@ def test_two_target_loss_is_the_reference_expression():
         _, _, ref_crit = import_reference()
         crit = ref_crit.LabelSmoothingCrossEntropyLoss(10, smoothing=0.1)
         torch.testing.assert_close(ours, crit(z, ya) * lam + crit(z, yb) * (1 - lam), rtol=1e-6, atol=1e-7)
+
+
+def test_augment_oracle_equals_torchvision_semantics_for_given_draws():
+    """The oracle's crop/flip/normalize against the definition spelled out with plain indexing (torchvision's RandomCrop pads with
+    zeros, crops at (top, left); flip reverses the width axis; ToTensor divides by 255; Normalize is per channel)."""
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (5, 32, 32, 3), generator=g, dtype=torch.uint8)
+    dx = torch.tensor([0, 8, 4, 3, 7]); dy = torch.tensor([8, 0, 4, 5, 1]); fl = torch.tensor([0, 1, 0, 1, 1])
+    mean, std = (0.4914, 0.4822, 0.4465), (0.2470, 0.2435, 0.2616)
+    out = oracle.augment_crop_flip_normalize(img, dx, dy, fl, mean, std, 4)
+    for b in range(5):
+        for (c, y, x) in [(0, 0, 0), (1, 31, 31), (2, 10, 20), (0, 3, 29)]:
+            xs = 31 - x if fl[b] else x
+            sy, sx = y + int(dy[b]) - 4, xs + int(dx[b]) - 4
+            v = float(img[b, sy, sx, c]) / 255.0 if (0 <= sy < 32 and 0 <= sx < 32) else 0.0
+            assert abs(out[b, c, y, x].item() - (v - mean[c]) / std[c]) < 1e-6
+    ident = oracle.augment_crop_flip_normalize(img, torch.full((5,), 4), torch.full((5,), 4), torch.zeros(5), (0, 0, 0), (1, 1, 1), 4)
+    torch.testing.assert_close(ident, img.permute(0, 3, 1, 2).float() / 255.0)

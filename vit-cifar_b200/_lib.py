@@ -51,6 +51,7 @@ SIGNATURES = {
     "vitb_colsum": (_i, [_p, _p, _p, _sz, _i, _i, _i, _p]),
     "vitb_pool_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "vitb_pool_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "vitb_augment_crop_flip_normalize": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vitb_ls_ce_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_mix_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_adam_multi": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),

@@ -437,6 +437,35 @@ __global__ void pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// training-time input pipeline on the device (utils.py:337-355): RandomCrop(S, padding) + RandomHorizontalFlip + ToTensor +
+// Normalize as one gather from the raw uint8 HWC batch; the random draws (per-image offsets, flip flags) are inputs.
+//   out[b, c, y, x] = (src(b, y + dy[b] - pad, xs + dx[b] - pad, c) / 255 - mean[c]) / std[c],  xs = flip[b] ? S-1-x : x,
+//   src = 0 outside the image (torchvision pads the PIL image with black before ToTensor / Normalize)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    augment_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ dx, const int32_t* __restrict__ dy, const uint8_t* __restrict__ flip,
+                   float m0, float m1, float m2, float s0, float s1, float s2, float* __restrict__ out, int B, int S, int pad) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t total = (int64_t)B * S * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S), y = (int)((i / S) % S), b = (int)(i / ((int64_t)S * S));
+    const int ox = dx ? dx[b] : pad, oy = dy ? dy[b] : pad;
+    const int xs = (flip && flip[b]) ? S - 1 - x : x;  // flip acts on the cropped image
+    const int sx = xs + ox - pad, sy = y + oy - pad;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    if (sx >= 0 && sx < S && sy >= 0 && sy < S) {
+      const uint8_t* p = src + (((int64_t)b * S + sy) * S + sx) * 3;
+      r = (float)p[0] * (1.0f / 255.0f); g = (float)p[1] * (1.0f / 255.0f); bl = (float)p[2] * (1.0f / 255.0f);
+    }
+    float* o = out + (int64_t)b * 3 * S * S + (int64_t)y * S + x;
+    o[0] = (r - m0) / s0;
+    o[(int64_t)S * S] = (g - m1) / s1;
+    o[(int64_t)2 * S * S] = (bl - m2) / s2;
+  }
+}
+
 }  // namespace vitb
 
 using namespace vitb;
@@ -545,6 +574,20 @@ int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int row
   VITB_REQUIRE(x && colsum && rows > 0, "colsum: null pointer / empty");
   if (dt == VITB_BF16) return launch_rows_colsum<bf16>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
   return launch_rows_colsum<float>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+}
+
+int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip, const float* mean3,
+                                     const float* std3, float* out, int B, int S, int pad, void* stream) {
+  VITB_REQUIRE(img_u8 && out && mean3 && std3, "augment: null pointer");
+  VITB_REQUIRE(B > 0 && S > 0 && pad >= 0, "augment: bad shape B=%d S=%d pad=%d", B, S, pad);
+  VITB_REQUIRE(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "augment: zero std");
+  const int64_t total = (int64_t)B * S * S;
+  int blocks = (int)ceil_div64(total, 256);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  VITB_LAUNCH((augment_kernel), blocks, 256, 0, (cudaStream_t)stream, img_u8, dx, dy, flip, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out,
+              B, S, pad);
+  VITB_LAUNCH_OK();
+  return 0;
 }
 
 int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream) {

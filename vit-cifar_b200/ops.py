@@ -176,6 +176,21 @@ def pool_bwd(dy, dx, B: int, T: int, H: int, mode: int) -> None:
     check(_lib.load().vitb_pool_bwd(_ptr(dy), _ptr(dx), B, T, H, mode, dt_of(dx), _stream()), "pool_bwd")
 
 
+_F3 = C.c_float * 3
+
+
+def augment(img_u8, dx, dy, flip, mean, std, out, pad: int) -> None:
+    """RandomCrop(pad) + RandomHorizontalFlip + ToTensor + Normalize (utils.py:337-355) of a uint8 (B,S,S,3) device batch into
+    fp32 (B,3,S,S); dx / dy (int32, device) and flip (uint8, device) are the per-image random draws (None = identity)."""
+    B, S = img_u8.shape[0], img_u8.shape[1]
+    assert img_u8.dtype == torch.uint8 and img_u8.shape == (B, S, S, 3) and out.dtype == torch.float32 and out.shape == (B, 3, S, S)
+    assert (dx is None or dx.dtype == torch.int32) and (dy is None or dy.dtype == torch.int32) and (flip is None or flip.dtype == torch.uint8)
+    _contig(img_u8, out, dx, dy, flip)
+    m, s_ = _F3(*[float(v) for v in mean]), _F3(*[float(v) for v in std])
+    check(_lib.load().vitb_augment_crop_flip_normalize(_ptr(img_u8), _ptr(dx), _ptr(dy), _ptr(flip), C.cast(m, C.c_void_p), C.cast(s_, C.c_void_p),
+                                                       _ptr(out), B, S, int(pad), _stream()), "augment_crop_flip_normalize")
+
+
 def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None) -> None:
     """LS-CE forward + dlogits.  With `labels_b`: the two-target CutMix / MixUp loss lam*L(a) + (1-lam)*L(b) (network.py:149-167);
     `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step."""

@@ -1,5 +1,5 @@
-"""Epoch-level pieces around the hot step (SURVEY.md §8f ranks 1-2): the reference's learning-rate schedule, its
-validation step and its checkpoint format.  Host code only.
+"""Epoch-level pieces around the hot step (SURVEY.md §8f ranks 1-3): the reference's learning-rate schedule, its
+validation step, its checkpoint format (host code only) and its training-time input transform on the device.
 
 Learning rate — network.py:113-122: `CosineAnnealingLR(T_max=max_epochs, eta_min=min_lr)` wrapped in
 `warmup_scheduler.GradualWarmupScheduler(multiplier=1.0, total_epoch=warmup_epoch)`, stepped once per epoch by Lightning.
@@ -80,3 +80,39 @@ def load_checkpoint(model, ckpt, strict: bool = False, prefix: str = "model."):
     sd = ckpt.get("state_dict", ckpt)
     sd = {(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in sd.items()}
     return model.load_state_dict(sd, strict=strict)
+
+
+# ---------------------------------------------------------------------------------------------
+# training-time input transform on the device (utils.py:337-355)
+# ---------------------------------------------------------------------------------------------
+CIFAR10_MEAN, CIFAR10_STD = (0.4914, 0.4822, 0.4465), (0.2470, 0.2435, 0.2616)      # utils.py:380
+CIFAR100_MEAN, CIFAR100_STD = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)    # utils.py:470
+
+
+class GpuAugment:
+    """RandomCrop(size, padding) + RandomHorizontalFlip + ToTensor + Normalize(mean, std) — get_transform's training pipeline
+    without AutoAugment — on a raw uint8 (B, S, S, 3) batch that is already on the device: one gather kernel instead of a
+    per-image PIL pipeline in DataLoader workers, and 4x fewer bytes over PCIe than normalised fp32 batches.
+    The random draws use a torch.Generator on the device (torchvision draws them on the host, per image)."""
+
+    def __init__(self, size: int = 32, padding: int = 4, mean=CIFAR10_MEAN, std=CIFAR10_STD, flip: bool = True, seed: int = 0,
+                 device="cuda"):
+        self.size, self.padding, self.mean, self.std, self.flip = int(size), int(padding), tuple(mean), tuple(std), bool(flip)
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+
+    def draw(self, B: int, device):
+        hi = 2 * self.padding + 1
+        dx = torch.randint(0, hi, (B,), generator=self.gen, device=device, dtype=torch.int32)
+        dy = torch.randint(0, hi, (B,), generator=self.gen, device=device, dtype=torch.int32)
+        fl = (torch.rand((B,), generator=self.gen, device=device) < 0.5).to(torch.uint8) if self.flip else None  # p = 0.5
+        return dx, dy, fl
+
+    def __call__(self, img_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from . import ops
+        B = img_u8.shape[0]
+        if out is None:
+            out = torch.empty((B, 3, self.size, self.size), dtype=torch.float32, device=img_u8.device)
+        dx, dy, fl = self.draw(B, img_u8.device)
+        ops.augment(img_u8, dx, dy, fl, self.mean, self.std, out, self.padding)
+        return out
