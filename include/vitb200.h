@@ -133,7 +133,8 @@ int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, c
                                      const float* mean3, const float* std3, float* out, int B, int S, int pad, void* stream);
 
 /* ---- token pooling for the head: vit.py:72-75.  mode 0: y[b] = x[b,0] (cls); mode 1: mean over T.
- * bwd: dx (B,T,H) fully written (zeros where no gradient flows). */
+ * bwd: dx (B,T,H) fully written (zeros where no gradient flows); mode 2 = cls pooling into a dx whose other rows the caller
+ * keeps zero (a static buffer zeroed once): only the B cls rows are written. */
 int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt, void* stream);
 int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int dt, void* stream);
 

@@ -275,6 +275,13 @@ def test_pool(ops, dtype, mode):
     else:
         ref[:] = dy.float()[:, None] / T
     assert rel(dx, ref) < tol(dtype)
+    if mode == 0:  # mode 2: cls rows only, into a buffer the caller keeps zero elsewhere
+        dx2 = torch.zeros((B, T, H), dtype=dtype, device="cuda")
+        ops.pool_bwd(cu(dy), dx2, B, T, H, 2)
+        assert torch.equal(dx2, dx)
+        dx2[:, 1:] = 3.0
+        ops.pool_bwd(cu(dy), dx2, B, T, H, 2)
+        assert torch.equal(dx2[:, 0], dx[:, 0]) and bool((dx2[:, 1:] == 3.0).all())  # really writes nothing else
 
 
 @pytest.mark.parametrize("B,C", [(4, 10), (128, 100), (1000, 10), (3, 1000)])

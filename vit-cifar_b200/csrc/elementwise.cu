@@ -437,6 +437,20 @@ __global__ void pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, in
   }
 }
 
+// mode 2: only the cls rows (token 0) of dx are written; the other rows must already be zero (a static, pre-zeroed buffer)
+template <typename T>
+__global__ void pool_bwd_cls_rows_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Tn, int H) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t total4 = (int64_t)B * H / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 4;
+    const int c = (int)(e % H);
+    const int64_t b = e / H;
+    st4(dx + (b * Tn) * H + c, ld4(dy + b * H + c));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // training-time input pipeline on the device (utils.py:337-355): RandomCrop(S, padding) + RandomHorizontalFlip + ToTensor +
 // Normalize as one gather from the raw uint8 HWC batch; the random draws (per-image offsets, flip flags) are inputs.
@@ -600,8 +614,15 @@ int vitb_pool_fwd(const void* x, void* y, int B, int T, int H, int mode, int dt,
 }
 
 int vitb_pool_bwd(const void* dy, void* dx, int B, int T, int H, int mode, int dt, void* stream) {
-  VITB_REQUIRE(dy && dx && B > 0 && T > 0 && H % 4 == 0 && (mode == 0 || mode == 1), "pool_bwd: bad argument");
+  VITB_REQUIRE(dy && dx && B > 0 && T > 0 && H % 4 == 0 && (mode == 0 || mode == 1 || mode == 2), "pool_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 2) {  // cls rows only, the rest of dx is already zero
+    const int nb = (int)ceil_div64((int64_t)B * H / 4, 256);
+    if (dt == VITB_BF16) VITB_LAUNCH((pool_bwd_cls_rows_kernel<bf16>), nb, 256, 0, st, (const bf16*)dy, (bf16*)dx, B, T, H);
+    else VITB_LAUNCH((pool_bwd_cls_rows_kernel<float>), nb, 256, 0, st, (const float*)dy, (float*)dx, B, T, H);
+    VITB_LAUNCH_OK();
+    return 0;
+  }
   int blocks = (int)ceil_div64((int64_t)B * T * H / 4, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (dt == VITB_BF16) VITB_LAUNCH((pool_bwd_kernel<bf16>), blocks, 256, 0, st, (const bf16*)dy, (bf16*)dx, B, T, H, mode);

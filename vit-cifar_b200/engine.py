@@ -120,7 +120,8 @@ class TrainEngine:
             key = f"{scope}.{name}"
             t = self._bufs.get(key)
             if t is None:
-                t = torch.empty(shape, dtype=dtype, device=self.dev)
+                # "dxL" (gradient of the last block's output): only its cls rows are ever written, the rest must read as zero
+                t = (torch.zeros if name == "dxL" else torch.empty)(shape, dtype=dtype, device=self.dev)
                 self._bufs[key] = t
             return t
         return alloc
@@ -158,7 +159,7 @@ class TrainEngine:
 
         g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
         dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
-                         self._alloc("headb"))
+                         self._alloc("headb"), dx_prezeroed=True)
         self._allreduce(self.buckets[-1])
         for i in reversed(range(m.num_layers)):
             # backward scratch is shared by all layers; the input-gradient buffer ping-pongs

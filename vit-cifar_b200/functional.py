@@ -180,7 +180,7 @@ def head_fwd(x: torch.Tensor, ln_w, ln_b, fc_w_c, fc_b, B: int, T: int, H: int, 
 
 
 def head_bwd(dlogits: torch.Tensor, saved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B: int, T: int, H: int, C: int,
-             is_cls: bool, act: torch.dtype, alloc: Alloc) -> torch.Tensor:
+             is_cls: bool, act: torch.dtype, alloc: Alloc, dx_prezeroed: bool = False) -> torch.Tensor:
     """dlogits (B,C) fp32 -> grad of the encoder output (B*T,H) act (zeros where nothing flows)."""
     src, stride, hn, mean, rstd = saved
     ops.gemm_wgrad(dlogits, hn, g_fc_w, g_fc_b, B, C, H, dy_f32=True)
@@ -189,5 +189,6 @@ def head_bwd(dlogits: torch.Tensor, saved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w,
     dpool = alloc("dpool", (B, H), act)
     ops.layernorm_bwd(dhn, src, stride, ln_w, mean, rstd, None, dpool, H, g_ln_w, g_ln_b, None, B, H)
     dx = alloc("dxL", (B * T, H), act)
-    ops.pool_bwd(dpool, dx, B, T, H, 0 if is_cls else 1)
+    # dx_prezeroed: `alloc` hands out a static buffer whose non-cls rows are zero and stay zero (TrainEngine): write B rows, not B*T
+    ops.pool_bwd(dpool, dx, B, T, H, (2 if dx_prezeroed else 0) if is_cls else 1)
     return dx
