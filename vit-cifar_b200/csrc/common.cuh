@@ -257,7 +257,60 @@ __global__ void __launch_bounds__(256) partials_finalize2_kernel(const float* __
   else finalize_block_cols(ws1, nparts, cols1, out1, blockIdx.x - nb0, gridDim.x - nb0);
 }
 
+// "tall" variant for MANY partial rows of FEW columns (LayerNorm / GELU column sums: 300-740 partials x 384): block (8, 64) =
+// 8 four-column lanes x 64 slices of the partials, grid (ceil(cols / 32), outputs).  The plain kernel would run such a shape on 3
+// blocks whose threads each walk ~90 dependent L2 round trips (21 us for 1 MB); here a thread walks nparts / 64 of them.
+// Slices are combined in a fixed order (8 groups of 8, then the 8 group sums): deterministic.
+template <int kUnused = 0>
+__global__ void __launch_bounds__(512) partials_finalize_tall_kernel(const float* __restrict__ ws, int nparts, int64_t cols, float* out0, float* out1,
+                                                                     float* out2) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float4 red[64][8];
+  const int k = blockIdx.y;
+  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+  if (out == nullptr) return;
+  const float* base = ws + (size_t)k * nparts * cols;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t c = ((int64_t)blockIdx.x * 8 + tx) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    for (int i = ty; i < nparts; i += 64) {
+      const float4 a = *reinterpret_cast<const float4*>(base + (size_t)i * cols + c);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty < 8) {  // group ty sums slices 8 ty .. 8 ty + 7
+    float4 r = red[8 * ty][tx];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const float4 o = red[8 * ty + j][tx];
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    red[8 * ty][tx] = r;
+  }
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float4 r = red[0][tx];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const float4 o = red[8 * j][tx];
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    *reinterpret_cast<float4*>(out + c) = r;
+  }
+}
+
 inline dim3 finalize_grid(int64_t cols, int nout) { return dim3((unsigned)((cols + 127) / 128), (unsigned)nout); }
+// picks the tall kernel for many partials of a narrow output, the plain one otherwise (one launch either way)
+inline cudaError_t launch_finalize(const float* ws, int nparts, int64_t cols, float* out0, float* out1, float* out2, int nout, cudaStream_t st) {
+  if ((cols & 3) == 0 && nparts >= 64 && cols <= 8192)
+    return launch_kernel(partials_finalize_tall_kernel<0>, dim3((unsigned)((cols + 31) / 32), (unsigned)nout), dim3(8, 64), 0, st, ws, nparts, cols, out0,
+                         out1, out2);
+  return launch_kernel(partials_finalize_kernel<0>, finalize_grid(cols, nout), dim3(32, 8), 0, st, ws, nparts, cols, out0, out1, out2);
+}
 inline dim3 finalize_block() { return dim3(32, 8); }
 
 // ---------------------------------------------------------------------------------------------

@@ -368,7 +368,7 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
     VITB_LAUNCH((gelu_bwd_bf16x8_kernel), gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st, (const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
     VITB_LAUNCH_OK();
     if (colsum != nullptr) {
-      VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(cols, 1), finalize_block(), 0, st, w8, gx8, cols, colsum, nullptr, nullptr);
+      (void)::vitb::launch_finalize(w8, gx8, cols, colsum, nullptr, nullptr, 1, st);
       VITB_LAUNCH_OK();
     }
     return 0;
@@ -386,7 +386,7 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
     VITB_LAUNCH((rows_colsum_kernel<T, false>), grid, block, 0, st, (const T*)a, nullptr, nullptr, wsf, rows, cols);
   VITB_LAUNCH_OK();
   if (colsum != nullptr) {
-    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(cols, 1), finalize_block(), 0, st, wsf, g.gx, cols, colsum, nullptr, nullptr);
+    (void)::vitb::launch_finalize(wsf, g.gx, cols, colsum, nullptr, nullptr, 1, st);
     VITB_LAUNCH_OK();
   }
   return 0;
@@ -564,7 +564,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   }
 #undef VITB_LN_BWD
   VITB_LAUNCH_OK();
-  VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(H, 3), finalize_block(), 0, st, (const float*)ws, blocks, H, dgamma, dbeta, dx_colsum);
+  (void)::vitb::launch_finalize((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum, 3, st);
   VITB_LAUNCH_OK();
   return 0;
 }

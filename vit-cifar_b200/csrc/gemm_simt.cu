@@ -389,7 +389,7 @@ int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, 
     else VITB_LAUNCH((batch_sum_kernel<float>), grid, 128, 0, st, (const float*)dout, bpart, B, n);
     VITB_LAUNCH_OK();
     if (slices > 1) {
-      VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, bpart, slices, n, dpos, nullptr, nullptr);
+      (void)::vitb::launch_finalize(bpart, slices, n, dpos, nullptr, nullptr, 1, st);
       VITB_LAUNCH_OK();
     }
     VITB_LAUNCH((patch_bias_cls_kernel), ceil_div(H, 128), 128, 0, st, dpos, dbias, dcls, Tn, H, has_cls ? 1 : 0);
@@ -410,7 +410,7 @@ int vitb_patch_embed_bwd(const float* img, const void* words, const void* dout, 
   if (rc) return rc;
   if (splits > 1) {
     const int64_t n = (int64_t)H * K;
-    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
+    (void)::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st);
     VITB_LAUNCH_OK();
   }
   return 0;

@@ -1153,7 +1153,7 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
         const unsigned nb = (unsigned)((n + 127) / 128 + (N + 127) / 128);
         VITB_LAUNCH((partials_finalize2_kernel<0>), nb, finalize_block(), 0, st, part, n, dw, bpart, N, dbias, splits);
       } else {
-        VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
+        (void)::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st);
       }
       VITB_LAUNCH_OK();
     }
@@ -1172,7 +1172,7 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   }
   if (splits > 1) {
     const int64_t n = (int64_t)N * K;
-    VITB_LAUNCH((partials_finalize_kernel<0>), finalize_grid(n, 1), finalize_block(), 0, st, part, splits, n, dw, nullptr, nullptr);
+    (void)::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st);
     VITB_LAUNCH_OK();
   }
   if (dbias != nullptr) {

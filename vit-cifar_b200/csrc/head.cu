@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const floa
 #pragma unroll
     for (int j = 0; j < kHeadCC; ++j) acc[j] = 0.f;
     if (k < K) {
+#pragma unroll 4  // four images' loads in flight per thread: the loop is latency-bound
       for (int b = s; b < M; b += kHeadSlices) {
         const float xv = Act<T>::ld(x + (size_t)b * K + k);
         const float* d = dy + (size_t)b * N + c0;
@@ -102,8 +103,10 @@ __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const floa
     for (int c0 = 0; c0 < N; c0 += 32) {
       const int c = c0 + lane;
       float t = 0.f;
-      if (c < N)
+      if (c < N) {
+#pragma unroll 4
         for (int b = s; b < M; b += kHeadSlices) t += dy[(size_t)b * N + c];
+      }
       r2[s * 32 + lane] = t;
       __syncthreads();
       if (s == 0 && c < N) {
