@@ -173,6 +173,7 @@ def probe_kernels(eng, steps=3):
             flags = tuple(sorted((kk, vv) for kk, vv in k.items() if isinstance(vv, bool) and vv))
             extra = ("res",) if name == "gemm_fwd" and a[3] is not None else ()
             extra += ("z",) if name == "gemm_dgrad" and a[2] is not None else ()
+            extra += ("colsum",) if name == "layernorm_bwd" and a[11] is not None else ()
             rec.append((name, shape, flags + extra, s, e))
             return r
         return inner
