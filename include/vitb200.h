@@ -132,6 +132,16 @@ int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int row
 int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip,
                                      const float* mean3, const float* std3, float* out, int B, int S, int pad, void* stream);
 
+/* ---- nn.Dropout of the encoder block (layers.py:35, 38, 102; replaces torch's native_dropout on this path):
+ *   out[i] = x[i] * keep[i] / (1 - p)  (+ residual[i] if residual != NULL);  x / residual / out act, n elements, n % 8 == 0; in place allowed.
+ * keep is not stored: it is Philox4x32-10 with key = seed and counter = (i / 8 as 64 bits, site, step); element i takes the 16-bit
+ * field (i % 8) of the 128-bit output (word (i % 8) / 2, low half first) and is kept iff field >= vitb_dropout_threshold(p)
+ * = round(p * 65536) (host function, no GPU).  The backward pass is the same call on the gradient with the same (seed, site, step).
+ * step_dev != NULL: the step is read from that device word instead of `step` (CUDA-graph replays draw fresh masks). 0 <= p < 1. ---- */
+uint32_t vitb_dropout_threshold(float p);
+int vitb_dropout(const void* x, const void* residual, void* out, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step,
+                 const uint32_t* step_dev, int dt, void* stream);
+
 /* ---- token pooling for the head: vit.py:72-75.  mode 0: y[b] = x[b,0] (cls); mode 1: mean over T.
  * bwd: dx (B,T,H) fully written (zeros where no gradient flows); mode 2 = cls pooling into a dx whose other rows the caller
  * keeps zero (a static buffer zeroed once): only the B cls rows are written. */

@@ -26,6 +26,10 @@ from .vit_oracle import (  # noqa: F401
     ls_ce_loss,
     ls_ce_dlogits,
     mixed_ls_ce_loss,
+    philox4x32_10,
+    dropout_threshold,
+    dropout_keep_mask,
+    philox_drop,
     augment_crop_flip_normalize,
     adam_step,
     train_step,

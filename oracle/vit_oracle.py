@@ -145,8 +145,54 @@ def to_words(x: torch.Tensor, cfg: ViTConfig) -> torch.Tensor:
     return out.reshape(x.size(0), cfg.patch ** 2, -1)
 
 
+# ---------------------------------------------------------------------------
+# nn.Dropout (layers.py:35, 38, 102).  The reference draws its masks from torch's generator; the build draws them from a
+# counter-based generator (include/vitb200.h, vitb_dropout) restated here in numpy so that tests can replay the exact masks.
+# `drop` arguments below are callables (site, tensor) -> tensor implementing `tensor * keep / (1 - p)`; None = eval / p = 0.
+# ---------------------------------------------------------------------------
+def philox4x32_10(counter: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
+    """Philox4x32 with 10 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter (n,4) uint32,
+    key two uint32 words -> (n,4) uint32."""
+    c = [counter[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0] & 0xFFFFFFFF), np.uint64(key[1] & 0xFFFFFFFF)
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def dropout_threshold(p: float) -> int:
+    t = int(p * 65536.0 + 0.5)
+    return min(max(t, 0), 65535)
+
+
+def dropout_keep_mask(n: int, p: float, seed: int, site: int, step: int) -> np.ndarray:
+    """The keep mask (bool, n) libvitb200 uses for (seed, site, step): one Philox call per group of 8 elements, counter =
+    (group lo, group hi, site, step), key = seed; element j of a group takes 16-bit field j of the output and is kept iff it
+    is >= round(p * 65536)."""
+    assert n % 8 == 0
+    g = np.arange(n // 8, dtype=np.uint64)
+    ctr = np.stack([(g & np.uint64(0xFFFFFFFF)).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
+                    np.full(g.shape, site, np.uint32), np.full(g.shape, step & 0xFFFFFFFF, np.uint32)], axis=1)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    fields = np.stack([(r[:, j >> 1] >> np.uint32(16 * (j & 1))) & np.uint32(0xFFFF) for j in range(8)], axis=1)
+    return (fields >= dropout_threshold(p)).reshape(-1)
+
+
+def philox_drop(p: float, seed: int, step: int):
+    """(site, tensor) -> tensor * keep / (1 - p) with libvitb200's mask for one encoder block's stream."""
+    def drop(site: int, t: torch.Tensor) -> torch.Tensor:
+        keep = torch.from_numpy(dropout_keep_mask(t.numel(), p, seed, site, step)).view(t.shape)
+        return t * keep.to(t.dtype) / (1.0 - p)
+    return drop
+
+
 def mhsa_forward(p: Params, prefix: str, x: torch.Tensor, head: int,
-                 return_attn: bool = False):
+                 return_attn: bool = False, drop=None):
     """layers.py:90-103.  Scale is 1/sqrt(features) (layers.py:79, 97), not 1/sqrt(head_dim)."""
     B, T, Fdim = x.shape
     d = Fdim // head
@@ -156,15 +202,17 @@ def mhsa_forward(p: Params, prefix: str, x: torch.Tensor, head: int,
     attn_map = F.softmax(torch.einsum("bhif,bhjf->bhij", q, k) / (Fdim ** 0.5), dim=-1)
     attn = torch.einsum("bhij,bhjf->bihf", attn_map, v)
     out = F.linear(attn.flatten(2), p[prefix + "out_project.weight"], p[prefix + "out_project.bias"])
+    if drop is not None:
+        out = drop(0, out)  # layers.py:102
     return (out, attn_map) if return_attn else out
 
 
 def encoder_forward(p: Params, prefix: str, x: torch.Tensor, head: int, use_mlp: bool = True,
-                    return_attn: bool = False):
+                    return_attn: bool = False, drop=None):
     """layers.py:44-48 (pre-LN residual wiring) and layers.py:32-39 (Linear-GELU-Linear-GELU)."""
     H = x.shape[-1]
     h1 = F.layer_norm(x, (H,), p[prefix + "la1.weight"], p[prefix + "la1.bias"], 1e-5)
-    a = mhsa_forward(p, prefix + "attention.", h1, head, return_attn)
+    a = mhsa_forward(p, prefix + "attention.", h1, head, return_attn, drop)
     attn_map = None
     if return_attn:
         a, attn_map = a
@@ -172,13 +220,18 @@ def encoder_forward(p: Params, prefix: str, x: torch.Tensor, head: int, use_mlp:
     if use_mlp:
         h2 = F.layer_norm(out, (H,), p[prefix + "la2.weight"], p[prefix + "la2.bias"], 1e-5)
         m = F.gelu(F.linear(h2, p[prefix + "mlp.0.weight"], p[prefix + "mlp.0.bias"]))
+        if drop is not None:
+            m = drop(1, m)  # layers.py:35
         m = F.gelu(F.linear(m, p[prefix + "mlp.3.weight"], p[prefix + "mlp.3.bias"]))
+        if drop is not None:
+            m = drop(2, m)  # layers.py:38
         out = m + out
     return (out, attn_map) if return_attn else out
 
 
-def vit_forward(p: Params, x: torch.Tensor, cfg: ViTConfig, return_attn: bool = False):
-    """vit.py:65-77 (dropout = 0 / eval; the reference default, main.py:87)."""
+def vit_forward(p: Params, x: torch.Tensor, cfg: ViTConfig, return_attn: bool = False, drops=None):
+    """vit.py:65-77.  `drops`: None (eval, or dropout = 0: the reference default, main.py:87) or one (site, tensor) -> tensor
+    callable per encoder block (training with dropout > 0)."""
     out = to_words(x, cfg)
     out = F.linear(out, p["emb.weight"], p["emb.bias"])  # vit.py:67
     if cfg.is_cls_token:
@@ -186,7 +239,7 @@ def vit_forward(p: Params, x: torch.Tensor, cfg: ViTConfig, return_attn: bool = 
     out = out + p["pos_emb"]  # vit.py:70
     maps = []
     for i in range(cfg.num_layers):  # vit.py:71
-        out = encoder_forward(p, f"enc.{i}.", out, cfg.head, cfg.encoder_mlp, return_attn)
+        out = encoder_forward(p, f"enc.{i}.", out, cfg.head, cfg.encoder_mlp, return_attn, drops[i] if drops is not None else None)
         if return_attn:
             out, am = out
             maps.append(am)
@@ -267,11 +320,11 @@ def adam_step(params: Params, grads: Params, exp_avg: Params, exp_avg_sq: Params
 
 
 def train_step(params: Params, x: torch.Tensor, y: torch.Tensor, cfg: ViTConfig, smoothing: float = 0.1,
-               y_b: Optional[torch.Tensor] = None, lam: float = 1.0):
+               y_b: Optional[torch.Tensor] = None, lam: float = 1.0, drops=None):
     """forward + LS-CE (two-target form when y_b is given, network.py:149-167) + backward on leaf copies of ``params``;
     returns (logits, loss, grads)."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    logits = vit_forward(leaf, x, cfg)
+    logits = vit_forward(leaf, x, cfg, drops=drops)
     if y_b is None:
         loss = ls_ce_loss(logits, y, cfg.num_classes, smoothing)
     else:

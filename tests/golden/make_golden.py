@@ -99,5 +99,38 @@ def main():
               f"({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def dropout_block():
+    """One reference TransformerEncoder in TRAINING mode with dropout 0.2 (layers.py:35, 38, 102): the masks torch drew at the three
+    nn.Dropout sites (captured by forward hooks), the output, and every gradient for a fixed cotangent."""
+    _, ref_layers, _ = import_reference()
+    torch.set_num_threads(1)
+    p_drop, F_, M, head, B, T = 0.2, 128, 256, 4, 2, 17
+    torch.manual_seed(5)
+    blk = ref_layers.TransformerEncoder(F_, M, head=head, dropout=p_drop)
+    sd = blk.state_dict()
+    hash_init_(sd, seed=3)
+    blk.train()
+    x = torch.randn(B, T, F_, requires_grad=True)
+    w = torch.randn(B, T, F_)
+    masks = {}
+    sites = {blk.attention.dropout: 0, blk.mlp[2]: 1, blk.mlp[5]: 2}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, s=s: masks.__setitem__(s, ((out != 0) | (inp[0] == 0)).clone()))
+             for m, s in sites.items()]
+    y = blk(x)
+    for h in hooks:
+        h.remove()
+    (y * w).sum().backward()
+    out = dict(p=p_drop, features=F_, mlp_hidden=M, head=head, state_dict={k: v.detach().clone() for k, v in blk.state_dict().items()},
+               x=x.detach().clone(), w=w, masks=masks, y=y.detach().clone(), dx=x.grad.clone(),
+               grads={k: v.grad.detach().clone() for k, v in blk.named_parameters()}, torch_version=torch.__version__)
+    path = os.path.join(HERE, "dropout_block.pt")
+    torch.save(out, path)
+    print(f"dropout_block: keep rates {[round(m.float().mean().item(), 3) for m in masks.values()]} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dropout":  # only the newer fixture; the others stay byte-identical
+        dropout_block()
+    else:
+        main()
+        dropout_block()

@@ -387,3 +387,48 @@ def test_gpu_augment_class_statistics(ops):
         assert torch.all(((ch - hi[c]).abs() < 1e-5) | ((ch - lo[c]).abs() < 1e-5))
     frac = ((out[:, 0] - hi[0]).abs() < 1e-5).float().mean().item()
     assert 0.85 < frac < 0.93   # E[(32 - |d|) / 32]^2 with d uniform in [-4, 4]: 0.879
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dropout_is_the_documented_philox_stream(ops, dtype):
+    """vitb_dropout: the keep mask equals the numpy restatement of Philox4x32-10 bit for bit; kept values are scaled by
+    1/(1-p) (nn.Dropout, layers.py:35, 38, 102); residual add, in-place use, device-side step, backward = same call."""
+    import oracle
+    n, p, seed, site, step = 8 * 4099, 0.3, 0x1234567890ABCDEF, 2, 77
+    x = rnd((n,), dtype, 1); x[x == 0] = 1.0
+    res = rnd((n,), dtype, 2)
+    keep = torch.from_numpy(oracle.dropout_keep_mask(n, p, seed, site, step))
+    out = torch.empty(n, dtype=dtype, device="cuda")
+    ops.dropout(cu(x), None, out, p, seed, site, step)
+    assert torch.equal((out != 0).cpu(), keep)
+    ref = x.float() * keep / (1 - p)
+    assert rel(out, ref) < (1e-6 if dtype == torch.float32 else 4e-3)
+    step_dev = torch.tensor([step], dtype=torch.int32, device="cuda")
+    y = cu(x).clone()
+    ops.dropout(y, cu(res), y, p, seed, site, 0, step_dev)  # in place, residual, step read on the device
+    assert rel(y, ref + res.float()) < (1e-6 if dtype == torch.float32 else 4e-3)
+    for other in [dict(site=1), dict(step=78), dict(seed=seed + 1)]:
+        kw = dict(seed=seed, site=site, step=step); kw.update(other)
+        o2 = torch.empty_like(out)
+        ops.dropout(cu(x), None, o2, p, kw["seed"], kw["site"], kw["step"])
+        assert torch.equal((o2 != 0).cpu(), torch.from_numpy(oracle.dropout_keep_mask(n, p, kw["seed"], kw["site"], kw["step"])))
+        assert not torch.equal(o2 != 0, out != 0)
+    ops.dropout(cu(x), None, out, 0.0, seed, site, step)
+    assert torch.equal(out.cpu(), x)
+    with pytest.raises(Exception):
+        ops.dropout(cu(x), None, out, 1.0, seed, site, step)
+    with pytest.raises(Exception):
+        ops.dropout(cu(x)[:12], None, out[:12], p, seed, site, step)
+
+
+def test_dropout_keep_rate_at_training_size(ops):
+    """Activation-sized tensor (66 560 x 384 bf16): keep rate within 5 sigma of 1 - round(p * 65536) / 65536, mean preserved."""
+    n, p = 66560 * 384, 0.1
+    x = torch.ones(n, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty_like(x)
+    ops.dropout(x, None, out, p, 42, 0, 1)
+    kept = (out != 0).float().mean().item()
+    q = 1.0 - round(p * 65536) / 65536
+    assert abs(kept - q) < 5 * math.sqrt(q * (1 - q) / n)
+    assert abs(out.float().mean().item() - q / (1 - p)) < 1e-2

@@ -353,3 +353,72 @@ def test_engine_two_target_batches_match_oracle(vb, use_graph):
             assert e < 1e-4, (step, k, e)
     with pytest.raises(ValueError):
         vb.TrainEngine(build(vb, cfg, "fp32"), 8, use_graph=False).step(x.cuda(), y.cuda(), yb.cuda(), 0.5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_encoder_block_training_dropout_vs_oracle(vb, golden_dir, precision):
+    """TransformerEncoder(dropout=0.2).train(): the block's three nn.Dropout sites (layers.py:35, 38, 102).  The kernels draw their
+    masks from (seed, site, step); the oracle replays exactly those masks (oracle.philox_drop) on the reference fixture's weights."""
+    g = torch.load(os.path.join(golden_dir, "dropout_block.pt"), weights_only=False)
+    vb.set_precision(precision)
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    enc = vb.TransformerEncoder(g["features"], g["mlp_hidden"], head=g["head"], dropout=g["p"])
+    enc.load_state_dict(g["state_dict"])
+    enc = enc.cuda().train()
+    outs = []
+    for step in (1, 2):
+        xg = g["x"].cuda().requires_grad_(True)
+        enc.zero_grad()
+        y = enc(xg)
+        (y * g["w"].cuda()).sum().backward()
+        leaf = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+        xr = g["x"].clone().requires_grad_(True)
+        yr = oracle.encoder_forward(leaf, "", xr, g["head"], True, drop=oracle.philox_drop(g["p"], enc._drop_seed, step))
+        (yr * g["w"]).sum().backward()
+        assert rel(y, yr.detach()) < tol, step
+        assert rel(xg.grad, xr.grad) < tol, step
+        gs = grad_scale_of({k: v.grad for k, v in leaf.items()})
+        for k, prm in enc.named_parameters():
+            assert (rel(prm.grad, leaf[k].grad) if "Wk.bias" not in k else grad_err(prm.grad, leaf[k].grad, gs)) < tol, (step, k)
+        outs.append(y.detach())
+    assert rel(outs[0], outs[1]) > 0.05  # a fresh mask on every training call
+    enc.eval()  # eval: identity, as nn.Dropout
+    with torch.no_grad():
+        ye = enc(g["x"].cuda())
+    assert rel(ye, oracle.encoder_forward(g["state_dict"], "", g["x"], g["head"], True)) < tol
+    att = vb.MultiHeadSelfAttention(g["features"], head=g["head"], dropout=0.5).cuda().train()
+    pa = {k: v.detach().cpu().clone() for k, v in att.state_dict().items()}
+    ya = att(g["x"].cuda())
+    assert rel(ya, oracle.mhsa_forward(pa, "", g["x"], g["head"], drop=oracle.philox_drop(0.5, att._drop_seed, 1))) < tol
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_with_dropout_matches_oracle(vb, use_graph):
+    """TrainEngine on a ViT built with dropout=0.1: three Adam steps (eager, and warm-up + capture + replay: the step index
+    reaches the mask generator through device memory) against the oracle replaying the same mask streams."""
+    cfg, _ = CASES["tiny65"]
+    vb.set_precision("fp32")
+    p_drop, B = 0.1, 8
+    m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, dropout=p_drop, num_layers=cfg.num_layers, hidden=cfg.hidden,
+               mlp_hidden=cfg.mlp_hidden, head=cfg.head)
+    m.load_state_dict(oracle.init_params(cfg, seed=0))
+    m = m.cuda().train()
+    eng = vb.TrainEngine(m, B, smoothing=0.1, use_graph=use_graph, **ADAM)
+    seeds = [blk._drop_seed for blk in m.enc]
+    assert all(s is not None for s in seeds) and len(set(seeds)) == len(seeds)
+    params = oracle.init_params(cfg, 0)
+    mo = {k: torch.zeros_like(v) for k, v in params.items()}
+    vo = {k: torch.zeros_like(v) for k, v in params.items()}
+    for t in range(1, 5):
+        x, y = oracle.hash_inputs(cfg, B, seed=20 + t)
+        loss = eng.step(x.cuda(), y.cuda()).item()
+        drops = [oracle.philox_drop(p_drop, s, t) for s in seeds]
+        _, loss_ref, grads_ref = oracle.train_step(params, x, y, cfg, 0.1, drops=drops)
+        assert abs(loss - loss_ref.item()) < 1e-4 * abs(loss_ref.item()), (t, loss, loss_ref.item())
+        gs = grad_scale_of(grads_ref)
+        for k, gr in eng.grads().items():
+            e = rel(gr, grads_ref[k]) if "Wk.bias" not in k else grad_err(gr, grads_ref[k], gs)
+            assert e < 1e-4, (t, k, e)
+        oracle.adam_step(params, grads_ref, mo, vo, t, ADAM["lr"], ADAM["betas"], ADAM["eps"], ADAM["weight_decay"])
+    _, loss_nodrop, _ = oracle.train_step(params, x, y, cfg, 0.1)
+    assert abs(loss_nodrop.item() - loss_ref.item()) > 1e-3  # the masks matter at this size

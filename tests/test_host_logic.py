@@ -99,11 +99,25 @@ def test_dims_validation_messages():
         Dims(B=2, T=197, H=384, heads=12, M=384).check()  # 14x14+1 tokens do not fit the short-sequence kernel
 
 
-def test_dropout_training_is_loud():
+def test_dropout_stream_state_of_the_modules():
+    """nn.Dropout(p) bookkeeping on the host: no mask stream in eval or at p = 0, a lazily drawn seed (torch.manual_seed makes it
+    repeatable and it does not perturb the constructor's RNG stream), one step per training call, p validated like nn.Dropout."""
     import vit_cifar_b200 as vb
-    m = vb.ViT(3, 10, img_size=32, patch=4, dropout=0.1, num_layers=1, hidden=128, mlp_hidden=128, head=4)
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 32, 32))
+    torch.manual_seed(3)
+    a = vb.TransformerEncoder(128, 128, head=4, dropout=0.25)
+    torch.manual_seed(3)
+    b = vb.TransformerEncoder(128, 128, head=4, dropout=0.0)
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    assert a._drop_seed is None and a._next_drop(0.25, training=False) is None and b._next_drop(0.0, training=True) is None
+    torch.manual_seed(9)
+    d1, d2 = a._next_drop(0.25, True), a._next_drop(0.25, True)
+    assert (d1.p, d1.step, d2.step) == (0.25, 1, 2) and d1.seed == d2.seed == a._drop_seed
+    c = vb.TransformerEncoder(128, 128, head=4, dropout=0.25)
+    torch.manual_seed(9)
+    assert c._next_drop(0.25, True).seed == d1.seed
+    with pytest.raises(ValueError):
+        a._next_drop(1.0, True)
+    assert isinstance(a.mlp[2], torch.nn.Dropout) and a.mlp[2].p == 0.25 and a.attention.dropout.p == 0.25  # reference structure
 
 
 def _dp_worker(rank, world, port, outdir):

@@ -168,3 +168,75 @@ def test_augment_oracle_equals_torchvision_semantics_for_given_draws():
             assert abs(out[b, c, y, x].item() - (v - mean[c]) / std[c]) < 1e-6
     ident = oracle.augment_crop_flip_normalize(img, torch.full((5,), 4), torch.full((5,), 4), torch.zeros(5), (0, 0, 0), (1, 1, 1), 4)
     torch.testing.assert_close(ident, img.permute(0, 3, 1, 2).float() / 255.0)
+
+
+def test_philox_restatement_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors): the generator behind libvitb200's dropout masks."""
+    import numpy as np
+    kat = [((0, 0, 0, 0), (0, 0), "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kat:
+        r = oracle.philox4x32_10(np.array([ctr], dtype=np.uint32), key)
+        assert " ".join("%08x" % v for v in r[0]) == want
+    keep = oracle.dropout_keep_mask(1 << 18, 0.25, seed=0x1234567890ABCDEF, site=2, step=5)
+    assert abs(keep.mean() - 0.75) < 4 * math.sqrt(0.25 * 0.75 / (1 << 18))
+    assert not (keep == oracle.dropout_keep_mask(1 << 18, 0.25, seed=0x1234567890ABCDEF, site=1, step=5)).all()
+    assert oracle.dropout_threshold(0.0) == 0 and oracle.dropout_keep_mask(64, 0.0, 1, 0, 0).all()
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("use_mlp", [True, False])
+def test_oracle_dropout_sites_match_live_reference(use_mlp):
+    """The three nn.Dropout sites of the reference block (layers.py:35, 38, 102) in training mode: replay the masks torch drew
+    (captured by forward hooks) through the oracle's `drop` hook and compare output and every gradient."""
+    import torch.nn as nn
+    _, ref_layers, _ = import_reference()
+    p_drop = 0.3
+    torch.manual_seed(11)
+    blk = ref_layers.TransformerEncoder(64, 96, head=4, dropout=p_drop, use_mlp=use_mlp)
+    blk.train()
+    x = torch.randn(3, 17, 64, requires_grad=True)
+    masks = {}
+    sites = {blk.attention.dropout: 0}
+    if use_mlp:
+        sites[blk.mlp[2]] = 1
+        sites[blk.mlp[5]] = 2
+    hooks = [m.register_forward_hook(lambda mod, inp, out, s=s: masks.__setitem__(s, (out != 0) | (inp[0] == 0))) for m, s in sites.items()]
+    y_ref = blk(x)
+    for h in hooks:
+        h.remove()
+    assert all(isinstance(m, nn.Dropout) for m in sites) and len(masks) == len(sites)
+    w = torch.randn_like(y_ref)
+    (y_ref * w).sum().backward()
+
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xo = x.detach().clone().requires_grad_(True)
+    y = oracle.encoder_forward(params, "", xo, 4, use_mlp, drop=lambda site, t: t * masks[site].to(t.dtype) / (1.0 - p_drop))
+    torch.testing.assert_close(y, y_ref.detach(), rtol=1e-5, atol=1e-6)
+    (y * w).sum().backward()
+    torch.testing.assert_close(xo.grad, x.grad, rtol=1e-4, atol=1e-6)
+    for k, v in blk.named_parameters():
+        if params[k].grad is None:
+            assert v.grad is None
+            continue
+        torch.testing.assert_close(params[k].grad, v.grad, rtol=1e-4, atol=1e-6)
+    # eval mode: identity (the oracle's drop=None path)
+    blk.eval()
+    torch.testing.assert_close(oracle.encoder_forward({k: v.detach() for k, v in params.items()}, "", x.detach(), 4, use_mlp), blk(x).detach(),
+                               rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_dropout_block_matches_reference_golden(golden_dir):
+    """Committed fixture of the reference block in training mode with dropout 0.2 (tests/golden/make_golden.py dropout_block):
+    replaying the stored masks through the oracle reproduces the reference's output and gradients."""
+    g = _load(golden_dir, "dropout_block")
+    torch.set_num_threads(1)
+    params = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    y = oracle.encoder_forward(params, "", x, g["head"], True, drop=lambda site, t: t * g["masks"][site].to(t.dtype) / (1.0 - g["p"]))
+    torch.testing.assert_close(y, g["y"], rtol=1e-5, atol=1e-6)
+    (y * g["w"]).sum().backward()
+    torch.testing.assert_close(x.grad, g["dx"], rtol=1e-4, atol=1e-6)
+    for k, v in g["grads"].items():
+        torch.testing.assert_close(params[k].grad, v, rtol=1e-4, atol=1e-6)

@@ -108,7 +108,7 @@ __device__ __forceinline__ float4 cvt4(const Raw4<bf16>& r) {
 }
 
 template <typename T, int VEC, bool HAS_RES, bool COLSUM>
-__global__ void __launch_bounds__(kLnBwdWarps * 32)
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must be one wave: keep <= 128 registers
     ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t xs,
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
@@ -480,6 +480,55 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// dropout (nn.Dropout at layers.py:35, 38, 102): out = x * keep / (1 - p) (+ residual)
+//
+// The keep mask is never stored: it is a pure function of (seed, site, step, element index) — Philox4x32-10 with key = seed
+// and counter = (group lo, group hi, site, step), one call per group of eight consecutive elements, sixteen bits per element
+// (element j of the group uses bits 16 (j & 1) .. of word j >> 1; kept iff that value >= round(p * 65536)).  Backward calls
+// the same function on the gradient with the same (seed, site, step) and regenerates the mask.  `step` comes from device
+// memory when step_dev != NULL, so a captured CUDA graph draws a fresh mask on every replay.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    dropout_kernel(const T* x, const T* residual, T* out, int64_t groups,  // no __restrict__: in-place (out == x) is allowed
+                   uint32_t thr, float scale,
+                   uint2 key, uint32_t site, uint32_t step, const uint32_t* __restrict__ step_dev) {
+  pdl_trigger();
+  pdl_wait();
+  if (step_dev != nullptr) step = *step_dev;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)((uint64_t)g >> 32), site, step), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const int64_t e = g * 8;
+    float4 v[2] = {ld4(x + e), ld4(x + e + 4)};
+    float f[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t u = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+      f[j] = u >= thr ? f[j] * scale : 0.f;
+    }
+    if (residual != nullptr) {
+      const float4 a = ld4(residual + e), b = ld4(residual + e + 4);
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    st4(out + e, make_float4(f[0], f[1], f[2], f[3]));
+    st4(out + e + 4, make_float4(f[4], f[5], f[6], f[7]));
+  }
+}
+
 }  // namespace vitb
 
 using namespace vitb;
@@ -600,6 +649,31 @@ int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, c
   if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
   VITB_LAUNCH((augment_kernel), blocks, 256, 0, (cudaStream_t)stream, img_u8, dx, dy, flip, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out,
               B, S, pad);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+uint32_t vitb_dropout_threshold(float p) {
+  const double t = (double)p * 65536.0 + 0.5;
+  return t <= 0.0 ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
+}
+
+int vitb_dropout(const void* x, const void* residual, void* out, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step,
+                 const uint32_t* step_dev, int dt, void* stream) {
+  VITB_REQUIRE(x && out && n > 0, "dropout: null pointer / empty");
+  VITB_REQUIRE(n % 8 == 0, "dropout: the element count (%lld) must be a multiple of 8", (long long)n);
+  VITB_REQUIRE(p >= 0.f && p < 1.f, "dropout: p = %f outside [0, 1)", (double)p);
+  const int64_t groups = n / 8;
+  const int blocks = (int)(ceil_div64(groups, 256) < 16 * (int64_t)kNumSMs ? ceil_div64(groups, 256) : 16 * (int64_t)kNumSMs);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const float scale = 1.0f / (1.0f - p);
+  const uint32_t thr = vitb_dropout_threshold(p);
+  if (dt == VITB_BF16)
+    VITB_LAUNCH((dropout_kernel<bf16>), blocks, 256, 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)residual, (bf16*)out, groups, thr, scale, key, site,
+                step, step_dev);
+  else
+    VITB_LAUNCH((dropout_kernel<float>), blocks, 256, 0, (cudaStream_t)stream, (const float*)x, (const float*)residual, (float*)out, groups, thr, scale, key,
+                site, step, step_dev);
   VITB_LAUNCH_OK();
   return 0;
 }

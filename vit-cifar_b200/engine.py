@@ -48,8 +48,8 @@ class TrainEngine:
         mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "single")
         self._dp_mode = mode
         self.overlap_comm = (mode == "overlap") and self.world > 1
-        if model.p_drop > 0.0:
-            raise NotImplementedError("dropout > 0 is not implemented in the fused training step (reference default 0.0)")
+        if not 0.0 <= model.p_drop < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), got {model.p_drop}")
 
         st = model._ensure_packed()
         self.store = st
@@ -106,6 +106,17 @@ class TrainEngine:
         self.dlogits = torch.zeros((self.B, model.num_classes), dtype=torch.float32, device=self.dev)
         self.logits: Optional[torch.Tensor] = None
         self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=self.dev)
+        # nn.Dropout(p) of the blocks (layers.py:35, 38, 102): each block owns a mask stream (seed), the step index is word 10 of
+        # the per-step block (as an integer), so that graph replays draw fresh masks
+        self.drops = None
+        if model.p_drop > 0.0:
+            from .layers import _new_drop_seed
+            step_dev = self.hyper_dev.view(torch.int32)[10:11]
+            self.drops = []
+            for blk in model.enc:
+                if blk._drop_seed is None:
+                    blk._drop_seed = _new_drop_seed()
+                self.drops.append(Fn.Drop(p=float(model.p_drop), seed=blk._drop_seed, step_dev=step_dev))
         # ring of pinned slots: the async H2D of step k must not see the host writing step k+1's values
         self.hyper_host = torch.zeros((1024, 16), dtype=torch.float32).pin_memory()
         self.step_count = 0
@@ -148,7 +159,7 @@ class TrainEngine:
         x, words = Fn.stem_fwd(self.img, emb_w, emb_w_c, emb_b, cls, pos, m.patch, self.act, self._alloc("stem"))
         saved = []
         for i in range(m.num_layers):
-            x, sv = Fn.encoder_fwd(x, self.lc[i], self.lp[i], dm, self._alloc(f"l{i}"))
+            x, sv = Fn.encoder_fwd(x, self.lc[i], self.lp[i], dm, self._alloc(f"l{i}"), drop=self.drops[i] if self.drops else None)
             saved.append(sv)
         ln_w, ln_b, fc_w_c, fc_b = self.head_p
         self.logits, hsaved = Fn.head_fwd(x, ln_w, ln_b, fc_w_c, fc_b, B, T, H, Cn, m.is_cls_token, self._alloc("head"))
@@ -163,7 +174,8 @@ class TrainEngine:
         self._allreduce(self.buckets[-1])
         for i in reversed(range(m.num_layers)):
             # backward scratch is shared by all layers; the input-gradient buffer ping-pongs
-            dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i))
+            dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i),
+                                drop=self.drops[i] if self.drops else None)
             self._allreduce(self.buckets[1 + i])
         g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
         Fn.stem_bwd(self.img, words, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
@@ -233,6 +245,7 @@ class TrainEngine:
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
         slot[:9] = torch.tensor(h, dtype=torch.float32)
         slot[9] = self._lam
+        slot.view(torch.int32)[10] = self.step_count & 0x7FFFFFFF  # dropout mask step
         self.hyper_dev.copy_(slot, non_blocking=True)
         if not self.use_graph:
             n0 = ops.launch_count()

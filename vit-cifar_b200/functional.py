@@ -58,12 +58,26 @@ class Dims:
             raise ValueError(f"mlp_hidden={self.M} must be a multiple of 128")
 
 
+@dataclass
+class Drop:
+    """Training-mode nn.Dropout(p) of one encoder block (layers.py:35, 38, 102).  Its three sites (0: after out_project, 1: after the
+    first GELU, 2: after the second GELU) draw their keep masks from (seed, site, step); nothing is stored for the backward pass,
+    which regenerates them.  `step_dev` (1-element int32 device tensor) replaces `step` inside a captured CUDA graph."""
+    p: float
+    seed: int
+    step: int = 0
+    step_dev: Optional[torch.Tensor] = None
+
+    def __call__(self, x: torch.Tensor, residual: Optional[torch.Tensor], out: torch.Tensor, site: int) -> None:
+        ops.dropout(x, residual, out, self.p, self.seed, site, self.step, self.step_dev)
+
+
 # ---------------------------------------------------------------------------------------------
 # attention block: layers.py:90-103  (x -> out_project(attn(QKV(x))))
 # ---------------------------------------------------------------------------------------------
 def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: Alloc, residual: Optional[torch.Tensor],
-             attn_map: Optional[torch.Tensor] = None):
-    """x (rows,H) act -> y (rows,H) = out_project(attention(x)) (+ residual).  Returns (y, saved)."""
+             attn_map: Optional[torch.Tensor] = None, drop: Optional[Drop] = None):
+    """x (rows,H) act -> y (rows,H) = dropout(out_project(attention(x))) (+ residual).  Returns (y, saved)."""
     rows, H, act = dm.rows, dm.H, x.dtype
     qkv = alloc("qkv", (rows, 3 * H), act)
     ops.gemm_fwd(x, c.wqkv, p.bqkv, None, qkv, None, rows, 3 * H, H)
@@ -71,14 +85,23 @@ def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: All
     lse = alloc("lse", (dm.B, dm.heads, dm.T), torch.float32)
     ops.attn_fwd(qkv, o, lse, attn_map, dm.B, dm.T, dm.heads, dm.d, dm.scale)
     y = alloc("x1", (rows, H), act)
-    ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H)
+    if drop is None:
+        ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H)
+    else:
+        ops.gemm_fwd(o, c.wo, p.bo, None, y, None, rows, H, H)
+        drop(y, residual, y, 0)                                                    # layers.py:102, then "+ x" of layers.py:45
     return y, (x, qkv, o, lse)
 
 
-def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc, bo_done: bool = False):
-    """dy (rows,H) = grad of the out_project output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x."""
+def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc, bo_done: bool = False,
+             drop: Optional[Drop] = None):
+    """dy (rows,H) = grad of the block's attention branch output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x."""
     x, qkv, o, lse = saved
     rows, H, act = dm.rows, dm.H, dy.dtype
+    if drop is not None:  # gradient of the out_project output = dy through the same mask (dy itself is still needed by the caller)
+        dya = alloc("dao", (rows, H), act)
+        drop(dy, None, dya, 0)
+        dy = dya
     ops.gemm_wgrad(dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
     do = alloc("do", (rows, H), act)
     ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
@@ -93,13 +116,14 @@ def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, al
 # ---------------------------------------------------------------------------------------------
 # encoder block: layers.py:44-48
 # ---------------------------------------------------------------------------------------------
-def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: Alloc, attn_map: Optional[torch.Tensor] = None):
+def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: Alloc, attn_map: Optional[torch.Tensor] = None,
+                drop: Optional[Drop] = None):
     rows, H, M, act = dm.rows, dm.H, dm.M, x.dtype
     xn = alloc("xn", (rows, H), act)
     mean1 = alloc("mean1", (rows,), torch.float32)
     rstd1 = alloc("rstd1", (rows,), torch.float32)
     ops.layernorm_fwd(x, H, p.ln1_w, p.ln1_b, xn, mean1, rstd1, rows, H)
-    x1, att_saved = mhsa_fwd(xn, c, p, dm, alloc, residual=x, attn_map=attn_map)  # out = attention(la1(x)) + x
+    x1, att_saved = mhsa_fwd(xn, c, p, dm, alloc, residual=x, attn_map=attn_map, drop=drop)  # out = attention(la1(x)) + x
     if not dm.use_mlp:
         return x1, (x, mean1, rstd1, att_saved, None)
     x1n = alloc("x1n", (rows, H), act)
@@ -111,32 +135,46 @@ def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: 
     ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True)            # mlp[0], mlp[1]
     z2 = alloc("z2", (rows, H), act)
     x2 = alloc("x2", (rows, H), act)
-    ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True)                # mlp[3], mlp[4], + out
+    if drop is None:
+        ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True)            # mlp[3], mlp[4], + out
+    else:
+        drop(a1, None, a1, 1)                                                      # mlp[2]
+        ops.gemm_fwd(a1, c.w2, p.b2, None, x2, z2, rows, H, M, gelu=True)          # mlp[3], mlp[4]
+        drop(x2, x1, x2, 2)                                                        # mlp[5], + out
     return x2, (x, mean1, rstd1, att_saved, (x1, x1n, mean2, rstd2, z1, a1, z2))
 
 
-def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc):
-    """dout = grad of the block output; fills every field of g; returns grad of the block input."""
+def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc,
+                drop: Optional[Drop] = None):
+    """dout = grad of the block output; fills every field of g; returns grad of the block input.  `drop`: the same Drop the
+    forward ran with (masks are regenerated, not stored)."""
     x, mean1, rstd1, att_saved, mlp_saved = saved
     rows, H, M, act = dm.rows, dm.H, dm.M, dout.dtype
     if dm.use_mlp:
         x1, x1n, mean2, rstd2, z1, a1, z2 = mlp_saved
         dz2 = alloc("dz2", (rows, H), act)
-        ops.gelu_bwd_colsum(dout, z2, dz2, g.b2, rows, H)                # second GELU (layers.py:37) + db2
+        dg2 = dout
+        if drop is not None:
+            dg2 = alloc("dg2", (rows, H), act)
+            drop(dout, None, dg2, 2)                                     # mlp[5] backward
+        ops.gelu_bwd_colsum(dg2, z2, dz2, g.b2, rows, H)                 # second GELU (layers.py:37) + db2
         ops.gemm_wgrad(dz2, a1, g.w2, None, rows, H, M)
         dz1 = alloc("dz1", (rows, M), act)
         ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)                   # first GELU's backward fused in the epilogue
+        if drop is not None:
+            drop(dz1, None, dz1, 1)                                      # mlp[2] backward (mask and gelu' commute)
         ops.gemm_wgrad(dz1, x1n, g.w1, g.b1, rows, M, H)
         dx1n = alloc("dx1n", (rows, H), act)
         ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
         dx1 = alloc("dx1", (rows, H), act)
         # grad of x1 = residual branch (dout) + LN2 backward; its column sums are out_project's bias grad
-        ops.layernorm_bwd(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, g.bo, rows, H)
-        bo_done = True
+        # (with dropout the out_project output gradient is the MASKED dx1: its bias gradient then comes from the wgrad instead)
+        bo_done = drop is None
+        ops.layernorm_bwd(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, g.bo if bo_done else None, rows, H)
     else:
         dx1 = dout
         bo_done = False
-    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done)
+    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done, drop=drop)
     dx = alloc("dx", (rows, H), act)
     ops.layernorm_bwd(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, None, rows, H)
     return dx

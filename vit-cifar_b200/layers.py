@@ -36,11 +36,27 @@ def act_dtype() -> torch.dtype:
     return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
 
-def _check_dropout(p: float, training: bool) -> None:
-    if p > 0.0 and training:
-        raise NotImplementedError(
-            "dropout > 0 in training mode is not implemented in the fused B200 path yet "
-            "(the reference default is --dropout 0.0, main.py:87)")
+def _new_drop_seed() -> int:
+    """Seed of a module's dropout stream, drawn from torch's global CPU generator (so `torch.manual_seed` makes runs repeatable)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+class _DropState:
+    """Mixin for modules that own an nn.Dropout(p) stream: a seed and a count of training-mode forward calls (the `step` of
+    the counter-based mask generator, so every call draws fresh masks and backward can regenerate them)."""
+
+    _drop_seed: Optional[int]
+    _drop_calls: int
+
+    def _next_drop(self, p: float, training: bool) -> Optional[Fn.Drop]:
+        if not training or p <= 0.0:
+            return None
+        if not 0.0 < p < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), got {p}")
+        if self._drop_seed is None:
+            self._drop_seed = _new_drop_seed()
+        self._drop_calls += 1  # the first training call is step 1, like TrainEngine's step count
+        return Fn.Drop(p=float(p), seed=self._drop_seed, step=self._drop_calls)
 
 
 class _FlatRoot:
@@ -81,7 +97,7 @@ class _FlatRoot:
 # ---------------------------------------------------------------------------------------------
 class _MHSAFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, module, wq, wk, wv, bq, bk, bv, wo, bo):
+    def forward(ctx, x, module, drop, wq, wk, wv, bq, bk, bv, wo, bo):
         st = module._ensure_packed()
         dm = module._dims(x)
         cbuf = module._compute_buffer(st)
@@ -90,25 +106,25 @@ class _MHSAFn(torch.autograd.Function):
         alloc = Fn.default_alloc(x.device)
         xa = x.reshape(dm.rows, dm.H).to(act_dtype()).contiguous()
         am = torch.empty((dm.B, dm.heads, dm.T, dm.T), dtype=torch.float32, device=x.device) if module.save_attn_map else None
-        y, saved = Fn.mhsa_fwd(xa, c, p, dm, alloc, residual=None, attn_map=am)
+        y, saved = Fn.mhsa_fwd(xa, c, p, dm, alloc, residual=None, attn_map=am, drop=drop)
         if am is not None:
             module.attn_map = am
-        ctx.saved = (saved, c, dm, st, x.dtype, x.shape)
+        ctx.saved = (saved, c, dm, st, x.dtype, x.shape, drop)
         return y.view(dm.B, dm.T, dm.H).to(x.dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        saved, c, dm, st, xdt, xshape = ctx.saved
+        saved, c, dm, st, xdt, xshape, drop = ctx.saved
         gbuf = torch.zeros(st.layout.total, dtype=torch.float32, device=dy.device)
         g = LayerViews(st.layout, gbuf, "", dm.H, 0, False, with_ln=False, attn_prefix="")
         dya = dy.reshape(dm.rows, dm.H).to(act_dtype()).contiguous()
-        dx = Fn.mhsa_bwd(dya, saved, c, g, dm, Fn.default_alloc(dy.device))
+        dx = Fn.mhsa_bwd(dya, saved, c, g, dm, Fn.default_alloc(dy.device), drop=drop)
         H = dm.H
-        return (dx.view(xshape).to(xdt), None, g.wqkv[:H], g.wqkv[H:2 * H], g.wqkv[2 * H:], g.bqkv[:H], g.bqkv[H:2 * H], g.bqkv[2 * H:],
+        return (dx.view(xshape).to(xdt), None, None, g.wqkv[:H], g.wqkv[H:2 * H], g.wqkv[2 * H:], g.bqkv[:H], g.bqkv[H:2 * H], g.bqkv[2 * H:],
                 g.wo, g.bo)
 
 
-class MultiHeadSelfAttention(nn.Module, _FlatRoot):
+class MultiHeadSelfAttention(nn.Module, _FlatRoot, _DropState):
     """layers.py:68-103: three Linear(F,F) projections, softmax(QKᵀ/sqrt(F)), PV, out_project, dropout."""
 
     def __init__(self, features: int, head: int = 8, dropout: float = 0.0, save_attn_map: bool = False):
@@ -122,6 +138,7 @@ class MultiHeadSelfAttention(nn.Module, _FlatRoot):
         self.out_project = nn.Linear(features, features)
         self.dropout = nn.Dropout(dropout)
         self.save_attn_map = save_attn_map
+        self._drop_seed, self._drop_calls = None, 0
         object.__setattr__(self, "_store", None)
 
     def _layout(self) -> FlatLayout:
@@ -134,8 +151,8 @@ class MultiHeadSelfAttention(nn.Module, _FlatRoot):
         return dm
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        _check_dropout(self.dropout.p, self.training)
-        return _MHSAFn.apply(x, self, self.Wq.weight, self.Wk.weight, self.Wv.weight, self.Wq.bias, self.Wk.bias, self.Wv.bias,
+        drop = self._next_drop(self.dropout.p, self.training)  # layers.py:102
+        return _MHSAFn.apply(x, self, drop, self.Wq.weight, self.Wk.weight, self.Wv.weight, self.Wq.bias, self.Wk.bias, self.Wv.bias,
                              self.out_project.weight, self.out_project.bias)
 
 
@@ -146,7 +163,7 @@ class _EncoderFn(torch.autograd.Function):
     """One autograd node per encoder block: fused kernels inside, module interface outside."""
 
     @staticmethod
-    def forward(ctx, x, module, views, *params):
+    def forward(ctx, x, module, views, drop, *params):
         layout, pflat, cbuf, prefix = views
         dm = module._dims(x)
         p = LayerViews(layout, pflat, prefix, dm.H, dm.M, dm.use_mlp)
@@ -156,30 +173,30 @@ class _EncoderFn(torch.autograd.Function):
             xa = xa.to(act_dtype())
         xa = xa.contiguous()
         am = torch.empty((dm.B, dm.heads, dm.T, dm.T), dtype=torch.float32, device=x.device) if module._save_attn_map else None
-        y, saved = Fn.encoder_fwd(xa, c, p, dm, Fn.default_alloc(x.device), attn_map=am)
+        y, saved = Fn.encoder_fwd(xa, c, p, dm, Fn.default_alloc(x.device), attn_map=am, drop=drop)
         if am is not None:
             module.attention.attn_map = am
-        ctx.saved = (saved, c, p, dm, x.dtype, x.shape, module)
+        ctx.saved = (saved, c, p, dm, x.dtype, x.shape, module, drop)
         return y.view(dm.B, dm.T, dm.H).to(x.dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        saved, c, p, dm, xdt, xshape, module = ctx.saved
+        saved, c, p, dm, xdt, xshape, module, drop = ctx.saved
         lay = module._own_layout()
         gbuf = torch.zeros(lay.total, dtype=torch.float32, device=dy.device)
         g = LayerViews(lay, gbuf, "", dm.H, dm.M, dm.use_mlp)
         dya = dy.reshape(dm.rows, dm.H)
         if dya.dtype != act_dtype():
             dya = dya.to(act_dtype())
-        dx = Fn.encoder_bwd(dya.contiguous(), saved, c, p, g, dm, Fn.default_alloc(dy.device))
+        dx = Fn.encoder_bwd(dya.contiguous(), saved, c, p, g, dm, Fn.default_alloc(dy.device), drop=drop)
         H = dm.H
         grads = [g.ln1_w, g.ln1_b, g.wqkv[:H], g.wqkv[H:2 * H], g.wqkv[2 * H:], g.bqkv[:H], g.bqkv[H:2 * H], g.bqkv[2 * H:], g.wo, g.bo]
         if dm.use_mlp:
             grads += [g.ln2_w, g.ln2_b, g.w1, g.b1, g.w2, g.b2]
-        return (dx.view(xshape).to(xdt), None, None, *grads)
+        return (dx.view(xshape).to(xdt), None, None, None, *grads)
 
 
-class TransformerEncoder(nn.Module, _FlatRoot):
+class TransformerEncoder(nn.Module, _FlatRoot, _DropState):
     """layers.py:15-65: out = attention(la1(x)) + x ; out = mlp(la2(out)) + out  (Linear-GELU-Linear-GELU MLP)."""
 
     def __init__(self, features: int, mlp_hidden: int, head: int = 8, dropout: float = 0.0, use_mlp: bool = True,
@@ -196,6 +213,7 @@ class TransformerEncoder(nn.Module, _FlatRoot):
             self.mlp = None
         self._save_attn_map = save_attn_map
         self._features, self._mlp_hidden, self._head, self._p_drop = features, mlp_hidden, head, dropout
+        self._drop_seed, self._drop_calls = None, 0
         object.__setattr__(self, "_store", None)
         object.__setattr__(self, "_parent_views", None)  # set by a ViT that packed this block into its own buffer
 
@@ -223,14 +241,14 @@ class TransformerEncoder(nn.Module, _FlatRoot):
 
     # -- reference interface ------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        _check_dropout(self._p_drop, self.training)
+        drop = self._next_drop(self._p_drop, self.training)  # one stream for the block's three nn.Dropout sites
         pv = self._parent_views
         if pv is not None and pv[4]():  # packed inside a ViT whose storage is still current
             views = pv[:4]
         else:
             st = self._ensure_packed()
             views = (st.layout, st.flat, self._compute_buffer(st), "")
-        return _EncoderFn.apply(x, self, views, *self._param_list())
+        return _EncoderFn.apply(x, self, views, drop, *self._param_list())
 
     @property
     def save_attn_map(self):

@@ -191,6 +191,16 @@ def augment(img_u8, dx, dy, flip, mean, std, out, pad: int) -> None:
                                                        _ptr(out), B, S, int(pad), _stream()), "augment_crop_flip_normalize")
 
 
+def dropout(x, residual, out, p: float, seed: int, site: int, step: int = 0, step_dev=None) -> None:
+    """out = x * keep / (1 - p) (+ residual), nn.Dropout semantics (layers.py:35, 38, 102).  keep is a pure function of
+    (seed, site, step, element index): the backward pass is the same call on the gradient.  `step_dev`: 1-element int32 device
+    tensor that overrides `step` (graph replays)."""
+    assert x.dtype == out.dtype and x.numel() == out.numel() and (residual is None or residual.dtype == x.dtype)
+    _contig(x, out, residual)
+    check(_lib.load().vitb_dropout(_ptr(x), _ptr(residual), _ptr(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site),
+                                   int(step) & 0xFFFFFFFF, _ptr(step_dev), dt_of(x), _stream()), "dropout")
+
+
 def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None) -> None:
     """LS-CE forward + dlogits.  With `labels_b`: the two-target CutMix / MixUp loss lam*L(a) + (1-lam)*L(b) (network.py:149-167);
     `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step."""

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .layers import TransformerEncoder, _FlatRoot, _check_dropout, act_dtype
+from .layers import TransformerEncoder, _FlatRoot, act_dtype
 from .params import FlatLayout, FlatStore, layer_entries
 
 
@@ -129,7 +129,6 @@ class ViT(nn.Module, _FlatRoot):
 
     # -- reference interface ------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        _check_dropout(self.p_drop, self.training)
         st = self._ensure_packed()
         Fn.Dims(B=x.shape[0], T=self.num_tokens, H=self.hidden, heads=self.head, M=self.mlp_hidden, use_mlp=self.encoder_mlp).check()
         cbuf = self._compute_buffer(st)  # bf16 shadow refreshed from the fp32 master (one cast kernel)
