@@ -118,7 +118,8 @@ def test_fp32_engine_matches_golden_after_3_adam_steps(vb, golden_dir, name):
     for k, ref in g["params3"].items():
         # Wk.bias: its gradient is pure rounding noise (analytically 0), and Adam turns noise of any size into
         # updates of ~lr * g/(|g| + eps), so the reference's own 3-step value is only reproducible to ~1e-6 absolute
-        assert rel(sd[k], ref) < (1e-5 if "Wk.bias" not in k else 1e-4), k
+        # (seen: 8e-7 on elements of size 3e-3, i.e. 1.2e-4 relative over the tensor)
+        assert rel(sd[k], ref) < (1e-5 if "Wk.bias" not in k else 1e-3), k
 
 
 @pytest.mark.parametrize("name", ["full65", "full17c100"])

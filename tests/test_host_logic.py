@@ -269,3 +269,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, timeout=600, env=env)
     assert r2.returncode == 0 and not [ln for ln in r2.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_fused_dp_slices_partition_the_flat_buffer():
+    """vitb_dp_reduce_adam's ownership rule (parallel.owned_slice mirrors the C side): float4-aligned, disjoint, covering, in rank order."""
+    from vit_cifar_b200.parallel import owned_slice
+    import vit_cifar_b200 as vb
+    n_model = vb.ViT(3, 10, img_size=32, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)._layout().active_end
+    for n in (n_model, 64, 4, 6_268_864):
+        assert n % 4 == 0
+        for world in (1, 2, 3, 4, 8):
+            edges = [owned_slice(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            assert all(lo % 4 == 0 and hi % 4 == 0 and lo <= hi for lo, hi in edges)
+            assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges[:-1] or edges) <= 4 * world or world == 1 or n < 64

@@ -1,16 +1,24 @@
 #!/bin/bash
-# Round-end evidence on one B200: tests, smoke, bench (+ per-kernel table), reference arm, ncu launch list, ncu full capture.
+# Round-end evidence on one B200.  One profiler per call:
+#   bash tools/gpu_final.sh          tests, smoke, bench (+ per-kernel table), reference arm, ncu launch list
+#   bash tools/gpu_final.sh full     ncu --set full capture of the hot kernels (backward window, then nothing else)
 mkdir -p gpurun_out
 T="timeout 900"
+CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
+if [ "$1" = "full" ]; then
+  $T $CMD > gpurun_out/plain2.log 2>&1 && \
+  $T ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|attn_fwd_bf16|attn_bwd_bf16|ln_bwd|gelu_bwd|ln_fwd|adam" -s ${2:-330} -c ${3:-40} -o gpurun_out/prof_r1 $CMD > gpurun_out/ncu_full.log 2>&1
+  tail -n 3 gpurun_out/ncu_full.log | cut -c1-300
+  ls -la gpurun_out/*.ncu-rep
+  exit 0
+fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 $T python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/t_gpu.log 2>&1
 $T python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 $T python bench.py --kernel-table gpurun_out/kernels_b1024.json > gpurun_out/bench.log 2>&1
 $T python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1
-CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
 $T $CMD > gpurun_out/plain.log 2>&1 && \
-$T ncu --metrics gpu__time_duration.sum --clock-control none -s 612 -c 210 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-$T $CMD > gpurun_out/plain2.log 2>&1 && \
-$T ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|attn_fwd_bf16|attn_bwd_bf16|ln_bwd|gelu_bwd|ln_fwd|adam" -s 368 -c 26 -o gpurun_out/prof_r1 $CMD > gpurun_out/ncu_full.log 2>&1
-for f in gpurun_out/t_gpu.log gpurun_out/smoke.log gpurun_out/bench.log gpurun_out/bench_ref.log gpurun_out/ncu_list.log gpurun_out/ncu_full.log; do echo "== $f"; tail -n 3 $f | cut -c1-700; done
-ls -la gpurun_out/*.ncu-rep
+$T ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+python tools/launch_summary.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1
+for f in gpurun_out/t_gpu.log gpurun_out/smoke.log gpurun_out/bench.log gpurun_out/bench_ref.log gpurun_out/ncu_list.log; do echo "== $f"; tail -n 3 $f | cut -c1-700; done
+head -n 12 gpurun_out/launch_summary.txt

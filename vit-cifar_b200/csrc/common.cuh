@@ -314,6 +314,29 @@ inline cudaError_t launch_finalize(const float* ws, int nparts, int64_t cols, fl
 inline dim3 finalize_block() { return dim3(32, 8); }
 
 // ---------------------------------------------------------------------------------------------
+// Adam (coupled L2), torch.optim.Adam single-tensor arithmetic: shared by the flat-buffer kernel (loss_adam.cu) and the
+// data-parallel reduce + Adam + broadcast kernel (dp.cu)
+// ---------------------------------------------------------------------------------------------
+struct AdamHyper {
+  float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale, one_minus_beta1, one_minus_beta2;
+};
+__host__ __device__ __forceinline__ AdamHyper adam_hyper_from(const float* h9) {
+  AdamHyper h;
+  h.step_size = h9[0]; h.bc2_sqrt = h9[1]; h.beta1 = h9[2]; h.beta2 = h9[3]; h.eps = h9[4]; h.wd = h9[5]; h.grad_scale = h9[6];
+  h.one_minus_beta1 = h9[7]; h.one_minus_beta2 = h9[8];
+  return h;
+}
+// Explicit rounding intrinsics: the compiler may not re-associate or contract differently in different kernels, so every kernel
+// that inlines this function produces the same bits for the same inputs.
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
+  g = __fmaf_rn(g, h.grad_scale, __fmul_rn(h.wd, p));
+  m = __fmaf_rn(__fsub_rn(g, m), h.one_minus_beta1, m);                             // exp_avg.lerp_(grad, 1 - beta1)
+  v = __fmaf_rn(__fmul_rn(h.one_minus_beta2, g), g, __fmul_rn(v, h.beta2));         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
+  p = __fmaf_rn(-h.step_size, __fdiv_rn(m, denom), p);
+}
+
+// ---------------------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT (fp32 check mode / small shapes) and tcgen05 paths
 // ---------------------------------------------------------------------------------------------
 enum EpiMode { EPI_FWD = 0, EPI_DGRAD = 1, EPI_RAW_F32 = 2 };

@@ -63,29 +63,13 @@ __global__ void __launch_bounds__(1024)
 // ---------------------------------------------------------------------------------------------
 // Adam (coupled L2), torch.optim.Adam single-tensor arithmetic, over one flat buffer
 // ---------------------------------------------------------------------------------------------
-struct AdamHyper {
-  float step_size, bc2_sqrt, beta1, beta2, eps, wd, grad_scale, one_minus_beta1, one_minus_beta2;
-};
-
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
-  g = g * h.grad_scale + h.wd * p;
-  m = m + (g - m) * h.one_minus_beta1;            // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * h.beta2 + h.one_minus_beta2 * g * g;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
-  p = p - h.step_size * (m / denom);
-}
-
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 bf16* __restrict__ shadow, int64_t n, AdamHyper hv, const float* __restrict__ hyper_dev) {
   pdl_trigger();
   pdl_wait();
   AdamHyper h = hv;
-  if (hyper_dev != nullptr) {
-    h.step_size = hyper_dev[0]; h.bc2_sqrt = hyper_dev[1]; h.beta1 = hyper_dev[2]; h.beta2 = hyper_dev[3];
-    h.eps = hyper_dev[4]; h.wd = hyper_dev[5]; h.grad_scale = hyper_dev[6];
-    h.one_minus_beta1 = hyper_dev[7]; h.one_minus_beta2 = hyper_dev[8];
-  }
+  if (hyper_dev != nullptr) h = adam_hyper_from(hyper_dev);
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -137,11 +121,7 @@ int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow
   VITB_REQUIRE(w_shadow == nullptr || (uintptr_t)w_shadow % 8 == 0, "adam: shadow must be 8-byte aligned");
   if (n == 0) return 0;
   AdamHyper h = {};
-  if (hyper_host) {
-    h.step_size = hyper_host[0]; h.bc2_sqrt = hyper_host[1]; h.beta1 = hyper_host[2]; h.beta2 = hyper_host[3];
-    h.eps = hyper_host[4]; h.wd = hyper_host[5]; h.grad_scale = hyper_host[6];
-    h.one_minus_beta1 = hyper_host[7]; h.one_minus_beta2 = hyper_host[8];
-  }
+  if (hyper_host) h = adam_hyper_from(hyper_host);
   int blocks = (int)ceil_div64(n / 4 + 1, 256);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   VITB_LAUNCH((adam_kernel), blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)w_shadow, n, h, hyper_dev);

@@ -44,8 +44,11 @@ class TrainEngine:
         self._lam = 1.0
         self._next_lam = 1.0
         # "overlap": per-layer buckets on a side stream while backward continues; "single": one all-reduce of the whole flat
-        # gradient buffer after backward (no SM contention between NCCL's CTAs and the persistent GEMM kernels)
+        # gradient buffer after backward (no SM contention between NCCL's CTAs and the persistent GEMM kernels); "fused": no NCCL
+        # in the step at all — one kernel does barrier + reduce-scatter over NVLink peer memory + Adam + all-gather (csrc/dp.cu)
         mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "single")
+        if mode not in ("single", "overlap", "fused", "none"):
+            raise ValueError(f"VITB_DP_MODE={mode!r}: expected single, overlap or fused")
         self._dp_mode = mode
         self.overlap_comm = (mode == "overlap") and self.world > 1
         if not 0.0 <= model.p_drop < 1.0:
@@ -71,6 +74,21 @@ class TrainEngine:
             dist.broadcast(self.P, src=0, group=self.pg)  # identical replicas
             if self.C is not self.P:
                 ops.cast_f32_to_bf16(self.P, self.C)
+
+        self._fused_dp = None
+        if self.world > 1 and mode == "fused":
+            import torch.distributed as dist
+            from .parallel import exchange_peer_pointers
+            if self.world > 8 or self.n % 4 != 0:
+                raise ValueError("fused data-parallel step: at most 8 ranks of one node and a flat buffer that is a multiple of 4 elements")
+            flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
+            sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
+            torch.cuda.synchronize(self.dev)
+            peers = dict(g=exchange_peer_pointers(self.G, self.pg), p=exchange_peer_pointers(self.P, self.pg),
+                         c=exchange_peer_pointers(self.C, self.pg) if self.C is not self.P else None,
+                         flags=exchange_peer_pointers(flags, self.pg))
+            dist.barrier(group=self.pg)  # every rank has mapped every peer before the first kernel touches them
+            self._fused_dp = dict(peers, flags_t=flags, sync=sync, rank=dist.get_rank(self.pg))
 
         H, M = model.hidden, model.mlp_hidden
         self.dm = Fn.Dims(B=self.B, T=model.num_tokens, H=H, heads=model.head, M=M, use_mlp=model.encoder_mlp)
@@ -144,7 +162,7 @@ class TrainEngine:
     def _allreduce(self, bucket: Tuple[int, int], last: bool = False) -> None:
         if self.world == 1:
             return
-        if self._dp_mode == "none":  # diagnostic only: replicas drift apart
+        if self._dp_mode in ("none", "fused"):  # none: diagnostic only (replicas drift apart); fused: the optimiser kernel does it
             return
         if self.overlap_comm:
             allreduce_bucket(self.G, bucket, self.pg, self._comm_stream)
@@ -183,7 +201,11 @@ class TrainEngine:
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         n = self.n
-        ops.adam(self.P[:n], self.G[:n], self.Mo[:n], self.V[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
+        if self._fused_dp is not None:
+            f = self._fused_dp
+            ops.dp_reduce_adam(f["g"], f["p"], f["c"], f["flags"], self.Mo, self.V, f["sync"], n, f["rank"], self.world, hyper_dev=self.hyper_dev)
+        else:
+            ops.adam(self.P[:n], self.G[:n], self.Mo[:n], self.V[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
 
     def _bwd_alloc(self, i: int):
         shared = self._alloc("bwd")

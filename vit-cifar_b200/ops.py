@@ -228,3 +228,42 @@ def adam(p, g, m, v, shadow, hyper_host=None, hyper_dev=None) -> None:
         hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (16 - len(hyper_host))))
     check(_lib.load().vitb_adam_multi(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), n,
                                       C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()), "adam_multi")
+
+
+# -- data parallel over NVLink peer memory ---------------------------------------------------------
+def ipc_export(t: torch.Tensor):
+    """(64-byte handle, byte offset) of a CUDA tensor's memory for another process on this node (vitb_ipc_open)."""
+    h = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    check(_lib.load().vitb_ipc_export(_ptr(t), C.cast(h, C.c_void_p), C.cast(C.pointer(off), C.c_void_p)), "ipc_export")
+    return bytes(h.raw), int(off.value)
+
+
+def ipc_open(handle: bytes, offset: int) -> int:
+    """Device address, valid in THIS process, of the memory another rank exported."""
+    out = C.c_void_p(0)
+    buf = C.create_string_buffer(handle, 64)
+    check(_lib.load().vitb_ipc_open(C.cast(buf, C.c_void_p), int(offset), C.cast(C.pointer(out), C.c_void_p)), "ipc_open")
+    return int(out.value)
+
+
+class PeerPointers:
+    """Host array of `world` device pointers (index = rank) in the form vitb_dp_reduce_adam takes."""
+
+    def __init__(self, ptrs):
+        self.ptrs = [int(p) for p in ptrs]
+        self.arr = (C.c_void_p * len(self.ptrs))(*self.ptrs)
+
+    def cptr(self):
+        return C.cast(self.arr, C.c_void_p)
+
+
+def dp_reduce_adam(g: PeerPointers, p: PeerPointers, shadow: Optional[PeerPointers], flags: PeerPointers, m, v, sync, n: int, rank: int, world: int,
+                   hyper_host=None, hyper_dev=None) -> None:
+    """Barrier, reduce-scatter of the peers' gradients, Adam on the owned slice, all-gather of the new parameters, barrier — one kernel."""
+    hh = None
+    if hyper_host is not None:
+        hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (16 - len(hyper_host))))
+    check(_lib.load().vitb_dp_reduce_adam(g.cptr(), p.cptr(), shadow.cptr() if shadow is not None else None, flags.cptr(), _ptr(m), _ptr(v), _ptr(sync),
+                                          int(n), int(rank), int(world), C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()),
+          "dp_reduce_adam")

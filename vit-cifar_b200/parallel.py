@@ -26,3 +26,25 @@ def allreduce_all(flat_grad: torch.Tensor, buckets: Sequence[Tuple[int, int]], g
     """Backward order: head bucket first, stem last (the order gradients become ready)."""
     for bk in reversed(list(buckets)):
         allreduce_bucket(flat_grad, bk, group, None)
+
+
+def owned_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Element range of the flat buffers whose reduction and Adam update rank `rank` performs in the fused data-parallel step
+    (vitb_dp_reduce_adam): ceil(n/4 / world) float4 groups per rank, in rank order."""
+    n4 = n // 4
+    per = (n4 + world - 1) // world
+    return min(per * rank, n4) * 4, min(per * (rank + 1), n4) * 4
+
+
+def exchange_peer_pointers(t: torch.Tensor, group=None):
+    """Map every rank's copy of `t` (same shape on all ranks of one node) into this process through CUDA IPC; returns the device
+    addresses in rank order (this rank's own address at [rank]).  torch.distributed only carries the 64-byte handles."""
+    from . import ops
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = ops.ipc_export(t)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    ptrs = []
+    for r, (handle, offset) in enumerate(everyone):
+        ptrs.append(t.data_ptr() if r == rank else ops.ipc_open(handle, offset))
+    return ops.PeerPointers(ptrs)
