@@ -358,7 +358,11 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
                        "l2": "working set per step (>4 GB of activations) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                             {"fused": "one peer-memory kernel: barrier + reduce-scatter (P2P loads) + Adam + all-gather (P2P stores)",
+                                              "single": "NCCL all-reduce of the flat gradient buffer, then the Adam kernel",
+                                              "overlap": "NCCL all-reduce per layer bucket on a side stream, then the Adam kernel"}.get(eng._dp_mode, eng._dp_mode))},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": B * (3 * 32 * 32 * 4 + 8) + 32, "d2h_bytes_per_step": 4},
             "gpu_launches": int(eng.launches_per_step * args.steps),

@@ -46,7 +46,7 @@ class TrainEngine:
         # "overlap": per-layer buckets on a side stream while backward continues; "single": one all-reduce of the whole flat
         # gradient buffer after backward (no SM contention between NCCL's CTAs and the persistent GEMM kernels); "fused": no NCCL
         # in the step at all — one kernel does barrier + reduce-scatter over NVLink peer memory + Adam + all-gather (csrc/dp.cu)
-        mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "single")
+        mode = os.environ.get("VITB_DP_MODE", "overlap" if overlap_comm else "fused")
         if mode not in ("single", "overlap", "fused", "none"):
             raise ValueError(f"VITB_DP_MODE={mode!r}: expected single, overlap or fused")
         self._dp_mode = mode
@@ -79,16 +79,26 @@ class TrainEngine:
         if self.world > 1 and mode == "fused":
             import torch.distributed as dist
             from .parallel import exchange_peer_pointers
-            if self.world > 8 or self.n % 4 != 0:
-                raise ValueError("fused data-parallel step: at most 8 ranks of one node and a flat buffer that is a multiple of 4 elements")
             flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
             sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
             torch.cuda.synchronize(self.dev)
-            peers = dict(g=exchange_peer_pointers(self.G, self.pg), p=exchange_peer_pointers(self.P, self.pg),
-                         c=exchange_peer_pointers(self.C, self.pg) if self.C is not self.P else None,
-                         flags=exchange_peer_pointers(flags, self.pg))
-            dist.barrier(group=self.pg)  # every rank has mapped every peer before the first kernel touches them
-            self._fused_dp = dict(peers, flags_t=flags, sync=sync, rank=dist.get_rank(self.pg))
+            peers, err = None, None
+            try:
+                if self.world > 8 or self.n % 4 != 0:
+                    raise ValueError("at most 8 ranks of one node and a flat buffer that is a multiple of 4 elements")
+                peers = dict(g=exchange_peer_pointers(self.G, self.pg), p=exchange_peer_pointers(self.P, self.pg),
+                             c=exchange_peer_pointers(self.C, self.pg) if self.C is not self.P else None,
+                             flags=exchange_peer_pointers(flags, self.pg))
+            except Exception as e:  # no peer access between these GPUs (or ranks on different nodes): all ranks use NCCL instead
+                err = e
+            ok = torch.tensor([0 if peers is None else 1], device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)  # also: every rank has mapped every peer before the first step
+            if int(ok.item()) == 1:
+                self._fused_dp = dict(peers, flags_t=flags, sync=sync, rank=dist.get_rank(self.pg))
+            else:
+                import warnings
+                warnings.warn(f"fused data-parallel step unavailable ({err}); using one NCCL all-reduce + the Adam kernel")
+                self._dp_mode = mode = "single"
 
         H, M = model.hidden, model.mlp_hidden
         self.dm = Fn.Dims(B=self.B, T=model.num_tokens, H=H, heads=model.head, M=M, use_mlp=model.encoder_mlp)
