@@ -7,9 +7,12 @@ T="timeout 900"
 CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
 if [ "$1" = "full" ]; then
   $T $CMD > gpurun_out/plain2.log 2>&1 && \
-  $T ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|attn_fwd_bf16|attn_bwd_bf16|ln_bwd|gelu_bwd|ln_fwd|adam" -s ${2:-330} -c ${3:-40} -o gpurun_out/prof_r1 $CMD > gpurun_out/ncu_full.log 2>&1
+  # the report goes to /tmp: gpurun only copies back 64 MiB, so export the per-kernel metrics as CSV and keep the report only if small
+  $T ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|attn_fwd_bf16|attn_bwd_bf16|ln_bwd|gelu_bwd|ln_fwd|adam" -s ${2:-330} -c ${3:-40} -o /tmp/prof_r1 $CMD > gpurun_out/ncu_full.log 2>&1
   tail -n 3 gpurun_out/ncu_full.log | cut -c1-300
-  ls -la gpurun_out/*.ncu-rep
+  ncu -i /tmp/prof_r1.ncu-rep --page raw --csv > gpurun_out/ncu_full_raw.csv 2> gpurun_out/ncu_export.log
+  ls -la /tmp/prof_r1.ncu-rep gpurun_out/ncu_full_raw.csv
+  [ $(stat -c %s /tmp/prof_r1.ncu-rep) -lt 40000000 ] && cp /tmp/prof_r1.ncu-rep gpurun_out/
   exit 0
 fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
