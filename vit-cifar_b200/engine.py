@@ -33,10 +33,10 @@ class TrainEngine:
         self.smoothing = float(smoothing)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
         self.pg = process_group
-        self.world = 1
+        self.world, self._rank = 1, 0
         if process_group is not None:
             import torch.distributed as dist
-            self.world = dist.get_world_size(process_group)
+            self.world, self._rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         self.use_graph = use_graph
         # two-target loss lam*L(out,y) + (1-lam)*L(out,y') for CutMix / MixUp batches (network.py:149-167); lam travels in the
         # per-step hyper-parameter block so the captured graph reads a fresh value every step
@@ -144,7 +144,9 @@ class TrainEngine:
             for blk in model.enc:
                 if blk._drop_seed is None:
                     blk._drop_seed = _new_drop_seed()
-                self.drops.append(Fn.Drop(p=float(model.p_drop), seed=blk._drop_seed, step_dev=step_dev))
+                # data parallel: every rank draws its own masks (per-rank offset of the stream seed)
+                seed = (blk._drop_seed + 0x9E3779B97F4A7C15 * self._rank) & 0xFFFFFFFFFFFFFFFF
+                self.drops.append(Fn.Drop(p=float(model.p_drop), seed=seed, step_dev=step_dev))
         # ring of pinned slots: the async H2D of step k must not see the host writing step k+1's values
         self.hyper_host = torch.zeros((1024, 16), dtype=torch.float32).pin_memory()
         self.step_count = 0
