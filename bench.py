@@ -31,6 +31,15 @@ sys.path.insert(0, ROOT)
 
 MODEL = dict(num_classes=10, img_size=32, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)
 PER_GPU_BATCH = 1024
+# --workload: the headline configuration (BASELINE.json configs[1], default — the only one the contract line is quoted on) and the
+# other shapes SURVEY.md §8(d) lists, for DESIGN.md's tables.  `patch` is the number of patches per side (vit.py:37).
+WORKLOADS = {
+    "headline": (MODEL, PER_GPU_BATCH),
+    "t17c100": (dict(MODEL, patch=4, num_classes=100), PER_GPU_BATCH),                                      # configs[3] as written (T = 17)
+    "t65c100": (dict(MODEL, patch=8, num_classes=100), PER_GPU_BATCH),                                      # configs[3] at 65 tokens
+    "scaled17": (dict(MODEL, patch=4, num_layers=12, hidden=768, mlp_hidden=3072, head=12), 512),           # configs[4] as written
+    "scaled65": (dict(MODEL, patch=8, num_layers=12, hidden=768, mlp_hidden=3072, head=12), 512),           # configs[4] at 65 tokens
+}
 ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
 SMOOTHING = 0.1
 METRIC = "train images/s (fwd+bwd+Adam)"
@@ -147,9 +156,12 @@ def run_reference(args):
     return 0
 
 
-def workload_name(n):
-    return (f"ViT-CIFAR 7L/384h/12heads/MLP384 patch=8 (T=65,K=48) C=10, per-GPU batch {PER_GPU_BATCH} "
-            f"(global {PER_GPU_BATCH * n}), LS 0.1, Adam, bf16")
+def workload_name(n, batch=None):
+    b = PER_GPU_BATCH if batch is None else batch
+    T = MODEL["patch"] ** 2 + 1
+    K = 3 * (MODEL["img_size"] // MODEL["patch"]) ** 2
+    return (f"ViT-CIFAR {MODEL['num_layers']}L/{MODEL['hidden']}h/{MODEL['head']}heads/MLP{MODEL['mlp_hidden']} patch={MODEL['patch']} "
+            f"(T={T},K={K}) C={MODEL['num_classes']}, per-GPU batch {b} (global {b * n}), LS 0.1, Adam, bf16")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -334,7 +346,8 @@ def run_ours(args):
     value = imgs / (ms_dev * 1e-3)
     e2e = imgs / (ms_e2e * 1e-3)
     pk = peaks()
-    fl = train_flops_per_image()
+    fl = train_flops_per_image(T=model.num_tokens, K=3 * (MODEL["img_size"] // MODEL["patch"]) ** 2, H=MODEL["hidden"], M=MODEL["mlp_hidden"],
+                               L=MODEL["num_layers"], C=MODEL["num_classes"])
 
     # ---- per-kernel probe + roofline of the dominant kernel (rank 0, after the timed regions) ----
     table = probe_kernels(eng, steps=3)
@@ -356,7 +369,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(world), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
+            "config": {"workload": workload_name(world, B), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
                        "l2": "working set per step (>4 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}",
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
@@ -399,11 +412,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default: the benchmark's 1024)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's, 1024 for the headline)")
+    ap.add_argument("--workload", default="headline", choices=list(WORKLOADS), help="model shape (default: BASELINE.json's headline configuration)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")
     args = ap.parse_args()
+    global MODEL, PER_GPU_BATCH
+    MODEL, PER_GPU_BATCH = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = PER_GPU_BATCH
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
