@@ -171,6 +171,12 @@ int vitb_ls_ce_mix_fwd_bwd(const float* logits, const int64_t* labels_a, const i
 int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow, int64_t n,
                     const float* hyper_host, const float* hyper_dev, void* stream);
 
+/* ---- SGD with momentum over a flat buffer: torch.optim.SGD as configured at network.py:78-84 (momentum = beta1, dampening 0, no
+ * Nesterov, coupled weight decay): g = g*grad_scale + wd*p; buf = momentum*buf + g; p -= lr*buf.  buf starts at zero.
+ * hyper: the same 16-float block as vitb_adam_multi, of which SGD reads [0] = lr, [2] = momentum, [5] = weight_decay,
+ * [6] = grad_scale (host, or device memory if hyper_dev != NULL).  w_shadow as in vitb_adam_multi. ---- */
+int vitb_sgd_multi(float* p, const float* g, float* buf, void* w_shadow, int64_t n, const float* hyper_host, const float* hyper_dev, void* stream);
+
 /* ---- Data-parallel step over NVLink peer memory: what Lightning's DDP all-reduce (main.py:220-231) followed by
  * torch.optim.Adam (network.py:71-77) does for the reference, as ONE kernel per rank and step:
  *   barrier (all ranks finished backward) -> rank r sums elements [r*ceil(n/4/W)*4, ...) of ALL ranks' gradient buffers in rank
@@ -178,10 +184,11 @@ int vitb_adam_multi(float* p, const float* g, float* m, float* v, void* w_shadow
  *   the owned slice) -> stores the new fp32 parameters and bf16 shadow into EVERY rank's buffers (P2P stores) -> barrier.
  * g_peers / p_peers / shadow_peers / flag_peers: HOST arrays of `world` device pointers (index = rank; the own buffers at [rank];
  * shadow_peers may be NULL).  flag buffers: >= world uint32 each, zeroed once; sync: 4 uint32 of this rank, zeroed once.
+ * optimizer: 0 = Adam; 1 = SGD with momentum as vitb_sgd_multi (m is the momentum buffer, v may be NULL).
  * Peer pointers come from vitb_ipc_open.  world <= 8, n % 4 == 0.  Every rank must issue the same sequence of calls; a rank that
  * waits longer than ~60 s for a peer traps.  Replicas end bit-identical. ---- */
 int vitb_dp_reduce_adam(const void* const* g_peers, void* const* p_peers, void* const* shadow_peers, void* const* flag_peers, float* m, float* v,
-                        uint32_t* sync, int64_t n, int rank, int world, const float* hyper_host, const float* hyper_dev, void* stream);
+                        uint32_t* sync, int64_t n, int rank, int world, int optimizer, const float* hyper_host, const float* hyper_dev, void* stream);
 /* CUDA IPC plumbing for the above (host functions; no kernels).  export: 64-byte handle of the allocation that contains dev_ptr and
  * dev_ptr's byte offset inside it (the caller ships both to the other ranks, e.g. with torch.distributed.all_gather_object).
  * open: maps a peer's allocation into this process (once per handle, cached) with peer access enabled; returns base + offset. */

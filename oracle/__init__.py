@@ -32,6 +32,7 @@ from .vit_oracle import (  # noqa: F401
     philox_drop,
     augment_crop_flip_normalize,
     adam_step,
+    sgd_step,
     train_step,
     OracleViT,
 )

@@ -319,6 +319,24 @@ def adam_step(params: Params, grads: Params, exp_avg: Params, exp_avg_sq: Params
             p.addcdiv_(exp_avg[k], denom, value=-step_size)
 
 
+def sgd_step(params: Params, grads: Params, bufs: Params, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 5e-5) -> None:
+    """In-place torch.optim.SGD step as network.py:78-84 configures it (momentum = beta1, dampening 0, no Nesterov, coupled weight
+    decay); torch's single-tensor arithmetic: g += wd*p; buf = g on the first step (bufs[k] is None), else buf = momentum*buf + g;
+    p -= lr*buf."""
+    with torch.no_grad():
+        for k, p in params.items():
+            g = grads.get(k)
+            if g is None:
+                continue
+            if weight_decay != 0.0:
+                g = g.add(p, alpha=weight_decay)
+            if bufs.get(k) is None:
+                bufs[k] = g.clone()
+            else:
+                bufs[k].mul_(momentum).add_(g)
+            p.add_(bufs[k], alpha=-lr)
+
+
 def train_step(params: Params, x: torch.Tensor, y: torch.Tensor, cfg: ViTConfig, smoothing: float = 0.1,
                y_b: Optional[torch.Tensor] = None, lam: float = 1.0, drops=None):
     """forward + LS-CE (two-target form when y_b is given, network.py:149-167) + backward on leaf copies of ``params``;

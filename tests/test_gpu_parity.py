@@ -423,3 +423,26 @@ def test_engine_with_dropout_matches_oracle(vb, use_graph):
         oracle.adam_step(params, grads_ref, mo, vo, t, ADAM["lr"], ADAM["betas"], ADAM["eps"], ADAM["weight_decay"])
     _, loss_nodrop, _ = oracle.train_step(params, x, y, cfg, 0.1)
     assert abs(loss_nodrop.item() - loss_ref.item()) > 1e-3  # the masks matter at this size
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_sgd_matches_oracle(vb, use_graph):
+    """TrainEngine(optimizer="sgd"): the reference's `--optimizer sgd` (network.py:78-84, momentum = beta1) against the oracle's
+    restatement of torch.optim.SGD, four steps on changing batches, fp32 check mode."""
+    cfg, _ = CASES["tiny65"]
+    vb.set_precision("fp32")
+    model = build(vb, cfg, "fp32")
+    eng = vb.TrainEngine(model, 8, smoothing=0.1, use_graph=use_graph, optimizer="sgd", lr=1e-2, betas=(0.9, 0.999), weight_decay=5e-5)
+    params = oracle.init_params(cfg, 0)
+    bufs = {}
+    for t in range(4):
+        x, y = oracle.hash_inputs(cfg, 8, seed=30 + t)
+        loss = eng.step(x.cuda(), y.cuda()).item()
+        _, loss_ref, grads_ref = oracle.train_step(params, x, y, cfg, 0.1)
+        assert abs(loss - loss_ref.item()) < 1e-4 * abs(loss_ref.item()), (t, loss, loss_ref.item())
+        oracle.sgd_step(params, grads_ref, bufs, 1e-2, 0.9, 5e-5)
+    sd = model.state_dict()
+    for k, ref in params.items():
+        assert rel(sd[k], ref) < 1e-5, k
+    with pytest.raises(NotImplementedError):
+        vb.TrainEngine(build(vb, cfg, "fp32"), 8, optimizer="madam")

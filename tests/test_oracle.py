@@ -240,3 +240,21 @@ def test_oracle_dropout_block_matches_reference_golden(golden_dir):
     torch.testing.assert_close(x.grad, g["dx"], rtol=1e-4, atol=1e-6)
     for k, v in g["grads"].items():
         torch.testing.assert_close(params[k].grad, v, rtol=1e-4, atol=1e-6)
+
+
+def test_sgd_restatement_matches_torch_sgd():
+    """network.py:78-84: torch.optim.SGD(lr, momentum=beta1, weight_decay)."""
+    torch.manual_seed(0)
+    p0 = {"a": torch.randn(7, 5), "b": torch.randn(11)}
+    ours = {k: v.clone() for k, v in p0.items()}
+    theirs = [torch.nn.Parameter(v.clone()) for v in p0.values()]
+    opt = torch.optim.SGD(theirs, lr=1e-2, momentum=0.9, weight_decay=5e-5)
+    bufs = {}
+    for _ in range(5):
+        g = {k: torch.randn_like(x) for k, x in p0.items()}
+        for p, gg in zip(theirs, g.values()):
+            p.grad = gg.clone()
+        opt.step()
+        oracle.sgd_step(ours, g, bufs, 1e-2, 0.9, 5e-5)
+    for p, k in zip(theirs, ours):
+        torch.testing.assert_close(ours[k], p.detach(), rtol=1e-6, atol=1e-7)

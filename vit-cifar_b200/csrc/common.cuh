@@ -336,6 +336,14 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = __fmaf_rn(-h.step_size, __fdiv_rn(m, denom), p);
 }
 
+// torch.optim.SGD with momentum (network.py:78-84: momentum = beta1, dampening 0, no Nesterov) on the same hyper block:
+// step_size = lr, beta1 = momentum, wd, grad_scale.  buf starts at zero, so the first step gives buf = g like torch's clone.
+__device__ __forceinline__ void sgd_one(float& p, float g, float& buf, const AdamHyper& h) {
+  g = __fmaf_rn(g, h.grad_scale, __fmul_rn(h.wd, p));
+  buf = __fmaf_rn(h.beta1, buf, g);
+  p = __fmaf_rn(-h.step_size, buf, p);
+}
+
 // ---------------------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT (fp32 check mode / small shapes) and tcgen05 paths
 // ---------------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ struct DpArgs {
   AdamHyper hyper;               // used when hyper_dev is null
   int64_t lo4, hi4;              // owned slice in float4 units
   int rank, world;
+  int optimizer;                 // 0 = Adam, 1 = SGD with momentum (m is the momentum buffer, v unused)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -109,17 +110,24 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
 #pragma unroll
     for (int q = 0; q < kDpMaxWorld; ++q)
       if (q < world) gq[q] = ld4_sys(a.g[q] + i * 4);  // all peers' loads in flight before the first add
-    float4 pp = ld4(pm + i * 4), mm = ld4(a.m + i * 4), vv = ld4(a.v + i * 4);
+    float4 pp = ld4(pm + i * 4), mm = ld4(a.m + i * 4), vv = a.optimizer == 0 ? ld4(a.v + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 gg = gq[0];
 #pragma unroll
     for (int q = 1; q < kDpMaxWorld; ++q)
       if (q < world) { gg.x = __fadd_rn(gg.x, gq[q].x); gg.y = __fadd_rn(gg.y, gq[q].y); gg.z = __fadd_rn(gg.z, gq[q].z); gg.w = __fadd_rn(gg.w, gq[q].w); }
-    adam_one(pp.x, gg.x, mm.x, vv.x, h);
-    adam_one(pp.y, gg.y, mm.y, vv.y, h);
-    adam_one(pp.z, gg.z, mm.z, vv.z, h);
-    adam_one(pp.w, gg.w, mm.w, vv.w, h);
+    if (a.optimizer == 0) {
+      adam_one(pp.x, gg.x, mm.x, vv.x, h);
+      adam_one(pp.y, gg.y, mm.y, vv.y, h);
+      adam_one(pp.z, gg.z, mm.z, vv.z, h);
+      adam_one(pp.w, gg.w, mm.w, vv.w, h);
+      st4(a.v + i * 4, vv);
+    } else {
+      sgd_one(pp.x, gg.x, mm.x, h);
+      sgd_one(pp.y, gg.y, mm.y, h);
+      sgd_one(pp.z, gg.z, mm.z, h);
+      sgd_one(pp.w, gg.w, mm.w, h);
+    }
     st4(a.m + i * 4, mm);
-    st4(a.v + i * 4, vv);
 #pragma unroll
     for (int q = 0; q < kDpMaxWorld; ++q)
       if (q < world) {
@@ -205,8 +213,9 @@ int vitb_ipc_open(const void* handle64, int64_t offset, void** dev_ptr) {
 }
 
 int vitb_dp_reduce_adam(const void* const* g_peers, void* const* p_peers, void* const* shadow_peers, void* const* flag_peers, float* m, float* v,
-                        uint32_t* sync, int64_t n, int rank, int world, const float* hyper_host, const float* hyper_dev, void* stream) {
-  VITB_REQUIRE(g_peers && p_peers && flag_peers && m && v && sync, "dp_reduce_adam: null pointer");
+                        uint32_t* sync, int64_t n, int rank, int world, int optimizer, const float* hyper_host, const float* hyper_dev, void* stream) {
+  VITB_REQUIRE(g_peers && p_peers && flag_peers && m && sync && (v || optimizer == 1), "dp_reduce_adam: null pointer");
+  VITB_REQUIRE(optimizer == 0 || optimizer == 1, "dp_reduce_adam: optimizer %d (0 = Adam, 1 = SGD)", optimizer);
   VITB_REQUIRE(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "dp_reduce_adam: rank %d / world %d (at most %d ranks)", rank, world,
                kDpMaxWorld);
   VITB_REQUIRE(n > 0 && n % 4 == 0, "dp_reduce_adam: the element count (%lld) must be a positive multiple of 4", (long long)n);
@@ -226,7 +235,7 @@ int vitb_dp_reduce_adam(const void* const* g_peers, void* const* p_peers, void* 
   const int64_t n4 = n / 4, per = (n4 + world - 1) / world;
   a.lo4 = per * rank < n4 ? per * rank : n4;
   a.hi4 = per * (rank + 1) < n4 ? per * (rank + 1) : n4;
-  a.rank = rank; a.world = world;
+  a.rank = rank; a.world = world; a.optimizer = optimizer;
   int blocks = (int)ceil_div64(a.hi4 - a.lo4 + 1, 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
   if (blocks < 1) blocks = 1;

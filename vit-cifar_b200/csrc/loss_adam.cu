@@ -92,11 +92,55 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// SGD with momentum over one flat buffer (the reference's `--optimizer sgd`, network.py:78-84)
+__global__ void __launch_bounds__(256)
+    sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, bf16* __restrict__ shadow, int64_t n, AdamHyper hv,
+               const float* __restrict__ hyper_dev) {
+  pdl_trigger();
+  pdl_wait();
+  AdamHyper h = hv;
+  if (hyper_dev != nullptr) h = adam_hyper_from(hyper_dev);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), bb = ld4(buf + i * 4);
+    sgd_one(pp.x, gg.x, bb.x, h);
+    sgd_one(pp.y, gg.y, bb.y, h);
+    sgd_one(pp.z, gg.z, bb.z, h);
+    sgd_one(pp.w, gg.w, bb.w, h);
+    st4(p + i * 4, pp);
+    st4(buf + i * 4, bb);
+    if (shadow != nullptr) st4(shadow + i * 4, pp);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pp = p[i], bb = buf[i];
+    sgd_one(pp, g[i], bb, h);
+    p[i] = pp; buf[i] = bb;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pp);
+  }
+}
+
 }  // namespace vitb
 
 using namespace vitb;
 
 extern "C" {
+
+int vitb_sgd_multi(float* p, const float* g, float* buf, void* w_shadow, int64_t n, const float* hyper_host, const float* hyper_dev, void* stream) {
+  VITB_REQUIRE(p && g && buf, "sgd: null pointer");
+  VITB_REQUIRE(hyper_host || hyper_dev, "sgd: need hyper_host or hyper_dev");
+  VITB_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)buf) % 16 == 0, "sgd: buffers must be 16-byte aligned");
+  VITB_REQUIRE(w_shadow == nullptr || (uintptr_t)w_shadow % 8 == 0, "sgd: shadow must be 8-byte aligned");
+  if (n == 0) return 0;
+  AdamHyper h = {};
+  if (hyper_host) h = adam_hyper_from(hyper_host);
+  int blocks = (int)ceil_div64(n / 4 + 1, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  VITB_LAUNCH((sgd_kernel), blocks, 256, 0, (cudaStream_t)stream, p, g, buf, (bf16*)w_shadow, n, h, hyper_dev);
+  VITB_LAUNCH_OK();
+  return 0;
+}
 
 int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, float* dlogits, int B, int C,
                        float smoothing, float grad_scale, void* stream) {

@@ -17,7 +17,7 @@ import torch
 from . import functional as Fn
 from . import ops
 from .layers import act_dtype
-from .optim import adam_hyper
+from .optim import adam_hyper, sgd_hyper
 from .parallel import allreduce_bucket
 from .params import LayerViews
 from .vit import ViT
@@ -26,8 +26,14 @@ from .vit import ViT
 class TrainEngine:
     def __init__(self, model: ViT, batch_size: int, smoothing: float = 0.1, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 5e-5, process_group=None, use_graph: bool = True,
-                 overlap_comm: bool = False, mixed_targets: bool = False):
+                 overlap_comm: bool = False, mixed_targets: bool = False, optimizer: str = "adam", momentum: Optional[float] = None):
+        """optimizer: "adam" (network.py:71-77) or "sgd" (network.py:78-84: torch.optim.SGD with momentum = beta1 unless `momentum`
+        is given, coupled weight decay)."""
         ops.require_device()
+        if optimizer not in ("adam", "sgd"):
+            raise NotImplementedError(f"Unknown optimizer: {optimizer}")  # the reference's message (network.py:110)
+        self.optimizer = optimizer
+        self.momentum = float(betas[0] if momentum is None else momentum)
         self.model = model
         self.B = int(batch_size)
         self.smoothing = float(smoothing)
@@ -215,9 +221,12 @@ class TrainEngine:
         n = self.n
         if self._fused_dp is not None:
             f = self._fused_dp
-            ops.dp_reduce_adam(f["g"], f["p"], f["c"], f["flags"], self.Mo, self.V, f["sync"], n, f["rank"], self.world, hyper_dev=self.hyper_dev)
-        else:
+            ops.dp_reduce_adam(f["g"], f["p"], f["c"], f["flags"], self.Mo, self.V, f["sync"], n, f["rank"], self.world, hyper_dev=self.hyper_dev,
+                               optimizer=0 if self.optimizer == "adam" else 1)
+        elif self.optimizer == "adam":
             ops.adam(self.P[:n], self.G[:n], self.Mo[:n], self.V[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
+        else:
+            ops.sgd(self.P[:n], self.G[:n], self.Mo[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
 
     def _bwd_alloc(self, i: int):
         shared = self._alloc("bwd")
@@ -275,7 +284,10 @@ class TrainEngine:
             self._consumed.record(cur)
             self._pending = False
         self.step_count += 1
-        h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        if self.optimizer == "adam":
+            h = adam_hyper(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        else:
+            h = sgd_hyper(self.lr, self.momentum, self.weight_decay, 1.0 / self.world)
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
         slot[:9] = torch.tensor(h, dtype=torch.float32)
         slot[9] = self._lam

@@ -230,6 +230,15 @@ def adam(p, g, m, v, shadow, hyper_host=None, hyper_dev=None) -> None:
                                       C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()), "adam_multi")
 
 
+def sgd(p, g, buf, shadow, hyper_host=None, hyper_dev=None) -> None:
+    """torch.optim.SGD with momentum (network.py:78-84) over flat buffers; hyper as optim.sgd_hyper (Adam's 16-float block layout)."""
+    hh = None
+    if hyper_host is not None:
+        hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (16 - len(hyper_host))))
+    check(_lib.load().vitb_sgd_multi(_ptr(p), _ptr(g), _ptr(buf), _ptr(shadow), p.numel(), C.cast(hh, C.c_void_p) if hh is not None else None,
+                                     _ptr(hyper_dev), _stream()), "sgd_multi")
+
+
 # -- data parallel over NVLink peer memory ---------------------------------------------------------
 def ipc_export(t: torch.Tensor):
     """(64-byte handle, byte offset) of a CUDA tensor's memory for another process on this node (vitb_ipc_open)."""
@@ -259,11 +268,12 @@ class PeerPointers:
 
 
 def dp_reduce_adam(g: PeerPointers, p: PeerPointers, shadow: Optional[PeerPointers], flags: PeerPointers, m, v, sync, n: int, rank: int, world: int,
-                   hyper_host=None, hyper_dev=None) -> None:
+                   hyper_host=None, hyper_dev=None, optimizer: int = 0) -> None:
     """Barrier, reduce-scatter of the peers' gradients, Adam on the owned slice, all-gather of the new parameters, barrier — one kernel."""
     hh = None
     if hyper_host is not None:
         hh = _HyperArr(*[float(x) for x in hyper_host], *([0.0] * (16 - len(hyper_host))))
     check(_lib.load().vitb_dp_reduce_adam(g.cptr(), p.cptr(), shadow.cptr() if shadow is not None else None, flags.cptr(), _ptr(m), _ptr(v), _ptr(sync),
-                                          int(n), int(rank), int(world), C.cast(hh, C.c_void_p) if hh is not None else None, _ptr(hyper_dev), _stream()),
+                                          int(n), int(rank), int(world), int(optimizer), C.cast(hh, C.c_void_p) if hh is not None else None,
+                                          _ptr(hyper_dev), _stream()),
           "dp_reduce_adam")

@@ -17,6 +17,11 @@ def adam_hyper(step: int, lr: float, beta1: float, beta2: float, eps: float, wei
     return [lr / bc1, math.sqrt(bc2), beta1, beta2, eps, weight_decay, grad_scale, 1.0 - beta1, 1.0 - beta2]
 
 
+def sgd_hyper(lr: float, momentum: float, weight_decay: float, grad_scale: float = 1.0):
+    """The scalars of vitb_sgd_multi in the slots of Adam's block: [0] lr, [2] momentum, [5] weight decay, [6] gradient scale."""
+    return [lr, 0.0, momentum, 0.0, 0.0, weight_decay, grad_scale, 0.0, 0.0]
+
+
 class FusedAdam:
     """Optimiser over a module packed by vit-cifar_b200 (``module._ensure_packed()``).
 
