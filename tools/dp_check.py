@@ -23,14 +23,14 @@ rank, world = dist.get_rank(), dist.get_world_size()
 ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
 
 
-def run(cfg, B, mode, steps, use_graph, precision):
+def run(cfg, B, mode, steps, use_graph, precision, optimizer="adam"):
     os.environ["VITB_DP_MODE"] = mode
     vb.set_precision(precision)
     m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, num_layers=cfg.num_layers, hidden=cfg.hidden,
                mlp_hidden=cfg.mlp_hidden, head=cfg.head)
     m.load_state_dict(oracle.init_params(cfg, seed=0))
     m = m.cuda()
-    eng = vb.TrainEngine(m, B, use_graph=use_graph, process_group=dist.group.WORLD, **ADAM)
+    eng = vb.TrainEngine(m, B, use_graph=use_graph, process_group=dist.group.WORLD, optimizer=optimizer, **ADAM)
     losses = []
     for t in range(steps):
         x, y = oracle.hash_inputs(cfg, B, seed=100 * t + rank)
@@ -51,11 +51,12 @@ def run(cfg, B, mode, steps, use_graph, precision):
 
 def main():
     ok = True
-    cases = [("tiny fp32", oracle.ViTConfig(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4), 8, "fp32", False),
-             ("bench bf16 graph", oracle.ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 1024, "bf16", True)]
-    for name, cfg, B, precision, graph in cases:
-        p_ref, l_ref, ms_ref = run(cfg, B, "single", 4, graph, precision)
-        p_fus, l_fus, ms_fus = run(cfg, B, "fused", 4, graph, precision)
+    tiny = oracle.ViTConfig(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+    cases = [("tiny fp32", tiny, 8, "fp32", False, "adam"), ("tiny fp32 sgd graph", tiny, 8, "fp32", True, "sgd"),
+             ("bench bf16 graph", oracle.ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 1024, "bf16", True, "adam")]
+    for name, cfg, B, precision, graph, optimizer in cases:
+        p_ref, l_ref, ms_ref = run(cfg, B, "single", 4, graph, precision, optimizer)
+        p_fus, l_fus, ms_fus = run(cfg, B, "fused", 4, graph, precision, optimizer)
         diff = ((p_fus - p_ref).double().norm() / p_ref.double().norm()).item()
         gathered = [torch.empty_like(p_fus) for _ in range(world)]
         dist.all_gather(gathered, p_fus)
