@@ -69,3 +69,16 @@ def test_no_cpu_fallback(built):
         m(torch.zeros(2, 3, 32, 32))
     with pytest.raises(vb.VitbError):
         vb.LabelSmoothingCrossEntropyLoss(10, 0.1)(torch.zeros(2, 10), torch.zeros(2, dtype=torch.long))
+
+
+def test_oracle_is_never_imported_by_the_product_or_the_tools():
+    """oracle/ is test infrastructure: the package and tools/ must not reference it (bench.py's CPU-baseline legs and
+    __graft_entry__.smoke() are the only other users)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for path in glob.glob(os.path.join(root, "vit-cifar_b200", "**", "*.py"), recursive=True) + glob.glob(os.path.join(root, "tools", "*.py")):
+        if re.search(r"^\s*(import|from)\s+oracle\b", open(path).read(), re.M):
+            offenders.append(os.path.relpath(path, root))
+    assert offenders == []

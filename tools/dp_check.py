@@ -13,7 +13,6 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle  # noqa: E402  (test infrastructure: deterministic weights and inputs)
 import vit_cifar_b200 as vb  # noqa: E402
 
 local = int(os.environ["LOCAL_RANK"])
@@ -26,14 +25,14 @@ ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
 def run(cfg, B, mode, steps, use_graph, precision, optimizer="adam"):
     os.environ["VITB_DP_MODE"] = mode
     vb.set_precision(precision)
-    m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, num_layers=cfg.num_layers, hidden=cfg.hidden,
-               mlp_hidden=cfg.mlp_hidden, head=cfg.head)
-    m.load_state_dict(oracle.init_params(cfg, seed=0))
-    m = m.cuda()
+    torch.manual_seed(2045)  # same initial weights for both paths and all ranks
+    m = vb.ViT(3, cfg["num_classes"], img_size=32, patch=cfg["patch"], num_layers=cfg["num_layers"], hidden=cfg["hidden"],
+               mlp_hidden=cfg["mlp_hidden"], head=cfg["head"]).cuda()
     eng = vb.TrainEngine(m, B, use_graph=use_graph, process_group=dist.group.WORLD, optimizer=optimizer, **ADAM)
     losses = []
     for t in range(steps):
-        x, y = oracle.hash_inputs(cfg, B, seed=100 * t + rank)
+        g = torch.Generator().manual_seed(100 * t + rank)  # rank-specific batches
+        x, y = torch.randn(B, 3, 32, 32, generator=g), torch.randint(0, cfg["num_classes"], (B,), generator=g)
         losses.append(eng.step(x.cuda(), y.cuda()).item())
     torch.cuda.synchronize()
     # timing: same batch again and again
@@ -51,9 +50,9 @@ def run(cfg, B, mode, steps, use_graph, precision, optimizer="adam"):
 
 def main():
     ok = True
-    tiny = oracle.ViTConfig(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+    tiny = dict(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
     cases = [("tiny fp32", tiny, 8, "fp32", False, "adam"), ("tiny fp32 sgd graph", tiny, 8, "fp32", True, "sgd"),
-             ("bench bf16 graph", oracle.ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 1024, "bf16", True, "adam")]
+             ("bench bf16 graph", dict(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12), 1024, "bf16", True, "adam")]
     for name, cfg, B, precision, graph, optimizer in cases:
         p_ref, l_ref, ms_ref = run(cfg, B, "single", 4, graph, precision, optimizer)
         p_fus, l_fus, ms_fus = run(cfg, B, "fused", 4, graph, precision, optimizer)
