@@ -132,6 +132,14 @@ int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int row
 int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip,
                                      const float* mean3, const float* std3, float* out, int B, int S, int pad, void* stream);
 
+/* ---- batch-level CutMix / MixUp (da.py:51-93; network.py:149-158) on a normalised fp32 (B, C, S, S) device batch; perm int32 (B) =
+ * the shuffled partner of every image (the caller draws it, with lam and the box, like the reference does on the host).
+ * mode 0: out[b, :, i, j] = img[perm[b], :, i, j] inside rows x1 <= i < x2, columns y1 <= j < y2 (the reference's own index order,
+ * da.py:68), img[b] elsewhere; mode 1: out = lam * img[b] + (1 - lam) * img[perm[b]] with lam and 1 - lam rounded to fp32 from the
+ * double, as torch does for a Python scalar.  out must not alias img; S % 4 == 0. ---- */
+int vitb_batch_mix(const float* img, const int32_t* perm, float* out, int B, int C, int S, int mode, double lam, int x1, int x2, int y1, int y2,
+                   void* stream);
+
 /* ---- nn.Dropout of the encoder block (layers.py:35, 38, 102; replaces torch's native_dropout on this path):
  *   out[i] = x[i] * keep[i] / (1 - p)  (+ residual[i] if residual != NULL);  x / residual / out act, n elements, n % 8 == 0; in place allowed.
  * keep is not stored: it is Philox4x32-10 with key = seed and counter = (i / 8 as 64 bits, site, step); element i takes the 16-bit

@@ -26,6 +26,8 @@ from .vit_oracle import (  # noqa: F401
     ls_ce_loss,
     ls_ce_dlogits,
     mixed_ls_ce_loss,
+    cutmix_apply,
+    mixup_apply,
     philox4x32_10,
     dropout_threshold,
     dropout_keep_mask,

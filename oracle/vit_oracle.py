@@ -285,6 +285,19 @@ def augment_crop_flip_normalize(img_u8: torch.Tensor, dx: torch.Tensor, dy: torc
     return out
 
 
+def cutmix_apply(img: torch.Tensor, perm: torch.Tensor, box) -> torch.Tensor:
+    """da.py:57-68: rand_img = img[perm]; img[:, :, x1:x2, y1:y2] = rand_img[:, :, x1:x2, y1:y2] (on a copy)."""
+    x1, x2, y1, y2 = box
+    out = img.clone()
+    out[:, :, x1:x2, y1:y2] = img[perm][:, :, x1:x2, y1:y2]
+    return out
+
+
+def mixup_apply(x: torch.Tensor, index: torch.Tensor, lam: float) -> torch.Tensor:
+    """da.py:90: mixed_x = lam * x + (1 - lam) * x[index, :]."""
+    return lam * x + (1 - lam) * x[index, :]
+
+
 def mixed_ls_ce_loss(logits: torch.Tensor, target_a: torch.Tensor, target_b: torch.Tensor, lam: float, classes: int,
                      smoothing: float) -> torch.Tensor:
     """CutMix / MixUp objective, network.py:163-165: loss(out, label) * lambda + loss(out, rand_label) * (1 - lambda)."""

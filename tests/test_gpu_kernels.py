@@ -432,3 +432,29 @@ def test_dropout_keep_rate_at_training_size(ops):
     q = 1.0 - round(p * 65536) / 65536
     assert abs(kept - q) < 5 * math.sqrt(q * (1 - q) / n)
     assert abs(out.float().mean().item() - q / (1 - p)) < 1e-2
+
+
+def test_cutmix_mixup_on_device(ops):
+    """vb.GpuCutMix / vb.GpuMixUp (da.py:51-93): with the generators seeded like the reference's they return the oracle's batches
+    bit for bit (the paste is a copy; the blend uses torch's rounding: two products, one sum), the shuffled labels and lambda."""
+    import numpy as np
+    import oracle
+    import vit_cifar_b200 as vb
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(64, 3, 32, 32, generator=g); label = torch.randint(0, 10, (64,), generator=g)
+    for seed in range(5):
+        np.random.seed(seed); torch.manual_seed(seed)
+        out, la, lb, lam = vb.GpuCutMix(32, 1.0)((img.cuda(), label.cuda()))
+        np.random.seed(seed); torch.manual_seed(seed)
+        perm = torch.randperm(64)
+        box, lam_ref = vb.cutmix_box(32, np.random.beta(1.0, 1.0), np.random.uniform(0, 32), np.random.uniform(0, 32))
+        assert lam == lam_ref and torch.equal(lb.cpu(), label[perm]) and torch.equal(la.cpu(), label)
+        assert torch.equal(out.cpu(), oracle.cutmix_apply(img, perm, box))
+        np.random.seed(seed); torch.manual_seed(seed)
+        mx, ya, yb, lam_m = vb.GpuMixUp(0.4)((img.cuda(), label.cuda()))
+        np.random.seed(seed); torch.manual_seed(seed)
+        lam2 = np.random.beta(0.4, 0.4); index = torch.randperm(64)
+        assert lam_m == lam2 and torch.equal(yb.cpu(), label[index])
+        assert torch.equal(mx.cpu(), oracle.mixup_apply(img, index, lam2))
+    with pytest.raises(Exception):
+        ops.batch_mix(img.cuda(), torch.arange(64, dtype=torch.int32, device="cuda"), img.cuda()[:, :, :, :30].contiguous(), 0)

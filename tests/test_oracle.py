@@ -258,3 +258,31 @@ def test_sgd_restatement_matches_torch_sgd():
         oracle.sgd_step(ours, g, bufs, 1e-2, 0.9, 5e-5)
     for p, k in zip(theirs, ours):
         torch.testing.assert_close(ours[k], p.detach(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_cutmix_mixup_restatements_match_live_reference():
+    """da.CutMix / da.MixUp (da.py:51-93) with seeded generators vs the oracle's paste / blend and the product's host-side box
+    arithmetic (vit_cifar_b200.cutmix_box draws nothing itself: same numbers in, same box out)."""
+    import numpy as np
+    import_reference()
+    import da as ref_da  # the reference's module (sys.path set by import_reference)
+    import vit_cifar_b200 as vb
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(16, 3, 32, 32, generator=g)
+    label = torch.randint(0, 10, (16,), generator=g)
+    for seed in range(6):
+        np.random.seed(seed); torch.manual_seed(seed)
+        out_ref, l_ref, rl_ref, lam_ref = ref_da.CutMix(32, 1.0)((img.clone(), label.clone()))
+        np.random.seed(seed); torch.manual_seed(seed)
+        perm = torch.randperm(16)
+        lam0 = np.random.beta(1.0, 1.0); r_x = np.random.uniform(0, 32); r_y = np.random.uniform(0, 32)
+        box, lam = vb.cutmix_box(32, lam0, r_x, r_y)
+        assert lam == lam_ref and torch.equal(label[perm], rl_ref) and torch.equal(l_ref, label)
+        assert torch.equal(oracle.cutmix_apply(img, perm, box), out_ref)
+        np.random.seed(seed); torch.manual_seed(seed)
+        mx_ref, ya, yb, lam_m = ref_da.MixUp(0.1)((img, label))
+        np.random.seed(seed); torch.manual_seed(seed)
+        lam2 = np.random.beta(0.1, 0.1); index = torch.randperm(16)
+        assert lam2 == lam_m and torch.equal(label[index], yb)
+        assert torch.equal(oracle.mixup_apply(img, index, lam2), mx_ref)

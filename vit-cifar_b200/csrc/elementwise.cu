@@ -481,6 +481,42 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// batch-level CutMix / MixUp (da.py:51-93, applied at network.py:149-158) on fp32 (B, C, S, S) batches:
+//   mode 0 (CutMix)  out[b, c, i, j] = img[perm[b], c, i, j] if x1 <= i < x2 and y1 <= j < y2 else img[b, c, i, j]
+//                    (the reference indexes rows with its "x" and columns with its "y": img[:, :, x1:x2, y1:y2], da.py:68)
+//   mode 1 (MixUp)   out = lam * img[b] + (1 - lam) * img[perm[b]]                                     (da.py:90)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    batch_mix_kernel(const float* __restrict__ img, const int32_t* __restrict__ perm, float* __restrict__ out, int64_t per_image, int B, int S, int mode,
+                     float lam, float oml, int x1, int x2, int y1, int y2) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t total4 = (int64_t)B * per_image / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = q * 4;
+    const int b = (int)(e / per_image);
+    const int64_t r = e - (int64_t)b * per_image;
+    const float4 a = ld4(img + e);
+    const float4 o = ld4(img + (int64_t)perm[b] * per_image + r);
+    float4 v;
+    if (mode == 1) {
+      // two rounded products and a rounded sum, as torch evaluates lam * x + (1 - lam) * x[index] (no contraction)
+      v = make_float4(__fadd_rn(__fmul_rn(lam, a.x), __fmul_rn(oml, o.x)), __fadd_rn(__fmul_rn(lam, a.y), __fmul_rn(oml, o.y)),
+                      __fadd_rn(__fmul_rn(lam, a.z), __fmul_rn(oml, o.z)), __fadd_rn(__fmul_rn(lam, a.w), __fmul_rn(oml, o.w)));
+    } else {
+      const int pix = (int)(r % ((int64_t)S * S));
+      const int i = pix / S, j = pix % S;  // S % 4 == 0: the four elements share the row
+      const bool row_in = i >= x1 && i < x2;
+      v.x = (row_in && j >= y1 && j < y2) ? o.x : a.x;
+      v.y = (row_in && j + 1 >= y1 && j + 1 < y2) ? o.y : a.y;
+      v.z = (row_in && j + 2 >= y1 && j + 2 < y2) ? o.z : a.z;
+      v.w = (row_in && j + 3 >= y1 && j + 3 < y2) ? o.w : a.w;
+    }
+    st4(out + e, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dropout (nn.Dropout at layers.py:35, 38, 102): out = x * keep / (1 - p) (+ residual)
 //
 // The keep mask is never stored: it is a pure function of (seed, site, step, element index) — Philox4x32-10 with key = seed
@@ -649,6 +685,22 @@ int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, c
   if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
   VITB_LAUNCH((augment_kernel), blocks, 256, 0, (cudaStream_t)stream, img_u8, dx, dy, flip, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out,
               B, S, pad);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+int vitb_batch_mix(const float* img, const int32_t* perm, float* out, int B, int C, int S, int mode, double lam, int x1, int x2, int y1, int y2,
+                   void* stream) {
+  VITB_REQUIRE(img && perm && out && img != out, "batch_mix: null pointer, or out aliases img (every image is read by two outputs)");
+  VITB_REQUIRE(B > 0 && C > 0 && S > 0 && S % 4 == 0, "batch_mix: bad shape B=%d C=%d S=%d (S must be a multiple of 4)", B, C, S);
+  VITB_REQUIRE(mode == 0 || mode == 1, "batch_mix: mode %d (0 = CutMix, 1 = MixUp)", mode);
+  VITB_REQUIRE(mode == 1 || (0 <= x1 && x1 <= x2 && x2 <= S && 0 <= y1 && y1 <= y2 && y2 <= S), "batch_mix: box [%d,%d) x [%d,%d) outside the image", x1, x2,
+               y1, y2);
+  const int64_t per_image = (int64_t)C * S * S;
+  int blocks = (int)ceil_div64((int64_t)B * per_image / 4, 256);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  VITB_LAUNCH((batch_mix_kernel), blocks, 256, 0, (cudaStream_t)stream, img, perm, out, per_image, B, S, mode, (float)lam, (float)(1.0 - lam), x1, x2,
+              y1, y2);
   VITB_LAUNCH_OK();
   return 0;
 }

@@ -191,6 +191,16 @@ def augment(img_u8, dx, dy, flip, mean, std, out, pad: int) -> None:
                                                        _ptr(out), B, S, int(pad), _stream()), "augment_crop_flip_normalize")
 
 
+def batch_mix(img, perm, out, mode: int, lam: float = 1.0, box=(0, 0, 0, 0)) -> None:
+    """CutMix (mode 0: paste rows box[0]:box[1], columns box[2]:box[3] of img[perm[b]] into img[b], da.py:68) or MixUp (mode 1:
+    lam * img + (1 - lam) * img[perm], da.py:90) of an fp32 (B, C, S, S) batch into `out`."""
+    B, Cn, S, S2 = img.shape
+    assert S == S2 and img.dtype == torch.float32 and out.dtype == torch.float32 and out.shape == img.shape and perm.dtype == torch.int32
+    _contig(img, perm, out)
+    x1, x2, y1, y2 = (int(v) for v in box)
+    check(_lib.load().vitb_batch_mix(_ptr(img), _ptr(perm), _ptr(out), B, Cn, S, int(mode), float(lam), x1, x2, y1, y2, _stream()), "batch_mix")
+
+
 def dropout(x, residual, out, p: float, seed: int, site: int, step: int = 0, step_dev=None) -> None:
     """out = x * keep / (1 - p) (+ residual), nn.Dropout semantics (layers.py:35, 38, 102).  keep is a pure function of
     (seed, site, step, element index): the backward pass is the same call on the gradient.  `step_dev`: 1-element int32 device

@@ -116,3 +116,58 @@ class GpuAugment:
         dx, dy, fl = self.draw(B, img_u8.device)
         ops.augment(img_u8, dx, dy, fl, self.mean, self.std, out, self.padding)
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# batch-level CutMix / MixUp on the device (da.py:51-93; used at network.py:149-158)
+# ---------------------------------------------------------------------------------------------
+def cutmix_box(size: int, lambda_: float, r_x: float, r_y: float):
+    """The box arithmetic of da.py:60-70: returns (x1, x2, y1, y2) and the area-corrected lambda."""
+    import numpy as np
+    r_w = size * np.sqrt(1 - lambda_)
+    r_h = size * np.sqrt(1 - lambda_)
+    x1 = int(np.clip(r_x - r_w // 2, a_min=0, a_max=size))
+    x2 = int(np.clip(r_x + r_w // 2, a_min=0, a_max=size))
+    y1 = int(np.clip(r_y - r_h // 2, a_min=0, a_max=size))
+    y2 = int(np.clip(r_y + r_h // 2, a_min=0, a_max=size))
+    return (x1, x2, y1, y2), 1 - (x2 - x1) * (y2 - y1) / (size * size)
+
+
+class GpuCutMix:
+    """da.CutMix (da.py:51-77) for a batch that is already on the device: same random draws in the same order from the same
+    generators (torch.randperm, then np.random.beta / uniform), same return tuple (img, label, rand_label, lambda_); the paste is
+    one kernel instead of a clone + fancy-index gather + slice assignment."""
+
+    def __init__(self, size: int, beta: float):
+        self.size, self.beta = size, beta
+
+    def __call__(self, batch):
+        import numpy as np
+        from . import ops
+        img, label = batch
+        rand_idx = torch.randperm(img.size(0))
+        lambda_ = np.random.beta(self.beta, self.beta)
+        r_x = np.random.uniform(0, self.size)
+        r_y = np.random.uniform(0, self.size)
+        box, lambda_ = cutmix_box(self.size, lambda_, r_x, r_y)
+        idx = rand_idx.to(img.device)
+        out = torch.empty_like(img)
+        ops.batch_mix(img, idx.to(torch.int32), out, 0, 1.0, box)
+        return out, label, label[idx], lambda_
+
+
+class GpuMixUp:
+    """da.MixUp (da.py:80-93) on the device: lam ~ Beta(alpha, alpha), index = randperm, lam * x + (1 - lam) * x[index]."""
+
+    def __init__(self, alpha: float = 0.1):
+        self.alpha = alpha
+
+    def __call__(self, batch):
+        import numpy as np
+        from . import ops
+        x, y = batch
+        lam = np.random.beta(self.alpha, self.alpha)
+        index = torch.randperm(x.size(0)).to(x.device)
+        out = torch.empty_like(x)
+        ops.batch_mix(x, index.to(torch.int32), out, 1, lam)
+        return out, y, y[index], lam

@@ -19,7 +19,7 @@ from ._lib import VitbError, LIB_PATH, load as load_library  # noqa: E402,F401
 from .layers import MultiHeadSelfAttention, TransformerEncoder, get_precision, set_precision  # noqa: E402,F401
 from .vit import ViT  # noqa: E402,F401
 from .criterions import LabelSmoothingCrossEntropyLoss  # noqa: E402,F401
-from .optim import FusedAdam, adam_hyper  # noqa: E402,F401
+from .optim import FusedAdam, adam_hyper, sgd_hyper  # noqa: E402,F401
 from .engine import TrainEngine  # noqa: E402,F401
 from .schedule import (WarmupCosine, warmup_cosine_lr, evaluate, save_checkpoint, load_checkpoint, to_lightning_checkpoint,  # noqa: E402,F401
-                       GpuAugment)
+                       GpuAugment, GpuCutMix, GpuMixUp, cutmix_box)
