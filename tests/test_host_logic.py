@@ -166,6 +166,67 @@ def test_bucket_allreduce_two_ranks_gloo():
     assert torch.equal(a["p"], b["p"])
 
 
+def _ipc_worker(rank, world, port, outdir, failing_rank, fail_at):
+    """Handle exchange of the fused data-parallel step with the CUDA IPC calls replaced by fakes (no GPU here): what is tested is
+    the collective choreography — one all_gather_object, failures stay local, every rank reaches the same verdict."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vit_cifar_b200 import ops
+        from vit_cifar_b200.parallel import exchange_peer_pointers
+
+        class FakeTensor:
+            def __init__(self, addr):
+                self.addr = addr
+
+            def data_ptr(self):
+                return self.addr
+
+        def fake_export(t):
+            if rank == failing_rank and fail_at == "export":
+                raise RuntimeError("cannot export")
+            return (bytes([rank]) * 64, t.addr)
+
+        def fake_open(handle, offset):
+            if rank == failing_rank and fail_at == "open":
+                raise RuntimeError("no peer access")
+            return 1_000_000 * (handle[0] + 1) + offset
+
+        ops.ipc_export, ops.ipc_open = fake_export, fake_open
+        tensors = dict(g=FakeTensor(16 + rank), p=FakeTensor(32 + rank), c=None, flags=FakeTensor(48 + rank))
+        peers, err = exchange_peer_pointers(tensors, None)
+        ok = torch.tensor([0 if peers is None else 1])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res = dict(ok=int(ok.item()), err=None if err is None else str(err),
+                   ptrs=None if peers is None else {k: (v.ptrs if v is not None else None) for k, v in peers.items()})
+        torch.save(res, os.path.join(outdir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_at", [None, "export", "open"])
+def test_peer_pointer_exchange_two_ranks_gloo(fail_at):
+    import tempfile
+    ctx = mp.get_context("spawn")
+    port = 31500 + os.getpid() % 2000 + {None: 0, "export": 1, "open": 2}[fail_at]
+    with tempfile.TemporaryDirectory() as outdir:
+        procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, outdir, 1, fail_at)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=180)
+            assert p.exitcode == 0  # in particular: nobody hangs when one rank fails
+        got = {r: torch.load(os.path.join(outdir, f"rank{r}.pt")) for r in range(2)}
+    if fail_at is None:
+        assert got[0]["ok"] == got[1]["ok"] == 1
+        # own address at [rank], the peer's mapped address (fake base of the OTHER rank + its offset) elsewhere; None passes through
+        assert got[0]["ptrs"]["g"] == [16, 2_000_000 + 17] and got[1]["ptrs"]["g"] == [1_000_000 + 16, 17]
+        assert got[0]["ptrs"]["flags"] == [48, 2_000_000 + 49] and got[0]["ptrs"]["c"] is None
+    else:
+        assert got[0]["ok"] == got[1]["ok"] == 0  # both fall back together
+        assert got[1]["err"] is not None
+
+
 # ---------------------------------------------------------------------------------------------
 # SURVEY.md §8f rank 1-2: LR schedule, checkpoint format
 # ---------------------------------------------------------------------------------------------

@@ -88,15 +88,10 @@ class TrainEngine:
             flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
             sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
             torch.cuda.synchronize(self.dev)
-            peers, err = None, None
-            try:
-                if self.world > 8 or self.n % 4 != 0:
-                    raise ValueError("at most 8 ranks of one node and a flat buffer that is a multiple of 4 elements")
-                peers = dict(g=exchange_peer_pointers(self.G, self.pg), p=exchange_peer_pointers(self.P, self.pg),
-                             c=exchange_peer_pointers(self.C, self.pg) if self.C is not self.P else None,
-                             flags=exchange_peer_pointers(flags, self.pg))
-            except Exception as e:  # no peer access between these GPUs (or ranks on different nodes): all ranks use NCCL instead
-                err = e
+            if self.world > 8 or self.n % 4 != 0:  # the same on every rank
+                peers, err = None, ValueError("at most 8 ranks of one node and a flat buffer that is a multiple of 4 elements")
+            else:
+                peers, err = exchange_peer_pointers(dict(g=self.G, p=self.P, c=self.C if self.C is not self.P else None, flags=flags), self.pg)
             ok = torch.tensor([0 if peers is None else 1], device=self.dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)  # also: every rank has mapped every peer before the first step
             if int(ok.item()) == 1:

@@ -36,15 +36,30 @@ def owned_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
     return min(per * rank, n4) * 4, min(per * (rank + 1), n4) * 4
 
 
-def exchange_peer_pointers(t: torch.Tensor, group=None):
-    """Map every rank's copy of `t` (same shape on all ranks of one node) into this process through CUDA IPC; returns the device
-    addresses in rank order (this rank's own address at [rank]).  torch.distributed only carries the 64-byte handles."""
+def exchange_peer_pointers(tensors, group=None):
+    """Map every rank's copies of `tensors` (a dict name -> CUDA tensor, same shapes on all ranks of one node; None values are
+    passed through) into this process through CUDA IPC.  Returns (dict name -> ops.PeerPointers in rank order, with this rank's
+    own address at [rank]; error or None).  Exactly ONE collective is issued (an all_gather_object of the 64-byte handles), and
+    it is issued before anything that can fail locally, so a rank whose mapping fails cannot desynchronise the others."""
     from . import ops
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    mine = ops.ipc_export(t)
+    mine, err = {}, None
+    try:
+        mine = {k: ops.ipc_export(t) for k, t in tensors.items() if t is not None}
+    except Exception as e:  # e.g. memory that cannot be exported (expandable segments)
+        err = e
     everyone = [None] * world
-    dist.all_gather_object(everyone, mine, group=group)
-    ptrs = []
-    for r, (handle, offset) in enumerate(everyone):
-        ptrs.append(t.data_ptr() if r == rank else ops.ipc_open(handle, offset))
-    return ops.PeerPointers(ptrs)
+    dist.all_gather_object(everyone, mine if err is None else None, group=group)
+    if err is None and any(e is None for e in everyone):
+        err = RuntimeError("another rank could not export its buffers")
+    out = {}
+    if err is None:
+        try:
+            for k, t in tensors.items():
+                if t is None:
+                    out[k] = None
+                    continue
+                out[k] = ops.PeerPointers([t.data_ptr() if r == rank else ops.ipc_open(*everyone[r][k]) for r in range(world)])
+        except Exception as e:  # no peer access between two of the GPUs
+            err = e
+    return (out if err is None else None), err
