@@ -43,6 +43,13 @@ unsigned long long vitb_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (the kernels are sm_100a only). */
 int vitb_device_supported(void);
 
+/* ---- L2 residency hint for the weights (host function; no kernel): every kernel launched through this library while a window is
+ * set carries it as cudaLaunchAttributeAccessPolicyWindow (so captured CUDA-graph nodes keep it): reads of [base, base + bytes)
+ * are persisting in a carve-out of `carve_out_bytes` of L2, everything else is streaming.  Intended for the bf16 weight shadow
+ * (12.5 MB for the 7-layer model): the resident GEMMs then find their weight block in L2 at kernel start instead of in HBM.
+ * base = NULL clears the window.  Values are clamped to the device limits. ---- */
+int vitb_set_l2_persisting_window(void* base, size_t bytes, size_t carve_out_bytes);
+
 /* fp32 -> bf16 copy of a flat buffer (weight shadow refresh after an external optimiser step). */
 int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

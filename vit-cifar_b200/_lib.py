@@ -32,6 +32,7 @@ SIGNATURES = {
     "vitb_last_error": (C.c_char_p, []),
     "vitb_device_supported": (_i, []),
     "vitb_launch_count": (C.c_ulonglong, []),
+    "vitb_set_l2_persisting_window": (_i, [_p, _sz, _sz]),
     "vitb_cast_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
     "vitb_patch_embed_fwd_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "vitb_patch_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),

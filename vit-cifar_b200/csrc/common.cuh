@@ -59,6 +59,23 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 bool pdl_enabled();  // VITB_PDL=1 in the environment switches the launch attribute on
 
+// Optional L2 persistence window (vitb_set_l2_persisting_window): every kernel launched while it is set carries it as a launch
+// attribute (so it is recorded in captured graph nodes): reads inside the window are kept in the persisting carve-out of L2.
+struct PersistWindow { void* base; size_t bytes; float hit_ratio; };
+const PersistWindow& persist_window();
+void set_persist_window(void* base, size_t bytes, float hit_ratio);
+inline int add_persist_attr(cudaLaunchAttribute* attr, int n) {
+  const PersistWindow& w = persist_window();
+  if (w.base == nullptr || w.bytes == 0) return n;
+  attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+  attr[n].val.accessPolicyWindow.base_ptr = w.base;
+  attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
+  attr[n].val.accessPolicyWindow.hitRatio = w.hit_ratio;
+  attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  return n + 1;
+}
+
 template <typename... Exp, typename... Act>
 inline cudaError_t launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -66,11 +83,16 @@ inline cudaError_t launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  n = add_persist_attr(attr, n);
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
 }
 // same, as thread-block clusters of `cluster` consecutive CTAs (cta_group::2 GEMM pairs)

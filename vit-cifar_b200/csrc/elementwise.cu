@@ -21,6 +21,9 @@ bool pdl_enabled() {
   static const bool on = getenv("VITB_PDL") && atoi(getenv("VITB_PDL")) != 0;
   return on;
 }
+static PersistWindow g_persist = {nullptr, 0, 1.0f};
+const PersistWindow& persist_window() { return g_persist; }
+void set_persist_window(void* base, size_t bytes, float hit_ratio) { g_persist = {base, bytes, hit_ratio}; }
 static unsigned long long g_launches = 0;  // host-side, single launching thread per process
 void count_launch() { ++g_launches; }
 
@@ -583,6 +586,25 @@ int vitb_device_supported(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10 ? 1 : 0;
+}
+
+int vitb_set_l2_persisting_window(void* base, size_t bytes, size_t carve_out_bytes) {
+  if (base == nullptr || bytes == 0) {
+    set_persist_window(nullptr, 0, 1.0f);
+    return 0;
+  }
+  int dev = 0, max_window = 0, max_persist = 0;
+  VITB_CUDA_OK(cudaGetDevice(&dev));
+  VITB_CUDA_OK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  VITB_CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  VITB_REQUIRE(max_window > 0 && max_persist > 0, "l2 persistence: not supported by this device");
+  if (carve_out_bytes > (size_t)max_persist) carve_out_bytes = (size_t)max_persist;
+  if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+  VITB_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve_out_bytes));
+  // a window larger than the carve-out keeps a random carve_out / bytes share of its lines resident instead of thrashing
+  const float ratio = bytes <= carve_out_bytes ? 1.0f : (float)((double)carve_out_bytes / (double)bytes);
+  set_persist_window(base, bytes, ratio);
+  return 0;
 }
 
 int vitb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {

@@ -47,6 +47,7 @@ class TrainEngine:
         # two-target loss lam*L(out,y) + (1-lam)*L(out,y') for CutMix / MixUp batches (network.py:149-167); lam travels in the
         # per-step hyper-parameter block so the captured graph reads a fresh value every step
         self.mixed_targets = bool(mixed_targets)
+        self._l2_persist = os.environ.get("VITB_L2_PERSIST", "0") != "0"
         self._lam = 1.0
         self._next_lam = 1.0
         # "overlap": per-layer buckets on a side stream while backward continues; "single": one all-reduce of the whole flat
@@ -288,6 +289,9 @@ class TrainEngine:
         slot[9] = self._lam
         slot.view(torch.int32)[10] = self.step_count & 0x7FFFFFFF  # dropout mask step
         self.hyper_dev.copy_(slot, non_blocking=True)
+        if self._l2_persist and self.step_count == 1 and self.C is not self.P:
+            # bf16 weights stay in a persisting carve-out of L2 (16 MB of 126): the resident GEMMs' weight blocks are L2 hits
+            ops.set_l2_persisting_window(self.C[:self.n], max(16 << 20, self.n * 2))
         if not self.use_graph:
             n0 = ops.launch_count()
             self._body()

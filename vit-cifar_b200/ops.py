@@ -201,6 +201,16 @@ def batch_mix(img, perm, out, mode: int, lam: float = 1.0, box=(0, 0, 0, 0)) -> 
     check(_lib.load().vitb_batch_mix(_ptr(img), _ptr(perm), _ptr(out), B, Cn, S, int(mode), float(lam), x1, x2, y1, y2, _stream()), "batch_mix")
 
 
+def set_l2_persisting_window(t: Optional[torch.Tensor], carve_out_bytes: int = 0) -> None:
+    """Keep reads of tensor `t` (the bf16 weight shadow) in a persisting carve-out of L2 for every kernel launched from now on
+    (recorded in captured graph nodes); None clears it."""
+    if t is None:
+        check(_lib.load().vitb_set_l2_persisting_window(None, 0, 0), "set_l2_persisting_window")
+        return
+    nbytes = t.numel() * t.element_size()
+    check(_lib.load().vitb_set_l2_persisting_window(_ptr(t), nbytes, int(carve_out_bytes) or nbytes), "set_l2_persisting_window")
+
+
 def dropout(x, residual, out, p: float, seed: int, site: int, step: int = 0, step_dev=None) -> None:
     """out = x * keep / (1 - p) (+ residual), nn.Dropout semantics (layers.py:35, 38, 102).  keep is a pure function of
     (seed, site, step, element index): the backward pass is the same call on the gradient.  `step_dev`: 1-element int32 device
