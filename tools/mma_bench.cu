@@ -26,6 +26,16 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
                "r"(idesc), "r"(accumulate)
                : "memory");
 }
+// A operand in tensor memory (the "TS" form): D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -112,7 +122,13 @@ __global__ void __launch_bounds__(384, 1) mma_bench_kernel(long long* out, int t
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + kk * kstep);
               const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(b_lo + kk * kstep);
-              tc_mma(d, ad, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              if (VARIANT == 2) {
+                // A (128 rows x 16 bf16 per k-step = 8 columns of 32 bit) resident in tensor memory behind the two accumulators:
+                // the K = 384 weight block of the 384-wide GEMMs would occupy 192 columns
+                tc_mma_ts(d, tmem_base + 2u * N + (uint32_t)((kb * 4 + kk) % ((512 - 2 * N) / 8)) * 8u, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);  // stay inside the 512 columns
+              } else {
+                tc_mma(d, ad, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              }
             }
             tc_commit(bars + stage * 8);
           }
@@ -340,6 +356,14 @@ int main() {
   run<128, 1, false>("v1 elect K-major +stream", d_out, gsrc, 64 * 98304);
   run<256, 1, false>("v1 elect K-major +stream", d_out, gsrc, 64 * 98304);
   run<128, 1, true>("v1 elect MN-major +stream", d_out, gsrc, 64 * 98304);
+  if (getenv("TS_ONLY")) {  // A from tensor memory vs A from shared memory
+    run<128, 1, false>("SS: A smem, B smem (K-major)", d_out, gsrc, 0);
+    run<128, 2, false>("TS: A tmem, B smem (K-major)", d_out, gsrc, 0);
+    run<192, 2, false>("TS: A tmem, B smem (K-major)", d_out, gsrc, 0);
+    run<128, 2, false>("TS +stream", d_out, gsrc, 64 * 98304);
+    run<128, 1, false>("SS +stream", d_out, gsrc, 64 * 98304);
+    return 0;
+  }
   if (getenv("MPS_ONLY")) {
     for (int mps = 4; mps <= 16; mps *= 2) {
       run_ring<128, 6>(d_out, gsrc, 0, 0, 1, 0, false, mps, 1);
