@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(384, 1) mma_bench_kernel(long long* out, int t
               if (VARIANT == 2) {
                 // A (128 rows x 16 bf16 per k-step = 8 columns of 32 bit) resident in tensor memory behind the two accumulators:
                 // the K = 384 weight block of the 384-wide GEMMs would occupy 192 columns
-                tc_mma_ts(d, tmem_base + 2u * N + (uint32_t)((kb * 4 + kk) % ((512 - 2 * N) / 8)) * 8u, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);  // stay inside the 512 columns
+                tc_mma_ts(d, tmem_base + 2u * N + (uint32_t)((kb * 4 + kk) % ((512 - 2 * N) / 8 > 0 ? (512 - 2 * N) / 8 : 1)) * 8u, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);  // stay inside the 512 columns
               } else {
                 tc_mma(d, ad, bd, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
               }
