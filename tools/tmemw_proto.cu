@@ -1,0 +1,322 @@
+// tmemw_proto.cu — prototype of the round-2 idea for the 384-wide GEMMs: keep the resident WEIGHT block in tensor memory instead
+// of shared memory, so that the whole shared memory is a ring for the activation tiles.
+//
+//   out[m, n] = sum_k A[m, k] W[n, k]        A: M x 384 bf16 (activations), W: 384 x 384 bf16 (nn.Linear layout), fp32 accumulation
+//
+// computed TRANSPOSED per CTA:  D[n_local, m_local] (+)= Wblk[n_local, k] * Atile[m_local, k]^T  with tcgen05.mma in its TMEM-A form:
+//   M side  = 128 weight rows of this CTA's column block, resident in TMEM columns [256, 448) (K = 384 -> 24 k-steps x 8 columns)
+//   N side  = 128 activation rows, K-major 128B-swizzled tiles streamed by TMA through a ring of STAGES x KPS x 16 KB
+//   D       = two accumulators (TMEM columns [0, 128) and [128, 256)): the epilogue of tile i overlaps the MMAs of tile i + 1
+// The epilogue here is minimal (validation: fp32 stores of the transposed tile; timing: one partial sum per thread): the point
+// is (1) is the TMEM-A operand layout what we think, (2) what does the main loop deliver with a 96 / 192 KB ring.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/tmemw_proto tools/tmemw_proto.cu
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+constexpr int BM = 128, BK = 64, K = 384, N = 384, KB = K / BK;  // KB = 6 k-blocks
+constexpr uint32_t kTileBytes = BM * BK * 2;                     // 16 KB
+constexpr uint32_t kColAcc = 0, kColW = 256;
+constexpr long long kSpin = 2LL * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > kSpin) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: LBO unused (16 B), SBO = 1024 B (eight 128-byte rows), version 1, swizzle mode 2 (128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+  const uint32_t hi = (uint32_t)((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+struct Params {
+  const __nv_bfloat16* w;  // [N][K]
+  float* out;              // validation: [M][N] fp32; timing: [M / 32][N] partial sums
+  long long* clocks;       // per CTA: cycles of the MMA issuer, bytes streamed
+  int M, validate;
+};
+
+template <int STAGES, int KPS>
+__global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ CUtensorMap map_a, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kStage = KPS * kTileBytes;
+  const uint32_t bars = base + STAGES * kStage;  // full[STAGES] empty[STAGES] tfull[2] tempty[2] wready
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t wready = bars + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    mbar_init(wready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int nb = blockIdx.x % 3, member = blockIdx.x / 3, members = gridDim.x / 3;
+  const int m_tiles = p.M / BM;
+  // instruction descriptor: D fp32, A / B bf16, both K-major, N = 128 (activation rows), M = 128 (weight rows)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = member; mt < m_tiles; mt += members) {
+      for (int kb = 0; kb < KB; kb += KPS) {
+        mbar_wait(empty(stage), phase ^ 1u);
+        if (leader) {
+          mbar_arrive_expect_tx(full(stage), kStage);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) tma_load_2d(base + stage * kStage + j * kTileBytes, &map_a, full(stage), (kb + j) * BK, mt * BM);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const bool leader = elect_one();
+    mbar_wait(wready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const long long t0 = clock64();
+    long long tiles = 0;
+    for (int mt = member; mt < m_tiles; mt += members) {
+      ++tiles;
+      mbar_wait(tempty(acc), acc_phase ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem_base + kColAcc + (uint32_t)acc * 128u;
+      for (int kb = 0; kb < KB; kb += KPS) {
+        mbar_wait(full(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint32_t a_t = tmem_base + kColW + (uint32_t)((kb + j) * (BK / 16) + kk) * 8u;
+              const uint64_t bd = make_desc(base + stage * kStage + j * kTileBytes + kk * 32);
+              tc_mma_ts(d, a_t, bd, idesc, (kb + j > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(empty(stage));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) tc_commit(tfull(acc));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (leader) {
+      p.clocks[2 * blockIdx.x] = clock64() - t0;
+      p.clocks[2 * blockIdx.x + 1] = tiles * (long long)KB * kTileBytes;
+    }
+  } else {
+    // ---------------- weight loaders, then epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
+    const int q = warp & 3;
+    const int n_local = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    {  // W row n -> TMEM lane n_local, columns kColW + k / 2: 16 bf16 (8 columns) per store
+      const uint4* wrow = reinterpret_cast<const uint4*>(p.w + (size_t)(nb * 128 + n_local) * K);
+#pragma unroll 4
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint4 v0 = wrow[2 * ks], v1 = wrow[2 * ks + 1];
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(lane_base + kColW + (uint32_t)ks * 8u), "r"(v0.x),
+                     "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w)
+                     : "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(wready);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int mt = member; mt < m_tiles; mt += members) {
+      mbar_wait(tfull(acc), acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t = lane_base + kColAcc + (uint32_t)acc * 128u;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {  // 32 activation rows at a time
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+            "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+              "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+              "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(t + 32u * c));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int ncol = nb * 128 + n_local;
+        if (p.validate) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) p.out[(size_t)(mt * BM + c * 32 + j) * N + ncol] = __uint_as_float(r[j]);
+        } else {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(r[j]);
+          p.out[(size_t)(mt * 4 + c) * N + ncol] = s;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer) {
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {inner * 2};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  return ((EncodeTiledFn)fp)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int STAGES, int KPS>
+static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, long long* dClk, int M, int validate, const std::vector<float>* ref) {
+  CUtensorMap map;
+  if (!make_map(&map, dA, K, (uint64_t)M)) { printf("tensor map failed\n"); return false; }
+  const size_t smem = (size_t)STAGES * KPS * kTileBytes + (2 * STAGES + 8) * 8 + 1024;
+  auto kern = tmemw_kernel<STAGES, KPS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  Params p = {dW, dOut, dClk, M, validate};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e9f;
+  for (int rep = 0; rep < (validate ? 1 : 5); ++rep) {
+    cudaEventRecord(e0);
+    kern<<<147, 192, smem>>>(map, p);
+    cudaEventRecord(e1);
+    const cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { printf("stages %d kps %d: %s\n", STAGES, KPS, cudaGetErrorString(err)); return false; }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  if (validate) {
+    std::vector<float> h((size_t)M * N);
+    cudaMemcpy(h.data(), dOut, h.size() * 4, cudaMemcpyDeviceToHost);
+    double num = 0, den = 0, worst = 0;
+    for (size_t i = 0; i < h.size(); ++i) {
+      const double d = (double)h[i] - (*ref)[i];
+      num += d * d; den += (double)(*ref)[i] * (*ref)[i];
+      if (fabs(d) > worst) worst = fabs(d);
+    }
+    printf("validate M=%d stages=%d kps=%d: rel err %.3e, worst abs %.3e -> %s\n", M, STAGES, KPS, sqrt(num / den), worst, sqrt(num / den) < 1e-5 ? "OK" : "MISMATCH");
+    return sqrt(num / den) < 1e-5;
+  }
+  long long h[2 * 147];
+  cudaMemcpy(h, dClk, sizeof(h), cudaMemcpyDeviceToHost);
+  double cyc = 0, bytes = 0;
+  for (int b = 0; b < 147; ++b) { cyc += (double)h[2 * b]; bytes += (double)h[2 * b + 1]; }
+  const double tiles_per_cta = bytes / 147 / (KB * kTileBytes);
+  printf("M=%d ring %3d KB (stages %2d x %d k-blocks): %7.2f us | %6.0f cycles per tile (MMA floor %d) | %5.1f B/clk/SM delivered | %.0f TFLOP/s\n", M,
+         STAGES * KPS * 16, STAGES, KPS, best * 1e3, cyc / 147 / tiles_per_cta, KB * 4 * 64, bytes / cyc, 2.0 * M * N * K / (best * 1e-3) / 1e12);
+  return true;
+}
+
+int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  const int Mbig = 66560, Msmall = 1024;
+  std::vector<__nv_bfloat16> hA((size_t)Mbig * K), hW((size_t)N * K);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((int)(s >> 20) % 17 - 8) / 8.0f; };  // exact in bf16
+  for (auto& v : hA) v = __float2bfloat16(rnd());
+  for (auto& v : hW) v = __float2bfloat16(rnd());
+  __nv_bfloat16 *dA, *dW;
+  float* dOut;
+  long long* dClk;
+  cudaMalloc(&dA, hA.size() * 2);
+  cudaMalloc(&dW, hW.size() * 2);
+  cudaMalloc(&dOut, (size_t)Msmall * N * 4 > (size_t)(Mbig / 32) * N * 4 ? (size_t)Msmall * N * 4 : (size_t)(Mbig / 32) * N * 4);
+  cudaMalloc(&dClk, sizeof(long long) * 2 * 160);
+  cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice);
+  std::vector<float> ref((size_t)Msmall * N);
+  for (int m = 0; m < Msmall; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += __bfloat162float(hA[(size_t)m * K + k]) * __bfloat162float(hW[(size_t)n * K + k]);
+      ref[(size_t)m * N + n] = acc;
+    }
+  if (!run<6, 1>(dA, dW, dOut, dClk, Msmall, 1, &ref)) return 1;
+  run<6, 1>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   //  96 KB ring: what the shared-memory-resident kernel has today
+  run<12, 1>(dA, dW, dOut, dClk, Mbig, 0, nullptr);  // 192 KB ring
+  run<6, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   // 192 KB ring, half the waits / commits per MMA
+  run<3, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   //  96 KB ring, half the waits / commits
+  return 0;
+}
