@@ -73,7 +73,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 struct Params {
   const __nv_bfloat16* w;  // [N][K]
   float* out;              // validation: [M][N] fp32; timing: [M / 32][N] partial sums
-  long long* clocks;       // per CTA: cycles of the MMA issuer, bytes streamed
+  long long* clocks;       // per CTA: cycles of the MMA issuer, bytes streamed, prologue cycles (kernel entry -> first MMA may issue)
+  __nv_bfloat16* out_t;    // timing with stores: out^T [N][M] bf16 (the un-transposed epilogue: realistic output traffic, wrong layout)
   int M, validate;
 };
 
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
   const uint32_t wready = bars + 8u * (2 * STAGES + 4);
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_entry = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -166,8 +168,9 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (leader) {
-      p.clocks[2 * blockIdx.x] = clock64() - t0;
-      p.clocks[2 * blockIdx.x + 1] = tiles * (long long)KB * kTileBytes;
+      p.clocks[4 * blockIdx.x] = clock64() - t0;
+      p.clocks[4 * blockIdx.x + 1] = tiles * (long long)KB * kTileBytes;
+      p.clocks[4 * blockIdx.x + 2] = t0 - t_entry;
     }
   } else {
     // ---------------- weight loaders, then epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
@@ -209,6 +212,16 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
         if (p.validate) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) p.out[(size_t)(mt * BM + c * 32 + j) * N + ncol] = __uint_as_float(r[j]);
+        } else if (p.out_t != nullptr) {
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out_t + (size_t)ncol * p.M + mt * BM + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         } else {
           float s = 0.f;
 #pragma unroll
@@ -224,6 +237,7 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) p.clocks[4 * blockIdx.x + 3] = clock64() - t_entry;  // CTA lifetime
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -246,13 +260,14 @@ static bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t
 }
 
 template <int STAGES, int KPS>
-static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, long long* dClk, int M, int validate, const std::vector<float>* ref) {
+static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, long long* dClk, int M, int validate, const std::vector<float>* ref,
+                __nv_bfloat16* dOutT = nullptr) {
   CUtensorMap map;
   if (!make_map(&map, dA, K, (uint64_t)M)) { printf("tensor map failed\n"); return false; }
   const size_t smem = (size_t)STAGES * KPS * kTileBytes + (2 * STAGES + 8) * 8 + 1024;
   auto kern = tmemw_kernel<STAGES, KPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  Params p = {dW, dOut, dClk, M, validate};
+  Params p = {dW, dOut, dClk, dOutT, M, validate};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -279,13 +294,14 @@ static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, l
     printf("validate M=%d stages=%d kps=%d: rel err %.3e, worst abs %.3e -> %s\n", M, STAGES, KPS, sqrt(num / den), worst, sqrt(num / den) < 1e-5 ? "OK" : "MISMATCH");
     return sqrt(num / den) < 1e-5;
   }
-  long long h[2 * 147];
+  long long h[4 * 147];
   cudaMemcpy(h, dClk, sizeof(h), cudaMemcpyDeviceToHost);
-  double cyc = 0, bytes = 0;
-  for (int b = 0; b < 147; ++b) { cyc += (double)h[2 * b]; bytes += (double)h[2 * b + 1]; }
+  double cyc = 0, bytes = 0, pro = 0, life = 0;
+  for (int b = 0; b < 147; ++b) { cyc += (double)h[4 * b]; bytes += (double)h[4 * b + 1]; pro += (double)h[4 * b + 2]; life += (double)h[4 * b + 3]; }
   const double tiles_per_cta = bytes / 147 / (KB * kTileBytes);
-  printf("M=%d ring %3d KB (stages %2d x %d k-blocks): %7.2f us | %6.0f cycles per tile (MMA floor %d) | %5.1f B/clk/SM delivered | %.0f TFLOP/s\n", M,
-         STAGES * KPS * 16, STAGES, KPS, best * 1e3, cyc / 147 / tiles_per_cta, KB * 4 * 64, bytes / cyc, 2.0 * M * N * K / (best * 1e-3) / 1e12);
+  printf("M=%d ring %3d KB (stages %2d x %d) %s: %6.2f us | %5.0f cyc/tile (floor %d) %4.1f B/clk/SM | per CTA: prologue %5.0f, issue loop %6.0f, lifetime %6.0f cyc | %.0f TFLOP/s\n",
+         M, STAGES * KPS * 16, STAGES, KPS, dOutT ? "bf16 out^T stores" : "token epilogue   ", best * 1e3, cyc / 147 / tiles_per_cta, KB * 4 * 64, bytes / cyc,
+         pro / 147, cyc / 147, life / 147, 2.0 * M * N * K / (best * 1e-3) / 1e12);
   return true;
 }
 
@@ -303,7 +319,9 @@ int main() {
   cudaMalloc(&dA, hA.size() * 2);
   cudaMalloc(&dW, hW.size() * 2);
   cudaMalloc(&dOut, (size_t)Msmall * N * 4 > (size_t)(Mbig / 32) * N * 4 ? (size_t)Msmall * N * 4 : (size_t)(Mbig / 32) * N * 4);
-  cudaMalloc(&dClk, sizeof(long long) * 2 * 160);
+  cudaMalloc(&dClk, sizeof(long long) * 4 * 160);
+  __nv_bfloat16* dOutT;
+  cudaMalloc(&dOutT, (size_t)N * Mbig * 2);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice);
   std::vector<float> ref((size_t)Msmall * N);
@@ -318,5 +336,7 @@ int main() {
   run<12, 1>(dA, dW, dOut, dClk, Mbig, 0, nullptr);  // 192 KB ring
   run<6, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   // 192 KB ring, half the waits / commits per MMA
   run<3, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   //  96 KB ring, half the waits / commits
+  run<6, 1>(dA, dW, dOut, dClk, Mbig, 0, nullptr, dOutT);  // with 51 MB of (untransposed) bf16 output stores
+  run<6, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr, dOutT);
   return 0;
 }
