@@ -63,6 +63,16 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]  (the form the production kernel uses)
+__device__ __forceinline__ void tc_mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major, 128-byte swizzle: LBO unused (16 B), SBO = 1024 B (eight 128-byte rows), version 1, swizzle mode 2 (128B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
@@ -78,12 +88,14 @@ struct Params {
   int M, validate;
 };
 
-template <int STAGES, int KPS>
-__global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ CUtensorMap map_a, const Params p) {
+// TS = true: weight block in tensor memory (TMEM-A MMA); false: weight block in shared memory behind the ring (both operands by descriptor)
+template <int STAGES, int KPS, bool TS>
+__global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t kStage = KPS * kTileBytes;
-  const uint32_t bars = base + STAGES * kStage;  // full[STAGES] empty[STAGES] tfull[2] tempty[2] wready
+  const uint32_t wsm = base + STAGES * kStage;                        // !TS: the 6 weight k-blocks (96 KB)
+  const uint32_t bars = wsm + (TS ? 0u : (uint32_t)KB * kTileBytes);  // full[STAGES] empty[STAGES] tfull[2] tempty[2] wready
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull = [&](int a) { return bars + 8u * (2 * STAGES + a); };
@@ -96,7 +108,7 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
-    mbar_init(wready, 4);
+    mbar_init(wready, TS ? 4 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -119,6 +131,11 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    if (!TS && leader) {
+      mbar_arrive_expect_tx(wready, KB * kTileBytes);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(wsm + kb * kTileBytes, &map_w, wready, kb * BK, nb * 128);
+    }
+    __syncwarp();
     for (int mt = member; mt < m_tiles; mt += members) {
       for (int kb = 0; kb < KB; kb += KPS) {
         mbar_wait(empty(stage), phase ^ 1u);
@@ -155,7 +172,8 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
             for (int kk = 0; kk < BK / 16; ++kk) {
               const uint32_t a_t = tmem_base + kColW + (uint32_t)((kb + j) * (BK / 16) + kk) * 8u;
               const uint64_t bd = make_desc(base + stage * kStage + j * kTileBytes + kk * 32);
-              tc_mma_ts(d, a_t, bd, idesc, (kb + j > 0 || kk > 0) ? 1u : 0u);
+              if (TS) tc_mma_ts(d, a_t, bd, idesc, (kb + j > 0 || kk > 0) ? 1u : 0u);
+              else tc_mma_ss(d, make_desc(wsm + (kb + j) * kTileBytes + kk * 32), bd, idesc, (kb + j > 0 || kk > 0) ? 1u : 0u);
             }
           }
           tc_commit(empty(stage));
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(192, 1) tmemw_kernel(const __grid_constant__ C
     const int q = warp & 3;
     const int n_local = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    {  // W row n -> TMEM lane n_local, columns kColW + k / 2: 16 bf16 (8 columns) per store
+    if (TS) {  // W row n -> TMEM lane n_local, columns kColW + k / 2: 16 bf16 (8 columns) per store
       const uint4* wrow = reinterpret_cast<const uint4*>(p.w + (size_t)(nb * 128 + n_local) * K);
 #pragma unroll 4
       for (int ks = 0; ks < K / 16; ++ks) {
@@ -259,13 +277,15 @@ static bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int STAGES, int KPS>
+template <int STAGES, int KPS, bool TS = true>
 static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, long long* dClk, int M, int validate, const std::vector<float>* ref,
                 __nv_bfloat16* dOutT = nullptr) {
   CUtensorMap map;
   if (!make_map(&map, dA, K, (uint64_t)M)) { printf("tensor map failed\n"); return false; }
-  const size_t smem = (size_t)STAGES * KPS * kTileBytes + (2 * STAGES + 8) * 8 + 1024;
-  auto kern = tmemw_kernel<STAGES, KPS>;
+  CUtensorMap map_w;
+  if (!make_map(&map_w, dW, K, (uint64_t)N)) { printf("tensor map failed\n"); return false; }
+  const size_t smem = (size_t)STAGES * KPS * kTileBytes + (TS ? 0 : KB * kTileBytes) + (2 * STAGES + 8) * 8 + 1024;
+  auto kern = tmemw_kernel<STAGES, KPS, TS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   Params p = {dW, dOut, dClk, dOutT, M, validate};
   cudaEvent_t e0, e1;
@@ -274,7 +294,7 @@ static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, l
   float best = 1e9f;
   for (int rep = 0; rep < (validate ? 1 : 5); ++rep) {
     cudaEventRecord(e0);
-    kern<<<147, 192, smem>>>(map, p);
+    kern<<<147, 192, smem>>>(map, map_w, p);
     cudaEventRecord(e1);
     const cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("stages %d kps %d: %s\n", STAGES, KPS, cudaGetErrorString(err)); return false; }
@@ -300,7 +320,7 @@ static bool run(const __nv_bfloat16* dA, const __nv_bfloat16* dW, float* dOut, l
   for (int b = 0; b < 147; ++b) { cyc += (double)h[4 * b]; bytes += (double)h[4 * b + 1]; pro += (double)h[4 * b + 2]; life += (double)h[4 * b + 3]; }
   const double tiles_per_cta = bytes / 147 / (KB * kTileBytes);
   printf("M=%d ring %3d KB (stages %2d x %d) %s: %6.2f us | %5.0f cyc/tile (floor %d) %4.1f B/clk/SM | per CTA: prologue %5.0f, issue loop %6.0f, lifetime %6.0f cyc | %.0f TFLOP/s\n",
-         M, STAGES * KPS * 16, STAGES, KPS, dOutT ? "bf16 out^T stores" : "token epilogue   ", best * 1e3, cyc / 147 / tiles_per_cta, KB * 4 * 64, bytes / cyc,
+         M, STAGES * KPS * 16, STAGES, KPS, TS ? (dOutT ? "W in TMEM, bf16 out^T stores" : "W in TMEM, token epilogue   ") : "W in smem, token epilogue   ", best * 1e3, cyc / 147 / tiles_per_cta, KB * 4 * 64, bytes / cyc,
          pro / 147, cyc / 147, life / 147, 2.0 * M * N * K / (best * 1e-3) / 1e12);
   return true;
 }
@@ -337,6 +357,9 @@ int main() {
   run<6, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   // 192 KB ring, half the waits / commits per MMA
   run<3, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr);   //  96 KB ring, half the waits / commits
   run<6, 1>(dA, dW, dOut, dClk, Mbig, 0, nullptr, dOutT);  // with 51 MB of (untransposed) bf16 output stores
-  run<6, 2>(dA, dW, dOut, dClk, Mbig, 0, nullptr, dOutT);
+  // the same single-stream loop with the weight block in shared memory (two-descriptor MMA), 96 KB ring: isolates TMEM-A vs smem-A
+  if (!run<6, 1, false>(dA, dW, dOut, dClk, Msmall, 1, &ref)) return 1;
+  run<6, 1, false>(dA, dW, dOut, dClk, Mbig, 0, nullptr);
+  run<3, 2, false>(dA, dW, dOut, dClk, Mbig, 0, nullptr);
   return 0;
 }
