@@ -869,6 +869,11 @@ static bool use_pair(const TcArgs& a, int M) {
 //   <NS, STAGES, KPS> dual stream: wgrad 2 x 3 x 32 KB;  resident 2 x 3 x 16 KB (2 x 2 with a pre-activation slab);
 //   streaming 2 x 3 x 32 KB (2 x 2 x 32 KB).   g_tc_streams = 1 (tools) selects the single-stream plans.
 static int g_tc_streams = 2;
+// VITB_GEMM_TS=1: route the resident-weight shapes to the experimental TMEM-resident kernel (gemm_ts.cu); default off
+static bool ts_enabled() {
+  static const bool on = getenv("VITB_GEMM_TS") && atoi(getenv("VITB_GEMM_TS")) != 0;
+  return on;
+}
 static int g_tc_wgrad_bn = 192;  // wgrad tile width; tools can force 128
 
 template <int BN, bool A_MN, bool B_MN>
@@ -1014,6 +1019,8 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
   EpiParams e = {};
   e.mode = EPI_FWD; e.gelu = (flags & VITB_GEMM_GELU) ? 1 : 0; e.out_f32 = (flags & VITB_GEMM_OUT_F32) ? 1 : 0;
   e.bias = bias; e.residual = residual; e.out = c; e.preact = preact; e.ldc = N;
+  if (dt == VITB_BF16 && !e.out_f32 && ts_enabled() && ts_gemm_ok(M, N, K))  // experimental: weight block in tensor memory
+    return ts_gemm_launch(EPI_FWD, a, w, bias, residual, c, preact, M, N, K, e.gelu, false, st);
   if (dt == VITB_BF16 && tc_shape_ok(M, N, K) && !e.out_f32) {
     TcMaps m;
     if (make_map(&m.a, a, K, M, K, BM)) return -1;
@@ -1049,6 +1056,8 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
   EpiParams e = {};
   e.mode = EPI_DGRAD; e.out = dx; e.aux = z; e.ldc = K;
   // GEMM view: C[M, K] = dY[M, N] (K-major, reduction N) x W[N, K] (MN-major: reduction over rows)
+  if (dt == VITB_BF16 && !dy_f32 && ts_enabled() && ts_gemm_ok(M, K, N))
+    return ts_gemm_launch(EPI_DGRAD, dy, w, nullptr, z, dx, nullptr, M, K, N, 0, true, st);
   if (dt == VITB_BF16 && !dy_f32 && tc_shape_ok(M, K, N)) {
     TcMaps m;
     if (make_map(&m.a, dy, N, M, N, BM)) return -1;
