@@ -12,8 +12,11 @@ fp32 accumulation, per-GPU batch 1024 (weak scaling: global batch = 1024 * N; 81
 
 Prints ONE JSON line (rank 0).  `value` = steady-state img/s with the batch resident in HBM; `e2e` = the same
 through the public API from pinned HOST buffers (H2D of every batch and D2H of every loss inside the timed region).
-`--impl reference` times the CPU restatement of the reference (oracle/, "port": /root/reference is not on the GPU
-box) on the host cores over a bounded sample.
+`--impl reference` times the reference's own modules (oracle/_ref, a verbatim copy made by oracle/make_ref.py where
+/root/reference is mounted; kind "reference") or, without that copy, the CPU restatement (oracle/, kind "port") on the
+host cores over a bounded sample.  `--impl eager` times the same PyTorch modules on the B200 (eager ATen / cuBLAS: fp32
+with matmul precision "medium" as main.py:173, bf16 and fp16 autocast as main.py:58, and torch.compile) — the
+kernel-level bar the hand-written kernels have to beat, since the reference ships no GPU code of its own.
 """
 from __future__ import annotations
 
@@ -113,55 +116,148 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port (same arithmetic as the reference, torch fp32 on host cores)
 # ---------------------------------------------------------------------------------------------
-def cpu_port_images_per_s(batch: int, steps: int, warmup: int):
+def torch_reference_model():
+    """(model, criterion, kind): the reference's own vit.ViT + LabelSmoothingCrossEntropyLoss when a copy of the reference is
+    reachable (oracle/_ref on the GPU box, /root/reference in the authoring container; kind "reference"), else the oracle's
+    restatement with the same state_dict names (kind "port").  Same construction arguments as utils.get_model (utils.py:71-83)."""
     import torch
     import oracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    from oracle import ref_shim
+    torch.manual_seed(2045)  # main.py:150
+    if ref_shim.reference_available():
+        ref_vit, _, ref_crit = ref_shim.import_reference()
+        model = ref_vit.ViT(3, MODEL["num_classes"], img_size=MODEL["img_size"], patch=MODEL["patch"], dropout=0.0, mlp_hidden=MODEL["mlp_hidden"],
+                            num_layers=MODEL["num_layers"], hidden=MODEL["hidden"], head=MODEL["head"], is_cls_token=True)
+        return model, ref_crit.LabelSmoothingCrossEntropyLoss(MODEL["num_classes"], smoothing=SMOOTHING), "reference"
     cfg = oracle.ViTConfig(**MODEL)
     model = oracle.OracleViT(cfg, seed=0)
+    return model, (lambda out, y: oracle.ls_ce_loss(out, y, cfg.num_classes, SMOOTHING)), "port"
+
+
+def cpu_port_images_per_s(batch: int, steps: int, warmup: int):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, crit, kind = torch_reference_model()
     opt = torch.optim.Adam(model.parameters(), **ADAM)
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(batch, 3, 32, 32, generator=g)
-    y = torch.randint(0, cfg.num_classes, (batch,), generator=g)
+    y = torch.randint(0, MODEL["num_classes"], (batch,), generator=g)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss = oracle.ls_ce_loss(model(x), y, cfg.num_classes, SMOOTHING)
+        loss = crit(model(x), y)
         loss.backward()
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return batch * len(times) / total, cores, 1e3 * total / len(times)
+    return batch * len(times) / total, cores, 1e3 * total / len(times), kind
+
+
+def pctl(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = (len(xs) - 1) * q
+    lo, hi = int(k), min(int(k) + 1, len(xs) - 1)
+    return xs[lo] + (xs[hi] - xs[lo]) * (k - lo)
+
+
+def eager_gpu_images_per_s(mode: str, batch: int, steps: int, warmup: int, compile_: bool = False):
+    """The PyTorch modules of the reference path on cuda:0, timed per step with CUDA events.  mode: "fp32-medium" (main.py:173),
+    "bf16-autocast", "fp16-autocast" (main.py:58 "16-mixed": autocast + GradScaler)."""
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.set_float32_matmul_precision("medium")  # main.py:139-144, 173
+    model, crit, kind = torch_reference_model()
+    model = model.to(dev)
+    fwd = torch.compile(model) if compile_ else model
+    opt = torch.optim.Adam(model.parameters(), **ADAM)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 3, 32, 32, generator=g).to(dev)
+    y = torch.randint(0, MODEL["num_classes"], (batch,), generator=g).to(dev)
+    scaler = torch.amp.GradScaler("cuda") if mode == "fp16-autocast" else None
+    ac = {"fp32-medium": None, "bf16-autocast": torch.bfloat16, "fp16-autocast": torch.float16}[mode]
+    ev = []
+    for i in range(warmup + steps):
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        opt.zero_grad(set_to_none=True)
+        if ac is None:
+            loss = crit(fwd(x), y)
+        else:
+            with torch.autocast("cuda", dtype=ac):
+                loss = crit(fwd(x), y)
+        if scaler is not None:
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        else:
+            loss.backward()
+            opt.step()
+        e.record()
+        if i >= warmup:
+            ev.append((s, e))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    tot = sum(ms)
+    return {"mode": mode + ("+compile" if compile_ else ""), "img_s": round(batch * len(ms) / (tot * 1e-3), 1), "ms_per_step": round(tot / len(ms), 4),
+            "p10_ms": round(pctl(ms, 0.1), 4), "p50_ms": round(pctl(ms, 0.5), 4), "p90_ms": round(pctl(ms, 0.9), 4), "batch": batch, "kind": kind,
+            "final_loss": float(loss)}
+
+
+def run_eager(args):
+    """Extra arm (not part of the driver contract): the reference path in PyTorch eager on ONE B200."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    res = []
+    for mode, comp in (("fp32-medium", False), ("bf16-autocast", False), ("fp16-autocast", False), ("bf16-autocast", True)):
+        try:
+            res.append(eager_gpu_images_per_s(mode, args.batch, args.steps, max(3, args.warmup), comp))
+        except Exception as ex:  # torch.compile needs a working inductor tool chain on the box
+            res.append({"mode": mode + ("+compile" if comp else ""), "error": f"{type(ex).__name__}: {str(ex)[:200]}"})
+    best = max((r for r in res if "img_s" in r), key=lambda r: r["img_s"])
+    out = {"impl": "eager", "metric": METRIC, "value": best["img_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": best["mode"],
+           "data": "synthetic", "config": {"workload": workload_name(1, args.batch), "what": "PyTorch eager (ATen / cuBLAS) on the same B200"},
+           "modes": res}
+    print(json.dumps(out), flush=True)
+    return 0
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    batch = 128  # bounded sample of the 1024-image step: the CPU path is ~1e3x slower
-    v, cores, ms = cpu_port_images_per_s(batch, max(1, args.steps), max(1, min(args.warmup, 2)))
+    batch = min(128, args.batch)  # bounded sample of the step (the reference's own default batch, main.py:43): the CPU path is ~1e3x slower
+    v, cores, ms, kind = cpu_port_images_per_s(batch, max(1, args.steps), max(1, min(args.warmup, 2)))
+    what = "the reference's own vit.ViT / criterion" if kind == "reference" else "oracle port of the reference"
     out = {
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "sample": f"{batch}-image steps on CPU"},
-        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of batch {batch} (oracle port of the reference, torch fp32, {cores} threads)"},
+        "config": {"workload": model_name(), "per_step_batch": batch,
+                   "sample": f"every step is a {batch}-image sample of the {args.batch}-image per-GPU batch, fp32 on {cores} host threads (one CPU process)"},
+        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps of batch {batch} ({what}, torch fp32, {cores} threads)"},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
     return 0
 
 
-def workload_name(n, batch=None):
-    b = PER_GPU_BATCH if batch is None else batch
+def model_name():
     T = MODEL["patch"] ** 2 + 1
     K = 3 * (MODEL["img_size"] // MODEL["patch"]) ** 2
     return (f"ViT-CIFAR {MODEL['num_layers']}L/{MODEL['hidden']}h/{MODEL['head']}heads/MLP{MODEL['mlp_hidden']} patch={MODEL['patch']} "
-            f"(T={T},K={K}) C={MODEL['num_classes']}, per-GPU batch {b} (global {b * n}), LS 0.1, Adam, bf16")
+            f"(T={T},K={K}) C={MODEL['num_classes']}, LS 0.1, Adam")
+
+
+def workload_name(n, batch=None):
+    b = PER_GPU_BATCH if batch is None else batch
+    return f"{model_name()}, per-GPU batch {b} (global {b * n}), bf16"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -264,6 +360,86 @@ eng_numel = 0
 
 
 # ---------------------------------------------------------------------------------------------
+# data-parallel numerics (Lightning DDP semantics, main.py:220-231: every replica applies the MEAN of the ranks' gradients)
+# ---------------------------------------------------------------------------------------------
+def dp_verify(eng, vb, dist, pg, dev, rank, world):
+    """(1) the replicas of the benchmarked engine are bit-identical after the timed loops; (2) a small fp32 model: one step of
+    the data-parallel engine on rank-specific batches equals the oracle's Adam step on the gradient of the GLOBAL batch (= the
+    mean of the ranks' gradients); (3) the benchmark model: two steps of the fused peer-memory path against NCCL all-reduce +
+    the Adam kernel from the same weights and batches.  Returns a dict for `config`; `ok` False makes bench.py exit non-zero."""
+    import torch
+    res = {}
+    # (1) replica identity: compare every rank's parameters with rank 0's
+    mine = eng.P[:eng.n].clone()
+    ref = mine.clone()
+    dist.broadcast(ref, src=0, group=pg)
+    same = torch.tensor([1 if torch.equal(mine, ref) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN, group=pg)
+    res["replicas_bit_identical"] = bool(same.item())
+    # (2) oracle check on a small model (fp32 check mode, rank-specific batches)
+    import oracle
+    cfg = oracle.ViTConfig(num_classes=10, img_size=32, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+    Bs = 4
+    vb.set_precision("fp32")
+    m = vb.ViT(3, 10, img_size=32, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+    m.load_state_dict(oracle.init_params(cfg, 0))
+    m = m.to(dev)
+    e2 = vb.TrainEngine(m, Bs, smoothing=SMOOTHING, process_group=pg, use_graph=False, **ADAM)
+    xs, ys = oracle.hash_inputs(cfg, Bs * world, seed=3)
+    e2.step(xs[rank * Bs:(rank + 1) * Bs].to(dev), ys[rank * Bs:(rank + 1) * Bs].to(dev))
+    torch.cuda.synchronize()
+    err = 0.0
+    if rank == 0:
+        params = oracle.init_params(cfg, 0)
+        p0 = {k: v.clone() for k, v in params.items()}
+        _, _, grads = oracle.train_step(params, xs, ys, cfg, SMOOTHING)  # mean over the global batch = mean of the rank means
+        mo = {k: torch.zeros_like(v) for k, v in params.items()}
+        vo = {k: torch.zeros_like(v) for k, v in params.items()}
+        oracle.adam_step(params, grads, mo, vo, 1, ADAM["lr"], ADAM["betas"], ADAM["eps"], ADAM["weight_decay"])
+        sd = m.state_dict()
+        num = den = 0.0
+        for k in params:
+            if "Wk.bias" in k:  # analytically zero gradient: Adam turns its rounding noise into +-lr updates
+                continue
+            num += float(((sd[k].cpu().double() - p0[k].double()) - (params[k].double() - p0[k].double())).pow(2).sum())
+            den += float((params[k].double() - p0[k].double()).pow(2).sum())
+        err = (num / max(den, 1e-300)) ** 0.5
+    t = torch.tensor([err], device=dev, dtype=torch.float64)
+    dist.broadcast(t, src=0, group=pg)
+    res["adam_update_vs_oracle_global_batch_rel"] = float(t.item())
+    vb.set_precision("bf16")
+    # (3) fused peer-memory step vs NCCL all-reduce + Adam kernel on the benchmark model
+    def two_steps(mode):
+        prev = os.environ.get("VITB_DP_MODE")
+        os.environ["VITB_DP_MODE"] = mode
+        try:
+            torch.manual_seed(2045)
+            mm = vb.ViT(3, MODEL["num_classes"], img_size=32, patch=MODEL["patch"], dropout=0.0, num_layers=MODEL["num_layers"],
+                        hidden=MODEL["hidden"], mlp_hidden=MODEL["mlp_hidden"], head=MODEL["head"]).to(dev)
+            ee = vb.TrainEngine(mm, 64, smoothing=SMOOTHING, process_group=pg, use_graph=False, **ADAM)
+            for st in range(2):
+                g = torch.Generator().manual_seed(777 + 10 * st + rank)
+                ee.step(torch.randn(64, 3, 32, 32, generator=g).to(dev), torch.randint(0, MODEL["num_classes"], (64,), generator=g).to(dev))
+            torch.cuda.synchronize()
+            return ee.P[:ee.n].clone(), ee._dp_mode
+        finally:
+            if prev is None:
+                os.environ.pop("VITB_DP_MODE", None)
+            else:
+                os.environ["VITB_DP_MODE"] = prev
+    p_nccl, _ = two_steps("single")
+    p_fused, mode_used = two_steps("fused")
+    d = ((p_fused - p_nccl).double().norm() / p_nccl.double().norm()).item()
+    t = torch.tensor([d], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+    res["fused_vs_nccl_params_rel_after_2_steps"] = float(t.item())
+    res["fused_mode_active"] = mode_used == "fused"
+    res["ok"] = bool(res["replicas_bit_identical"] and res["adam_update_vs_oracle_global_batch_rel"] < 1e-3
+                     and res["fused_vs_nccl_params_rel_after_2_steps"] < 1e-3)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
 def run_ours(args):
     global eng_numel
     import torch
@@ -340,6 +516,16 @@ def run_ours(args):
         loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)
     ms_e2e = timed(e2e_step, args.steps, W)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- per-step distribution (median + p10/p90): one event pair per step, outside the contract's timed regions
+    evs = []
+    for i in range(max(args.steps, 20)):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(); eng.step(); e_.record()
+        evs.append((s_, e_))
+    torch.cuda.synchronize()
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    step_ms = {"p10": round(pctl(per_step, 0.1), 4), "p50": round(pctl(per_step, 0.5), 4), "p90": round(pctl(per_step, 0.9), 4), "n": len(per_step)}
+    dp_check = dp_verify(eng, vb, dist, pg, dev, rank, world) if world > 1 else None
     final_loss = float(loss_host[(W + args.steps - 1) % loss_host.numel()])
 
     imgs = B * world * args.steps
@@ -350,6 +536,9 @@ def run_ours(args):
                                L=MODEL["num_layers"], C=MODEL["num_classes"])
 
     # ---- per-kernel probe + roofline of the dominant kernel (rank 0, after the timed regions) ----
+    act_bytes = eng.activation_bytes()
+    launches_per_step = int(eng.launches_per_step)
+    dp_mode = eng._dp_mode
     table = probe_kernels(eng, steps=3)
     roof = None
     for row in table:
@@ -358,16 +547,24 @@ def run_ours(args):
             roof["share_of_step"] = row["ms_per_step"] / sum(r["ms_per_step"] for r in table)
             break
     cpu = None
+    eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, ms = cpu_port_images_per_s(128, 3, 1)
-        cpu = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 steps of batch 128 of the same model (oracle port of the reference, torch fp32, {cores} threads)"}
+        v, cores, ms, kind = cpu_port_images_per_s(min(128, B), 3, 1)
+        what = "the reference's own vit.ViT / criterion" if kind == "reference" else "oracle port of the reference"
+        cpu = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"3 steps of batch {min(128, B)} of the same model ({what}, torch fp32, {cores} threads)"}
+        try:  # the kernel-level bar: the same PyTorch modules on this GPU (eager ATen / cuBLAS under bf16 autocast)
+            del eng
+            torch.cuda.empty_cache()
+            eager = eager_gpu_images_per_s("bf16-autocast", B, 10, 3)
+        except Exception as ex:
+            eager = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     if world > 1:
         dist.barrier()
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_dev / args.steps, 4), "step_ms": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world, B), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
                        "l2": "working set per step (>4 GB of activations) exceeds the 126 MB L2; no flush needed",
@@ -375,18 +572,20 @@ def run_ours(args):
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                              {"fused": "one peer-memory kernel: barrier + reduce-scatter (P2P loads) + Adam + all-gather (P2P stores)",
                                               "single": "NCCL all-reduce of the flat gradient buffer, then the Adam kernel",
-                                              "overlap": "NCCL all-reduce per layer bucket on a side stream, then the Adam kernel"}.get(eng._dp_mode, eng._dp_mode))},
+                                              "overlap": "NCCL all-reduce per layer bucket on a side stream, then the Adam kernel"}.get(dp_mode, dp_mode))},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": B * (3 * 32 * 32 * 4 + 8) + 32, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(eng.launches_per_step * args.steps),
-            "launches_per_step": int(eng.launches_per_step),
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": launches_per_step,
             "clocks": clocks,
             "tensor_pipe_frac": {"of_burst": value * fl / world / 1e12 / pk["tf_burst"], "of_sustained": value * fl / world / 1e12 / pk["tf_sust"],
                                  "train_flop_per_img": fl, "peaks": pk["src"]},
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
+            "dp_check": dp_check,
             "final_loss": final_loss,
-            "activation_bytes": eng.activation_bytes(),
+            "activation_bytes": act_bytes,
         }
         print(json.dumps(out), flush=True)
         if args.kernel_table:
@@ -395,6 +594,9 @@ def run_ours(args):
                 r = kernel_roofline(row, pk, B, model.num_tokens, model.hidden)
                 row["roofline"] = r
             json.dump({"ms_per_step_graph": ms_dev / args.steps, "img_per_s": value, "kernels": table}, open(args.kernel_table, "w"), indent=1)
+    if world > 1 and dp_check is not None and not dp_check["ok"]:
+        sys.stdout.flush()
+        os._exit(3)  # a data-parallel numeric mismatch is a failed run, not a benchmark line
     if world > 1:
         # All ranks are done (barrier), results are printed.  Tearing NCCL down while captured CUDA graphs still reference
         # its communicator hung on B200 (observed at N=2), so leave without the interpreter/NCCL teardown.
@@ -411,7 +613,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's, 1024 for the headline)")
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS), help="model shape (default: BASELINE.json's headline configuration)")
     ap.add_argument("--no-graph", action="store_true")
@@ -424,6 +626,8 @@ def main():
         args.batch = PER_GPU_BATCH
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager":
+        return run_eager(args)
     return run_ours(args)
 
 

@@ -176,6 +176,14 @@ int vitb_ls_ce_mix_fwd_bwd(const float* logits, const int64_t* labels_a, const i
                            const float* lam_dev, float* loss, float* dlogits, int B, int C, float smoothing,
                            float grad_scale, void* stream);
 
+/* ---- the same for a fixed-size step fed a PARTIAL batch (the reference's DataLoader has no drop_last: the last batch of an
+ * epoch is 50000 % 128 = 80 images, main.py:43, utils.py:452-470): n_valid_dev (device int, may be NULL = B) is the number of
+ * real images in rows [0, n_valid); the loss is their mean (criterions.py:19 on the smaller batch), dlogits of the other rows
+ * is zero and the scale is grad_scale / n_valid. ---- */
+int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam,
+                             const float* lam_dev, const int* n_valid_dev, float* loss, float* dlogits, int B, int C,
+                             float smoothing, float grad_scale, void* stream);
+
 /* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77
  * (lr main.py:48, betas :51-52, weight_decay :56, eps 1e-8).  g is multiplied by grad_scale first
  * (1/world_size after a sum all-reduce).  hyper: 16 HOST floats {step_size = lr/(1-b1^t),
@@ -201,12 +209,15 @@ int vitb_sgd_multi(float* p, const float* g, float* buf, void* w_shadow, int64_t
  * shadow_peers may be NULL).  flag buffers: >= world uint32 each, zeroed once; sync: 4 uint32 of this rank, zeroed once.
  * optimizer: 0 = Adam; 1 = SGD with momentum as vitb_sgd_multi (m is the momentum buffer, v may be NULL).
  * Peer pointers come from vitb_ipc_open.  world <= 8, n % 4 == 0.  Every rank must issue the same sequence of calls; a rank that
- * waits longer than ~60 s for a peer traps.  Replicas end bit-identical. ---- */
+ * waits longer than the flag-wait bound for a peer traps (default 600 s; VITB_DP_TIMEOUT_S in the environment or
+ * vitb_dp_set_timeout(seconds) change it: all ranks must enter the step within that time of each other).  Replicas end
+ * bit-identical. ---- */
 int vitb_dp_reduce_adam(const void* const* g_peers, void* const* p_peers, void* const* shadow_peers, void* const* flag_peers, float* m, float* v,
                         uint32_t* sync, int64_t n, int rank, int world, int optimizer, const float* hyper_host, const float* hyper_dev, void* stream);
 /* CUDA IPC plumbing for the above (host functions; no kernels).  export: 64-byte handle of the allocation that contains dev_ptr and
  * dev_ptr's byte offset inside it (the caller ships both to the other ranks, e.g. with torch.distributed.all_gather_object).
  * open: maps a peer's allocation into this process (once per handle, cached) with peer access enabled; returns base + offset. */
+int vitb_dp_set_timeout(double seconds);
 int vitb_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset);
 int vitb_ipc_open(const void* handle64, int64_t offset, void** dev_ptr);
 

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference modules from /root/reference (TEST INFRASTRUCTURE).
+"""Import the UNMODIFIED reference modules (TEST INFRASTRUCTURE).
 
-Only usable where the reference is mounted (the authoring container); the GPU
-box has no /root/reference, so nothing under ``-m gpu``, ``smoke()`` or
-``bench.py`` may call this.  Two shims are needed:
+From /root/reference where it is mounted (the authoring container), else from
+``oracle/_ref`` — the verbatim copy ``oracle/make_ref.py`` makes there, which is
+git-ignored but travels to the GPU box.  Nothing on the GPU box reads
+/root/reference.  Two shims are needed:
   * vit.py:3 imports ``torchsummary`` (unused, not installed);
   * layers.py:12 -> nnmf/optimizer.py:8 imports the private
     ``torch.optim.optimizer._dispatch_sqrt`` removed in torch 2.11.
@@ -14,7 +15,10 @@ import os
 import sys
 import types
 
+_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("VITB_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "vit.py")) and os.path.isfile(os.path.join(_COPY, "vit.py")):
+    REFERENCE_ROOT = _COPY
 
 
 def reference_available() -> bool:

@@ -1,0 +1,233 @@
+"""GPU: parity cases added in round 2 ("next round" item 1).
+
+(a) fp32 check mode at B = 256 for the two 7-layer / 384-wide configurations: logits within 1e-4 of the oracle and
+    `torch.equal` argmax on all 256 predictions (north_star: "argmax predictions bit-exact in the fp32 check mode");
+(b) a bf16 loss TRAJECTORY: 30 Adam steps of the engine on 8 rotating batches against the fp32 oracle running the same
+    loop (network.py:189-208 + torch.optim.Adam), loss within 2e-2 relative at every step ("matched accuracy-per-step");
+(c) the GEMM kernels at the BENCHMARK shapes against an fp32 product of the same bf16-rounded operands;
+(d) partial last batch / checkpoint-resume / weight reload of the fixed-size training engine.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import ViTConfig
+
+pytestmark = pytest.mark.gpu
+
+ADAM = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5)
+FULL65 = ViTConfig(num_classes=10, patch=8, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+FULL17C100 = ViTConfig(num_classes=100, patch=4, num_layers=7, hidden=384, mlp_hidden=384, head=12)
+TINY65 = ViTConfig(num_classes=10, patch=8, num_layers=2, hidden=128, mlp_hidden=128, head=4)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture()
+def vb():
+    import vit_cifar_b200 as v
+    v.ops.require_device()
+    yield v
+    v.set_precision("bf16")
+
+
+def build(vb, cfg: ViTConfig, precision: str, seed: int = 0):
+    vb.set_precision(precision)
+    m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, dropout=0.0, num_layers=cfg.num_layers,
+               hidden=cfg.hidden, encoder_mlp=cfg.encoder_mlp, mlp_hidden=cfg.mlp_hidden, head=cfg.head,
+               is_cls_token=cfg.is_cls_token)
+    m.load_state_dict(oracle.init_params(cfg, seed=seed))
+    return m.cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) 256 predictions, bit-exact argmax in the fp32 check mode
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [FULL65, FULL17C100], ids=["full65", "full17c100"])
+def test_fp32_check_mode_argmax_on_256_images(vb, cfg):
+    B = 256
+    model = build(vb, cfg, "fp32").eval()
+    x, y = oracle.hash_inputs(cfg, B, seed=7)
+    params = oracle.init_params(cfg, 0)
+    with torch.no_grad():
+        ref = oracle.vit_forward(params, x, cfg)
+        out = model(x.cuda())
+    assert out.shape == ref.shape == (B, cfg.num_classes)
+    assert rel(out, ref) < 1e-4
+    assert float((out.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    assert torch.equal(out.argmax(-1).cpu(), ref.argmax(-1))  # all 256 predictions identical
+    # and the loss / accuracy a validation step (network.py:388-395) would log
+    crit = vb.LabelSmoothingCrossEntropyLoss(cfg.num_classes, smoothing=0.1)
+    loss = crit(out, y.cuda()).item()
+    loss_ref = oracle.ls_ce_loss(ref, y, cfg.num_classes, 0.1).item()
+    assert abs(loss - loss_ref) < 1e-4 * abs(loss_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) bf16 trajectory against the fp32 oracle
+# ---------------------------------------------------------------------------------------------
+def test_bf16_loss_trajectory_30_adam_steps_vs_fp32_oracle(vb):
+    cfg, B, steps, nb = FULL65, 16, 30, 8
+    batches = [oracle.hash_inputs(cfg, B, seed=100 + i) for i in range(nb)]
+    # oracle: the reference's loop (forward, LS-CE, backward, torch.optim.Adam) in fp32 on the host
+    ref_model = oracle.OracleViT(cfg, seed=0)
+    opt = torch.optim.Adam(ref_model.parameters(), **ADAM)
+    ref_losses = []
+    for t in range(steps):
+        x, y = batches[t % nb]
+        opt.zero_grad(set_to_none=True)
+        loss = oracle.ls_ce_loss(ref_model(x), y, cfg.num_classes, 0.1)
+        loss.backward()
+        opt.step()
+        ref_losses.append(loss.item())
+    model = build(vb, cfg, "bf16")
+    eng = vb.TrainEngine(model, B, smoothing=0.1, use_graph=True, **ADAM)
+    dev = [(x.cuda(), y.cuda()) for x, y in batches]
+    losses = [eng.step(*dev[t % nb]).item() for t in range(steps)]
+    worst = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+    assert worst < 2e-2, (worst, losses, ref_losses)
+    assert losses[-1] < 0.8 * losses[0]  # and it actually trains
+    # parameters after 30 steps stay close to the fp32 run's (Adam's per-element normalisation amplifies bf16 noise on
+    # near-zero gradients, so this is a loose global check, not an element-wise one)
+    sd = model.state_dict()
+    ref_sd = {k: v.detach() for k, v in ref_model.params().items()}
+    num = sum(float((sd[k].double().cpu() - ref_sd[k].double()).pow(2).sum()) for k in ref_sd)
+    den = sum(float(ref_sd[k].double().pow(2).sum()) for k in ref_sd)
+    assert math.sqrt(num / den) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) GEMM kernels at the benchmark shapes (B = 1024, T = 65 -> 66,560 rows; scaled ViT B = 512 -> 33,280 rows)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ops():
+    import vit_cifar_b200  # noqa: F401
+    from vit_cifar_b200 import ops as o
+    o.require_device()
+    return o
+
+
+def rnd_cuda(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def mm32(a, b):
+    """fp32 product of bf16 operands on the device with TF32 off (plain FFMA accumulation)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return a.float() @ b.float()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+BENCH_FWD = [(66560, 1152, 384), (66560, 384, 384), (33280, 768, 3072), (33280, 3072, 768), (33280, 2304, 768), (8320, 1152, 384), (8320, 384, 384)]
+
+
+@pytest.mark.parametrize("M,N,K", BENCH_FWD)
+def test_gemm_fwd_benchmark_shapes(ops, M, N, K):
+    a = rnd_cuda((M, K), 1); w = rnd_cuda((N, K), 2, 1 / math.sqrt(K)); bias = rnd_cuda((N,), 3).float()
+    res = rnd_cuda((M, N), 4)
+    z_ref = mm32(a, w.t()) + bias
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_fwd(a, w, bias, None, out, None, M, N, K)
+    assert rel(out, z_ref) < 2e-2
+    pre = torch.empty_like(out)
+    ops.gemm_fwd(a, w, bias, res, out, pre, M, N, K, gelu=True)
+    assert rel(pre, z_ref) < 2e-2
+    assert rel(out, F.gelu(z_ref) + res.float()) < 2e-2
+    ops.gemm_fwd(a, w, bias, res, out, None, M, N, K)
+    assert rel(out, z_ref + res.float()) < 2e-2
+
+
+# (rows, N = width of dY, K = width of dX)
+BENCH_DGRAD = [(66560, 1152, 384), (66560, 384, 384), (33280, 3072, 768), (33280, 768, 3072), (33280, 2304, 768), (8320, 1152, 384)]
+
+
+@pytest.mark.parametrize("M,N,K", BENCH_DGRAD)
+def test_gemm_dgrad_benchmark_shapes(ops, M, N, K):
+    dy = rnd_cuda((M, N), 1); w = rnd_cuda((N, K), 2, 1 / math.sqrt(N)); z = rnd_cuda((M, K), 3)
+    ref = mm32(dy, w)
+    dx = torch.empty((M, K), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_dgrad(dy, w, None, dx, M, N, K)
+    assert rel(dx, ref) < 2e-2
+    zz = z.float().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    ops.gemm_dgrad(dy, w, z, dx, M, N, K)
+    assert rel(dx, ref * zz.grad) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(66560, 384, 384), (66560, 1152, 384), (33280, 3072, 768), (33280, 768, 3072), (8320, 384, 384)])
+def test_gemm_wgrad_benchmark_shapes(ops, M, N, K):
+    dy = rnd_cuda((M, N), 1); x = rnd_cuda((M, K), 2)
+    dw = torch.empty((N, K), dtype=torch.float32, device="cuda"); db = torch.empty((N,), dtype=torch.float32, device="cuda")
+    ops.gemm_wgrad(dy, x, dw, db, M, N, K)
+    assert rel(dw, mm32(dy.t(), x)) < 1e-3   # fp32 accumulation of exact bf16 products; only the summation order differs
+    assert rel(db, dy.float().sum(0)) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# (d) the fixed-size engine: partial batches, resume, weight reload
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_partial_last_batch_matches_oracle(vb, use_graph):
+    """The reference's DataLoader keeps the partial last batch of an epoch (50000 % 128 = 80, no drop_last): an engine built for
+    B = 8 is fed 8, then 5, then 8 images; each step must equal the oracle's step on exactly those images (mean over n)."""
+    cfg = TINY65
+    model = build(vb, cfg, "fp32")
+    eng = vb.TrainEngine(model, 8, smoothing=0.1, use_graph=use_graph, **ADAM)
+    params = oracle.init_params(cfg, 0)
+    mo = {k: torch.zeros_like(v) for k, v in params.items()}
+    vo = {k: torch.zeros_like(v) for k, v in params.items()}
+    for t, n in enumerate([8, 5, 8, 1], start=1):
+        x, y = oracle.hash_inputs(cfg, n, seed=40 + t)
+        loss = eng.step(x.cuda(), y.cuda()).item()
+        _, loss_ref, grads_ref = oracle.train_step(params, x, y, cfg, 0.1)
+        assert abs(loss - loss_ref.item()) < 1e-4 * abs(loss_ref.item()), (t, n, loss, loss_ref.item())
+        for k, g in eng.grads().items():
+            if "Wk.bias" in k:
+                continue
+            assert rel(g, grads_ref[k]) < 1e-4, (t, n, k)
+        oracle.adam_step(params, grads_ref, mo, vo, t, ADAM["lr"], ADAM["betas"], ADAM["eps"], ADAM["weight_decay"])
+    with pytest.raises(ValueError):
+        eng.step(*[t.cuda() for t in oracle.hash_inputs(cfg, 9, seed=1)])
+    with pytest.raises(ValueError):
+        eng.load_batch(torch.zeros(4, 3, 16, 16, device="cuda"), torch.zeros(4, dtype=torch.int64, device="cuda"))
+    # prefetch path: a pinned partial batch
+    x, y = oracle.hash_inputs(cfg, 3, seed=77)
+    eng.prefetch(x.pin_memory(), y.pin_memory())
+    loss = eng.step().item()
+    _, loss_ref, _ = oracle.train_step(params, x, y, cfg, 0.1)
+    assert abs(loss - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+
+
+def test_engine_checkpoint_resume_and_sync_weights(vb):
+    """checkpoint() -> a fresh engine -> load_checkpoint(): the next steps continue bit for bit (parameters, Adam moments, step
+    count); loading weights behind a live engine's back needs sync_weights() (bf16 copy refreshed from the fp32 master)."""
+    cfg = TINY65
+    batches = [tuple(t.cuda() for t in oracle.hash_inputs(cfg, 8, seed=60 + i)) for i in range(5)]
+    a = vb.TrainEngine(build(vb, cfg, "bf16"), 8, use_graph=True, **ADAM)
+    for i in range(3):
+        a.step(*batches[i])
+    ck = a.checkpoint(hyper_parameters={"model_name": "vit"}, epoch=1)
+    assert set(ck) >= {"state_dict", "hyper_parameters", "optimizer_states", "global_step", "epoch"} and ck["global_step"] == 3
+    assert all(k.startswith("model.") for k in ck["state_dict"])
+    la = [a.step(*batches[i]).item() for i in (3, 4)]
+    b = vb.TrainEngine(build(vb, cfg, "bf16", seed=5), 8, use_graph=True, **ADAM)  # different initial weights
+    b.load_checkpoint(ck)
+    lb = [b.step(*batches[i]).item() for i in (3, 4)]
+    assert la == lb
+    assert torch.equal(a.P, b.P) and torch.equal(a.Mo, b.Mo) and torch.equal(a.V, b.V)
+    # stale shadow: write the master behind the engine's back, then sync
+    c = vb.TrainEngine(build(vb, cfg, "bf16", seed=5), 8, use_graph=False, lr=0.0, weight_decay=0.0)
+    c.model.load_state_dict(oracle.init_params(cfg, seed=0))
+    c.sync_weights()
+    d = vb.TrainEngine(build(vb, cfg, "bf16", seed=0), 8, use_graph=False, lr=0.0, weight_decay=0.0)
+    assert c.step(*batches[0]).item() == d.step(*batches[0]).item()

@@ -324,7 +324,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "img/s" and d["higher_is_better"] is True and d["value"] > 0
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    # "reference" when a copy of the reference's own modules is reachable (/root/reference here, oracle/_ref on the GPU box), else the port
+    from oracle import ref_shim
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert "bf16" not in d["config"]["workload"] and d["config"]["per_step_batch"] == 128  # the arm says what it actually ran
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],

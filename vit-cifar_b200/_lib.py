@@ -58,9 +58,11 @@ SIGNATURES = {
     "vitb_dropout": (_i, [_p, _p, _p, _i64, _f, C.c_uint64, C.c_uint32, C.c_uint32, _p, _i, _p]),
     "vitb_ls_ce_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_mix_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _i, _i, _f, _f, _p]),
+    "vitb_ls_ce_batch_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_adam_multi": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "vitb_sgd_multi": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p]),
     "vitb_dp_reduce_adam": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p]),
+    "vitb_dp_set_timeout": (_i, [C.c_double]),
     "vitb_ipc_export": (_i, [_p, _p, _p]),
     "vitb_ipc_open": (_i, [_p, _i64, _p]),
 }

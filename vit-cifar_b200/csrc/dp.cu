@@ -16,6 +16,7 @@
 // Peer buffers are mapped with CUDA IPC (vitb_ipc_export / vitb_ipc_open below): torch.distributed only carries the 64-byte handles.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -40,6 +41,8 @@ struct DpArgs {
   int64_t lo4, hi4;              // owned slice in float4 units
   int rank, world;
   int optimizer;                 // 0 = Adam, 1 = SGD with momentum (m is the momentum buffer, v unused)
+  long long spin_limit;          // bound of every flag wait in SM clocks (vitb_dp_set_timeout / VITB_DP_TIMEOUT_S)
+  long long* phase_clk;          // optional [5] per-launch phase durations of block 0 / the last block (tools/dp_phases.py); null in production
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -62,7 +65,20 @@ __device__ __forceinline__ float4 ld4_sys(const float* p) {
   return v;
 }
 
-constexpr long long kDpSpinLimit = 120LL * 1000 * 1000 * 1000;  // ~60 s of SM clocks: a peer that never arrives is a dead job
+// Flag waits are bounded so that a dead peer becomes a launch error instead of a hung GPU.  The bound has to cover ordinary rank
+// skew (rank-0-only validation or checkpoint writing, a slow data loader, first-step graph capture): default 600 s of SM clocks at
+// ~2 GHz, like a collective library's watchdog; VITB_DP_TIMEOUT_S or vitb_dp_set_timeout() change it.  All ranks must enter
+// step() within that time of each other.
+static long long g_dp_spin_limit = -1;
+static long long dp_spin_limit() {
+  if (g_dp_spin_limit < 0) {
+    const char* e = getenv("VITB_DP_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (!(s > 0.0)) s = 600.0;
+    g_dp_spin_limit = (long long)(s * 2.0e9);
+  }
+  return g_dp_spin_limit;
+}
 
 // thread t < world: tell rank t that this rank reached `value`, then wait until rank t has told us the same
 __device__ __forceinline__ void dp_exchange(const DpArgs& a, int t, uint32_t value) {
@@ -71,7 +87,7 @@ __device__ __forceinline__ void dp_exchange(const DpArgs& a, int t, uint32_t val
   const uint32_t* mine = a.flags[a.rank] + t;
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
-    if (clock64() - t0 > kDpSpinLimit) {
+    if (clock64() - t0 > a.spin_limit) {
       printf("vitb dp: rank %d timed out waiting for rank %d (flag %u, want %u)\n", a.rank, t, ld_acquire_sys(mine), value);
       __trap();
     }
@@ -82,6 +98,10 @@ __device__ __forceinline__ void dp_exchange(const DpArgs& a, int t, uint32_t val
 __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   __shared__ uint32_t s_epoch;
   __shared__ bool s_last;
+  // Under programmatic dependent launch this grid may start before the backward kernels have finished: nothing below may read
+  // the gradients, touch sync[] or tell the peers "my backward is complete" before the preceding grid's memory is visible.
+  pdl_wait();
+  const long long c0 = clock64();
   if (threadIdx.x == 0) s_epoch = a.sync[0] + 1;  // sync[0] is only advanced by the last block of the previous launch
   __syncthreads();
   const uint32_t epoch = s_epoch;
@@ -94,11 +114,12 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_gpu(a.sync + 1) - epoch) < 0) {
-      if (clock64() - t0 > 2 * kDpSpinLimit) __trap();
+      if (clock64() - t0 > 2 * a.spin_limit) __trap();
       __nanosleep(32);
     }
   }
   __syncthreads();
+  const long long c1 = clock64();
 
   // ---- reduce-scatter + Adam + all-gather of the owned slice
   const AdamHyper h = a.hyper_dev != nullptr ? adam_hyper_from(a.hyper_dev) : a.hyper;
@@ -137,8 +158,13 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   }
 
   // ---- barrier B: the last block to finish (all stores of the grid are then ordered before its signal) trades flags again
+  const long long c2 = clock64();
   __threadfence_system();
   __syncthreads();
+  if (a.phase_clk != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {  // block 0: wait for the peers' backward, then its share of the slice
+    a.phase_clk[0] = c1 - c0;
+    a.phase_clk[1] = c2 - c1;
+  }
   if (threadIdx.x == 0) {
     const uint32_t done = atomicAdd(a.sync + 2, 1u);
     s_last = (done == gridDim.x - 1);
@@ -146,12 +172,18 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpArgs a) {
   __syncthreads();
   if (s_last) {
     __threadfence();
+    const long long c3 = clock64();
     if ((int)threadIdx.x < a.world) dp_exchange(a, threadIdx.x, 2 * epoch);
     __syncthreads();
     if (threadIdx.x == 0) {
       a.sync[2] = 0;
       a.sync[0] = epoch;
       __threadfence();
+      if (a.phase_clk != nullptr) {  // last block: whole grid (entry of this block to all stores issued), fence, barrier B
+        a.phase_clk[2] = c2 - c0;
+        a.phase_clk[3] = c3 - c2;
+        a.phase_clk[4] = clock64() - c3;
+      }
     }
   }
 }
@@ -169,6 +201,8 @@ static GetRangeFn get_range_fn() {
   return fn;
 }
 
+static long long* g_dp_phase_clk = nullptr;  // tools only (vitb_debug_dp_phases)
+
 static std::mutex g_ipc_mu;
 static std::map<std::string, void*> g_ipc_open;  // handle bytes -> mapped base (a handle may be opened once per process)
 
@@ -177,6 +211,19 @@ static std::map<std::string, void*> g_ipc_open;  // handle bytes -> mapped base 
 using namespace vitb;
 
 extern "C" {
+
+/* tools only (not in vitb200.h): device buffer of 5 int64 that every dp_reduce_adam launch fills with its phase durations
+   {barrier A, block 0's slice, last block's entry-to-stores, fence, barrier B} in SM clocks; NULL switches it off */
+int vitb_debug_dp_phases(long long* dev_buf) {
+  g_dp_phase_clk = dev_buf;
+  return 0;
+}
+
+int vitb_dp_set_timeout(double seconds) {
+  VITB_REQUIRE(seconds > 0.0, "dp_set_timeout: seconds must be positive");
+  g_dp_spin_limit = (long long)(seconds * 2.0e9);
+  return 0;
+}
 
 int vitb_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset) {
   VITB_REQUIRE(dev_ptr && handle64 && offset, "ipc_export: null pointer");
@@ -236,6 +283,8 @@ int vitb_dp_reduce_adam(const void* const* g_peers, void* const* p_peers, void* 
   a.lo4 = per * rank < n4 ? per * rank : n4;
   a.hi4 = per * (rank + 1) < n4 ? per * (rank + 1) : n4;
   a.rank = rank; a.world = world; a.optimizer = optimizer;
+  a.spin_limit = dp_spin_limit();
+  a.phase_clk = g_dp_phase_clk;
   int blocks = (int)ceil_div64(a.hi4 - a.lo4 + 1, 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
   if (blocks < 1) blocks = 1;

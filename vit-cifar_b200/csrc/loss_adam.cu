@@ -12,18 +12,27 @@ namespace vitb {
 // lam_dev != nullptr (so a captured CUDA graph sees a new value every step).
 __global__ void __launch_bounds__(1024)
     ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const int64_t* __restrict__ labels_b, float lam_host,
-                 const float* __restrict__ lam_dev, float* __restrict__ loss, float* __restrict__ dlogits, int B, int C, float smoothing,
-                 float grad_scale) {
+                 const float* __restrict__ lam_dev, const int* __restrict__ n_valid_dev, float* __restrict__ loss, float* __restrict__ dlogits, int B,
+                 int C, float smoothing, float grad_scale) {
   pdl_trigger();
   pdl_wait();
   __shared__ float part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float off = smoothing / (float)(C - 1);
   const float conf = 1.0f - smoothing;
-  const float gs = grad_scale / (float)B;
+  // a partial last batch of an epoch in a fixed-size (graph-captured) step: only the first n_valid rows are images; the mean runs
+  // over them (criterions.py:19 on a smaller batch) and the other rows get a zero gradient, which every downstream kernel
+  // propagates as zero (images are independent through the whole network)
+  const int nv = n_valid_dev != nullptr ? min(max(*n_valid_dev, 1), B) : B;
+  const float gs = grad_scale / (float)nv;
   const float lam = labels_b == nullptr ? 1.0f : (lam_dev != nullptr ? *lam_dev : lam_host);
   float acc = 0.f;
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    if (r >= nv) {
+      if (dlogits != nullptr)
+        for (int j = 0; j < C; ++j) dlogits[(size_t)r * C + j] = 0.f;
+      continue;
+    }
     const float* z = logits + (size_t)r * C;
     const int y = (int)labels[r];
     const int yb = labels_b != nullptr ? (int)labels_b[r] : y;
@@ -56,7 +65,7 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += part[w];
-    *loss = s / (float)B;
+    *loss = s / (float)nv;
   }
 }
 
@@ -149,10 +158,15 @@ int vitb_ls_ce_fwd_bwd(const float* logits, const int64_t* labels, float* loss, 
 
 int vitb_ls_ce_mix_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam, const float* lam_dev, float* loss,
                            float* dlogits, int B, int C, float smoothing, float grad_scale, void* stream) {
+  return vitb_ls_ce_batch_fwd_bwd(logits, labels_a, labels_b, lam, lam_dev, nullptr, loss, dlogits, B, C, smoothing, grad_scale, stream);
+}
+
+int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam, const float* lam_dev,
+                             const int* n_valid_dev, float* loss, float* dlogits, int B, int C, float smoothing, float grad_scale, void* stream) {
   VITB_REQUIRE(logits && labels_a && loss, "ls_ce: null pointer");
   VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
   VITB_REQUIRE(lam_dev != nullptr || (lam >= 0.0f && lam <= 1.0f), "ls_ce: lam=%f outside [0, 1]", lam);
-  VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels_a, labels_b, lam, lam_dev, loss, dlogits, B, C, smoothing, grad_scale);
+  VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels_a, labels_b, lam, lam_dev, n_valid_dev, loss, dlogits, B, C, smoothing, grad_scale);
   VITB_LAUNCH_OK();
   return 0;
 }

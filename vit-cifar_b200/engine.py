@@ -133,6 +133,10 @@ class TrainEngine:
         self._consumed = torch.cuda.Event()
         self._consumed.record()
         self._pending = False
+        # number of real images in the static batch buffers (a partial last batch of an epoch: the reference's DataLoader does
+        # not drop it, main.py:43 / utils.py:452-470); word 11 of the per-step block, read by the loss kernel
+        self._n_valid = self.B
+        self._next_n_valid = self.B
         self.dlogits = torch.zeros((self.B, model.num_classes), dtype=torch.float32, device=self.dev)
         self.logits: Optional[torch.Tensor] = None
         self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=self.dev)
@@ -195,10 +199,12 @@ class TrainEngine:
             saved.append(sv)
         ln_w, ln_b, fc_w_c, fc_b = self.head_p
         self.logits, hsaved = Fn.head_fwd(x, ln_w, ln_b, fc_w_c, fc_b, B, T, H, Cn, m.is_cls_token, self._alloc("head"))
+        n_valid_dev = self.hyper_dev.view(torch.int32)[11:12]
         if self.mixed_targets:
-            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, labels_b=self.labels_b, lam_dev=self.hyper_dev[9:10])
+            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, labels_b=self.labels_b, lam_dev=self.hyper_dev[9:10],
+                      n_valid_dev=n_valid_dev)
         else:
-            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0)
+            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, n_valid_dev=n_valid_dev)
 
         g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
         dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
@@ -236,29 +242,52 @@ class TrainEngine:
     def set_lr(self, lr: float) -> None:
         self.lr = float(lr)
 
-    def load_batch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor] = None) -> None:
-        """Copy a batch (pinned host or device tensors) into the static input buffers on the current stream."""
-        self.img.copy_(img, non_blocking=True)
-        self.labels.copy_(labels, non_blocking=True)
-        if self.mixed_targets:
-            self.labels_b.copy_(labels if labels_b is None else labels_b, non_blocking=True)
-        elif labels_b is not None:
+    def _check_batch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor]) -> int:
+        """Number of images of a batch for the fixed-size step: 1..B.  The step is a static kernel sequence over B rows (a CUDA
+        graph); a smaller batch — the last one of an epoch, the reference's DataLoader has no drop_last — occupies the first n
+        rows, the loss kernel averages over n and zeroes the gradient of the other rows."""
+        if img.dim() != 4 or tuple(img.shape[1:]) != tuple(self.img.shape[1:]):
+            raise ValueError(f"expected images of shape (n, {', '.join(str(d) for d in self.img.shape[1:])}) with n <= {self.B}, got {tuple(img.shape)}")
+        n = int(img.shape[0])
+        if not 1 <= n <= self.B:
+            raise ValueError(f"batch of {n} images: this engine was built for batches of 1..{self.B} (batch_size={self.B})")
+        if labels.dim() != 1 or labels.shape[0] != n or (labels_b is not None and tuple(labels_b.shape) != (n,)):
+            raise ValueError(f"expected {n} labels, got {tuple(labels.shape)}" + (f" / {tuple(labels_b.shape)}" if labels_b is not None else ""))
+        if labels_b is not None and not self.mixed_targets:
             raise ValueError("construct the engine with mixed_targets=True to train on (label, rand_label, lambda) batches")
+        return n
+
+    @staticmethod
+    def _copy_rows(dst: torch.Tensor, src: torch.Tensor, n: int) -> None:
+        if n == dst.shape[0]:
+            dst.copy_(src, non_blocking=True)
+        else:  # rows >= n: defined, finite values (their gradient is zeroed by the loss kernel)
+            dst[:n].copy_(src, non_blocking=True)
+            dst[n:].zero_()
+
+    def load_batch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor] = None) -> None:
+        """Copy a batch of n <= batch_size images (pinned host or device tensors) into the static input buffers on the current stream."""
+        n = self._check_batch(img, labels, labels_b)
+        self._copy_rows(self.img, img, n)
+        self._copy_rows(self.labels, labels, n)
+        if self.mixed_targets:
+            self._copy_rows(self.labels_b, labels if labels_b is None else labels_b, n)
+        self._n_valid = n
 
     def prefetch(self, img: torch.Tensor, labels: torch.Tensor, labels_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> None:
         """Start copying the NEXT batch (pinned host tensors) to the device on a side stream; the following `step()` (called
         without arguments) trains on it.  Called right after `step()` returns, the host-to-device transfer overlaps that step's
         kernels — the role the DataLoader's pinned-memory prefetch plays for the reference (main.py:175)."""
+        n = self._check_batch(img, labels, labels_b)
         cs = self._copy_stream
         cs.wait_event(self._consumed)  # the previously staged batch has been moved into the input buffers
         with torch.cuda.stream(cs):
-            self._img_stage.copy_(img, non_blocking=True)
-            self._labels_stage.copy_(labels, non_blocking=True)
+            self._copy_rows(self._img_stage, img, n)
+            self._copy_rows(self._labels_stage, labels, n)
             if self.mixed_targets:
-                self._labels_b_stage.copy_(labels if labels_b is None else labels_b, non_blocking=True)
-            elif labels_b is not None:
-                raise ValueError("construct the engine with mixed_targets=True to train on (label, rand_label, lambda) batches")
+                self._copy_rows(self._labels_b_stage, labels if labels_b is None else labels_b, n)
             self._staged.record(cs)
+        self._next_n_valid = n
         self._next_lam = float(lam) if labels_b is not None else 1.0
         self._pending = True
 
@@ -277,6 +306,7 @@ class TrainEngine:
             if self.mixed_targets:
                 self.labels_b.copy_(self._labels_b_stage, non_blocking=True)
             self._lam = self._next_lam
+            self._n_valid = self._next_n_valid
             self._consumed.record(cur)
             self._pending = False
         self.step_count += 1
@@ -288,6 +318,7 @@ class TrainEngine:
         slot[:9] = torch.tensor(h, dtype=torch.float32)
         slot[9] = self._lam
         slot.view(torch.int32)[10] = self.step_count & 0x7FFFFFFF  # dropout mask step
+        slot.view(torch.int32)[11] = self._n_valid
         self.hyper_dev.copy_(slot, non_blocking=True)
         if self._l2_persist and self.step_count == 1 and self.C is not self.P:
             # bf16 weights stay in a persisting carve-out of L2 (16 MB of 126): the resident GEMMs' weight blocks are L2 hits
@@ -315,6 +346,65 @@ class TrainEngine:
         else:
             self._graph.replay()
         return self.loss
+
+    def sync_weights(self) -> None:
+        """Call after writing parameters from outside the step (load_state_dict / load_checkpoint / manual edits on the packed
+        model): re-derives the bf16 weight copy the kernels read from the fp32 master and, with world > 1, makes rank 0's
+        parameters those of every replica.  The step itself keeps both in sync (the optimiser kernel writes both)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.P, src=0, group=self.pg)
+        if self.C is not self.P:
+            ops.cast_f32_to_bf16(self.P, self.C)
+
+    def load_checkpoint(self, ckpt, strict: bool = False):
+        """schedule.load_checkpoint into the engine's model, followed by sync_weights(); restores the optimiser state too when the
+        checkpoint carries one (`optimizer_states` as written by `checkpoint()`)."""
+        from .schedule import load_checkpoint
+        if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+            ckpt = torch.load(ckpt, map_location="cpu")
+        res = load_checkpoint(self.model, ckpt, strict=strict)
+        self.sync_weights()
+        if isinstance(ckpt, dict) and ckpt.get("optimizer_states"):
+            self.load_optimizer_state(ckpt["optimizer_states"][0], ckpt.get("global_step"))
+        return res
+
+    def optimizer_state(self) -> dict:
+        """torch.optim-style optimiser state of the flat parameter buffer: {"step", "exp_avg", "exp_avg_sq"} (Adam) or
+        {"step", "momentum_buffer"} (SGD) as CPU tensors of `n` elements.  In the fused data-parallel mode every rank maintains
+        the moments of its owned slice only (parallel.owned_slice): the slices are gathered here (a collective: call on all ranks)."""
+        from .parallel import owned_slice
+        bufs = {"exp_avg": self.Mo, "exp_avg_sq": self.V} if self.optimizer == "adam" else {"momentum_buffer": self.Mo}
+        out = {"step": int(self.step_count)}
+        for name, t in bufs.items():
+            full = t[:self.n].clone()
+            if self._fused_dp is not None:
+                import torch.distributed as dist
+                lo, hi = owned_slice(self.n, self._rank, self.world)
+                full[:lo].zero_()
+                full[hi:].zero_()
+                dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.pg)
+            out[name] = full.cpu()
+        return out
+
+    def load_optimizer_state(self, state: dict, step: Optional[int] = None) -> None:
+        self.step_count = int(state.get("step", 0) if step is None else step)
+        pairs = (("exp_avg", self.Mo), ("exp_avg_sq", self.V)) if self.optimizer == "adam" else (("momentum_buffer", self.Mo),)
+        for name, t in pairs:
+            src = state[name]
+            if src.numel() != self.n:
+                raise ValueError(f"optimizer state {name}: {src.numel()} elements, this model has {self.n}")
+            t[:self.n].copy_(src.to(self.dev, torch.float32).flatten())
+
+    def checkpoint(self, hyper_parameters: Optional[dict] = None, epoch: int = 0) -> dict:
+        """The reference's checkpoint dict (main.py:234-237: "state_dict" with "model." keys + "hyper_parameters") extended with
+        what Lightning also stores for resuming: "optimizer_states", "global_step", "epoch".  Collective when world > 1."""
+        from .schedule import to_lightning_checkpoint
+        ck = to_lightning_checkpoint(self.model, hyper_parameters)
+        ck["optimizer_states"] = [self.optimizer_state()]
+        ck["global_step"] = int(self.step_count)
+        ck["epoch"] = int(epoch)
+        return ck
 
     def grads(self) -> Dict[str, torch.Tensor]:
         """Views of the flat gradient buffer by state_dict name (of the LAST step; summed over ranks when world > 1)."""

@@ -221,12 +221,20 @@ def dropout(x, residual, out, p: float, seed: int, site: int, step: int = 0, ste
                                    int(step) & 0xFFFFFFFF, _ptr(step_dev), dt_of(x), _stream()), "dropout")
 
 
-def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None) -> None:
+def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None,
+          n_valid_dev=None) -> None:
     """LS-CE forward + dlogits.  With `labels_b`: the two-target CutMix / MixUp loss lam*L(a) + (1-lam)*L(b) (network.py:149-167);
-    `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step."""
+    `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step.
+    `n_valid_dev` (1-element int32 device tensor): only rows [0, n_valid) are images (partial last batch of an epoch)."""
     B, Cn = logits.shape
     assert logits.dtype == torch.float32 and labels.dtype == torch.int64
     _contig(logits, labels, dlogits)
+    if n_valid_dev is not None:
+        assert n_valid_dev.dtype == torch.int32 and (labels_b is None or labels_b.dtype == torch.int64)
+        _contig(labels_b)
+        check(_lib.load().vitb_ls_ce_batch_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(labels_b), float(lam), _ptr(lam_dev), _ptr(n_valid_dev), _ptr(loss),
+                                                   _ptr(dlogits), B, Cn, smoothing, grad_scale, _stream()), "ls_ce_batch_fwd_bwd")
+        return
     if labels_b is None:
         check(_lib.load().vitb_ls_ce_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(loss), _ptr(dlogits), B, Cn, smoothing, grad_scale, _stream()),
               "ls_ce_fwd_bwd")
