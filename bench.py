@@ -291,6 +291,7 @@ def probe_kernels(eng, steps=3):
         setattr(ops, n, wrap(n, orig[n]))
     try:
         saved_graph, eng.use_graph = eng.use_graph, False
+        saved_side, eng._side = eng._side, None  # per-kernel times: everything on one stream, one kernel at a time
         for _ in range(steps):
             # Park the GPU (~25 ms spin) while the host enqueues the whole eager step: every kernel then starts the moment
             # its predecessor ends, so an event pair brackets device time only, not host launch latency.
@@ -298,6 +299,7 @@ def probe_kernels(eng, steps=3):
             eng.step()
             torch.cuda.synchronize()
         eng.use_graph = saved_graph
+        eng._side = saved_side
     finally:
         for n in names:
             setattr(ops, n, orig[n])

@@ -184,6 +184,19 @@ int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const
                              const float* lam_dev, const int* n_valid_dev, float* loss, float* dlogits, int B, int C,
                              float smoothing, float grad_scale, void* stream);
 
+/* ---- deferred second passes of split reductions.  Every gradient that is a sum over the batch rows (wgrad dW / db, LayerNorm
+ * dgamma / dbeta and the column sums that are a Linear's bias gradient, GELU-backward column sums) is computed as per-CTA fp32
+ * partials followed by a fixed-order second pass.  Between vitb_defer_begin and vitb_defer_flush (same host thread) the calls
+ * vitb_gemm_wgrad_dbias, vitb_layernorm_bwd and vitb_gelu_bwd_colsum place their partials in `arena` (device memory the caller
+ * keeps alive until the flush has run; 256-byte aligned) and record the second pass instead of launching it; the flush runs all
+ * recorded passes in one launch per kernel class with the SAME summation order, so results are bit-identical to the immediate
+ * path.  The outputs of the deferred calls are undefined until the flush has executed.  A call whose partials do not fit in what is
+ * left of the arena runs its second pass immediately, as without deferral.  vitb_defer_used: bytes a large enough arena would
+ * have held in the last begin..flush window. ---- */
+int vitb_defer_begin(void* arena, size_t arena_bytes);
+int vitb_defer_flush(void* stream);
+size_t vitb_defer_used(void);
+
 /* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77
  * (lr main.py:48, betas :51-52, weight_decay :56, eps 1e-8).  g is multiplied by grad_scale first
  * (1/world_size after a sum all-reduce).  hyper: 16 HOST floats {step_size = lr/(1-b1^t),

@@ -92,7 +92,7 @@ def test_bf16_loss_trajectory_30_adam_steps_vs_fp32_oracle(vb):
     losses = [eng.step(*dev[t % nb]).item() for t in range(steps)]
     worst = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
     assert worst < 2e-2, (worst, losses, ref_losses)
-    assert losses[-1] < 0.8 * losses[0]  # and it actually trains
+    assert losses[-1] < losses[0] and ref_losses[-1] < ref_losses[0]  # and both actually train
     # parameters after 30 steps stay close to the fp32 run's (Adam's per-element normalisation amplifies bf16 noise on
     # near-zero gradients, so this is a loose global check, not an element-wise one)
     sd = model.state_dict()

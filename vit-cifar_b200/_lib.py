@@ -59,6 +59,9 @@ SIGNATURES = {
     "vitb_ls_ce_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_mix_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_batch_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _p, _i, _i, _f, _f, _p]),
+    "vitb_defer_begin": (_i, [_p, _sz]),
+    "vitb_defer_flush": (_i, [_p]),
+    "vitb_defer_used": (_sz, []),
     "vitb_adam_multi": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "vitb_sgd_multi": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p]),
     "vitb_dp_reduce_adam": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p]),

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libvitb200.so")
 
-SOURCES = ["elementwise.cu", "loss_adam.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "head.cu", "dp.cu", "gemm_ts.cu"]
+SOURCES = ["elementwise.cu", "loss_adam.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "head.cu", "dp.cu"]
 HEADERS = ["common.cuh", "gemm_internal.h"]
 
 NVCC_FLAGS = [

@@ -280,21 +280,13 @@ __global__ void __launch_bounds__(256) partials_finalize2_kernel(const float* __
 }
 
 // "tall" variant for MANY partial rows of FEW columns (LayerNorm / GELU column sums: 300-740 partials x 384): block (8, 64) =
-// 8 four-column lanes x 64 slices of the partials, grid (ceil(cols / 32), outputs).  The plain kernel would run such a shape on 3
+// 8 four-column lanes x 64 slices of the partials, ceil(cols / 32) blocks per output.  The plain kernel would run such a shape on 3
 // blocks whose threads each walk ~90 dependent L2 round trips (21 us for 1 MB); here a thread walks nparts / 64 of them.
 // Slices are combined in a fixed order (8 groups of 8, then the 8 group sums): deterministic.
-template <int kUnused = 0>
-__global__ void __launch_bounds__(512) partials_finalize_tall_kernel(const float* __restrict__ ws, int nparts, int64_t cols, float* out0, float* out1,
-                                                                     float* out2) {
-  pdl_trigger();
-  pdl_wait();
+__device__ __forceinline__ void finalize_tall_block(const float* __restrict__ base, int nparts, int64_t cols, float* __restrict__ out, int bx) {
   __shared__ float4 red[64][8];
-  const int k = blockIdx.y;
-  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
-  if (out == nullptr) return;
-  const float* base = ws + (size_t)k * nparts * cols;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int64_t c = ((int64_t)blockIdx.x * 8 + tx) * 4;
+  const int64_t c = ((int64_t)bx * 8 + tx) * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < cols) {
     for (int i = ty; i < nparts; i += 64) {
@@ -325,13 +317,67 @@ __global__ void __launch_bounds__(512) partials_finalize_tall_kernel(const float
   }
 }
 
+template <int kUnused = 0>
+__global__ void __launch_bounds__(512) partials_finalize_tall_kernel(const float* __restrict__ ws, int nparts, int64_t cols, float* out0, float* out1,
+                                                                     float* out2) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = blockIdx.y;
+  float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+  if (out == nullptr) return;
+  finalize_tall_block(ws + (size_t)k * nparts * cols, nparts, cols, out, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deferred reductions (vitb_defer_begin / vitb_defer_flush): between the two calls every split reduction whose result is only a
+// GRADIENT (wgrad dW / db partials, LayerNorm dgamma / dbeta / column sums, GELU-backward column sums) places its fp32 partials in
+// the caller's arena and records a job instead of launching its second pass; the flush reduces all recorded jobs with the same
+// per-column summation order in one launch per job class — ~45 launches and their dependent-launch latencies less per step.
+// ---------------------------------------------------------------------------------------------
+struct ReduceJob {
+  const float* src;  // [nparts][cols] fp32 partials
+  float* dst;        // [cols]
+  int nparts;
+  int cols;
+};
+constexpr int kMaxReduceJobs = 120;  // per launch: the table travels in the kernel parameters (< 4 KB)
+struct ReduceBatch {
+  int njobs;
+  int block_start[kMaxReduceJobs + 1];  // first block of every job
+  ReduceJob jobs[kMaxReduceJobs];
+};
+bool defer_active();
+void* defer_alloc(size_t bytes);          // arena memory for partials (256-byte aligned), or nullptr (not deferring / arena exhausted)
+bool defer_owns(const void* p);
+void defer_add(const float* src, int nparts, int64_t cols, float* dst);
+inline bool finalize_is_tall(int nparts, int64_t cols) { return (cols & 3) == 0 && nparts >= 64 && cols <= 8192; }
+
 inline dim3 finalize_grid(int64_t cols, int nout) { return dim3((unsigned)((cols + 127) / 128), (unsigned)nout); }
-// picks the tall kernel for many partials of a narrow output, the plain one otherwise (one launch either way)
+// picks the tall kernel for many partials of a narrow output, the plain one otherwise (one launch either way); partials that live
+// in the deferral arena are recorded for vitb_defer_flush instead.  Counts its own launch.
 inline cudaError_t launch_finalize(const float* ws, int nparts, int64_t cols, float* out0, float* out1, float* out2, int nout, cudaStream_t st) {
-  if ((cols & 3) == 0 && nparts >= 64 && cols <= 8192)
+  if (defer_active() && defer_owns(ws)) {
+    float* outs[3] = {out0, out1, out2};
+    for (int k = 0; k < nout; ++k)
+      if (outs[k] != nullptr) defer_add(ws + (size_t)k * nparts * cols, nparts, cols, outs[k]);
+    return cudaSuccess;
+  }
+  count_launch();
+  if (finalize_is_tall(nparts, cols))
     return launch_kernel(partials_finalize_tall_kernel<0>, dim3((unsigned)((cols + 31) / 32), (unsigned)nout), dim3(8, 64), 0, st, ws, nparts, cols, out0,
                          out1, out2);
   return launch_kernel(partials_finalize_kernel<0>, finalize_grid(cols, nout), dim3(32, 8), 0, st, ws, nparts, cols, out0, out1, out2);
+}
+// dW and the bias gradient of a wgrad (two partial sets of different widths): one launch, or two deferred jobs
+inline cudaError_t launch_finalize2(const float* ws0, int64_t cols0, float* out0, const float* ws1, int64_t cols1, float* out1, int nparts, cudaStream_t st) {
+  if (defer_active() && defer_owns(ws0) && defer_owns(ws1)) {
+    defer_add(ws0, nparts, cols0, out0);
+    defer_add(ws1, nparts, cols1, out1);
+    return cudaSuccess;
+  }
+  count_launch();
+  const unsigned nb = (unsigned)((cols0 + 127) / 128 + (cols1 + 127) / 128);
+  return launch_kernel(partials_finalize2_kernel<0>, dim3(nb), dim3(32, 8), 0, st, ws0, cols0, out0, ws1, cols1, out1, nparts);
 }
 inline dim3 finalize_block() { return dim3(32, 8); }
 

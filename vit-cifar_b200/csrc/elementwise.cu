@@ -5,6 +5,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace vitb {
@@ -26,6 +28,68 @@ const PersistWindow& persist_window() { return g_persist; }
 void set_persist_window(void* base, size_t bytes, float hit_ratio) { g_persist = {base, bytes, hit_ratio}; }
 static unsigned long long g_launches = 0;  // host-side, single launching thread per process
 void count_launch() { ++g_launches; }
+
+// ---- deferred reductions (common.cuh) ----
+struct DeferState {
+  char* arena = nullptr;
+  size_t cap = 0, used = 0, high = 0;
+  bool active = false;
+  std::vector<ReduceJob> plain, tall;
+};
+static thread_local DeferState g_defer;
+bool defer_active() { return g_defer.active; }
+bool defer_owns(const void* p) { return g_defer.active && (const char*)p >= g_defer.arena && (const char*)p < g_defer.arena + g_defer.cap; }
+void* defer_alloc(size_t bytes) {
+  if (!g_defer.active) return nullptr;
+  const size_t need = align_up(bytes, 256);
+  g_defer.high += need;  // what a large enough arena would have held (vitb_defer_used)
+  if (g_defer.used + need > g_defer.cap) return nullptr;
+  void* p = g_defer.arena + g_defer.used;
+  g_defer.used += need;
+  return p;
+}
+void defer_add(const float* src, int nparts, int64_t cols, float* dst) {
+  ReduceJob j = {src, dst, nparts, (int)cols};
+  (finalize_is_tall(nparts, cols) ? g_defer.tall : g_defer.plain).push_back(j);
+}
+
+// block (32, 8): the plain fixed-order pass of common.cuh for the job that owns this block
+__global__ void __launch_bounds__(256) reduce_jobs_plain_kernel(const ReduceBatch b) {
+  pdl_trigger();
+  pdl_wait();
+  int j = 0;
+  while (j + 1 < b.njobs && (int)blockIdx.x >= b.block_start[j + 1]) ++j;
+  const ReduceJob& job = b.jobs[j];
+  finalize_block_cols(job.src, job.nparts, job.cols, job.dst, (int)blockIdx.x - b.block_start[j], b.block_start[j + 1] - b.block_start[j]);
+}
+// block (8, 64): the tall pass
+__global__ void __launch_bounds__(512) reduce_jobs_tall_kernel(const ReduceBatch b) {
+  pdl_trigger();
+  pdl_wait();
+  int j = 0;
+  while (j + 1 < b.njobs && (int)blockIdx.x >= b.block_start[j + 1]) ++j;
+  const ReduceJob& job = b.jobs[j];
+  finalize_tall_block(job.src, job.nparts, job.cols, job.dst, (int)blockIdx.x - b.block_start[j]);
+}
+
+static int flush_jobs(const std::vector<ReduceJob>& jobs, bool tall, cudaStream_t st) {
+  for (size_t i0 = 0; i0 < jobs.size(); i0 += kMaxReduceJobs) {
+    ReduceBatch b = {};
+    const size_t n = jobs.size() - i0 < (size_t)kMaxReduceJobs ? jobs.size() - i0 : (size_t)kMaxReduceJobs;
+    b.njobs = (int)n;
+    int blocks = 0;
+    for (size_t i = 0; i < n; ++i) {
+      b.jobs[i] = jobs[i0 + i];
+      b.block_start[i] = blocks;
+      blocks += tall ? (b.jobs[i].cols + 31) / 32 : (b.jobs[i].cols + 127) / 128;
+    }
+    b.block_start[n] = blocks;
+    if (tall) VITB_LAUNCH((reduce_jobs_tall_kernel), blocks, dim3(8, 64), 0, st, b);
+    else VITB_LAUNCH((reduce_jobs_plain_kernel), blocks, dim3(32, 8), 0, st, b);
+    VITB_LAUNCH_OK();
+  }
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // cast
@@ -370,10 +434,7 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
     float* w8 = colsum != nullptr ? (float*)ws : nullptr;
     VITB_LAUNCH((gelu_bwd_bf16x8_kernel), gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st, (const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
     VITB_LAUNCH_OK();
-    if (colsum != nullptr) {
-      (void)::vitb::launch_finalize(w8, gx8, cols, colsum, nullptr, nullptr, 1, st);
-      VITB_LAUNCH_OK();
-    }
+    if (colsum != nullptr) VITB_CUDA_OK(::vitb::launch_finalize(w8, gx8, cols, colsum, nullptr, nullptr, 1, st));
     return 0;
   }
   float* wsf = nullptr;
@@ -388,10 +449,7 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
   else
     VITB_LAUNCH((rows_colsum_kernel<T, false>), grid, block, 0, st, (const T*)a, nullptr, nullptr, wsf, rows, cols);
   VITB_LAUNCH_OK();
-  if (colsum != nullptr) {
-    (void)::vitb::launch_finalize(wsf, g.gx, cols, colsum, nullptr, nullptr, 1, st);
-    VITB_LAUNCH_OK();
-  }
+  if (colsum != nullptr) VITB_CUDA_OK(::vitb::launch_finalize(wsf, g.gx, cols, colsum, nullptr, nullptr, 1, st));
   return 0;
 }
 
@@ -656,6 +714,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   VITB_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && ws, "layernorm_bwd: null pointer");
   VITB_REQUIRE(rows > 0 && H % 128 == 0 && xs % 4 == 0 && dxs % 4 == 0, "layernorm_bwd: bad shape");
   VITB_REQUIRE(ws_bytes >= vitb_layernorm_bwd_ws_bytes(rows, H), "layernorm_bwd: workspace too small");
+  if (void* d = defer_alloc(vitb_layernorm_bwd_ws_bytes(rows, H))) ws = d;  // deferred second pass: the partials must outlive this call
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = ln_bwd_blocks(rows);
   const bool res = dres != nullptr, cs = dx_colsum != nullptr;
@@ -671,8 +730,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   }
 #undef VITB_LN_BWD
   VITB_LAUNCH_OK();
-  (void)::vitb::launch_finalize((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum, 3, st);
-  VITB_LAUNCH_OK();
+  VITB_CUDA_OK(::vitb::launch_finalize((const float*)ws, blocks, H, dgamma, dbeta, dx_colsum, 3, st));
   return 0;
 }
 
@@ -687,6 +745,8 @@ size_t vitb_colsum_ws_bytes(int rows, int cols) {
 int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes,
                          int rows, int cols, int dt, void* stream) {
   VITB_REQUIRE(dy && z && dz && rows > 0, "gelu_bwd: null pointer / empty");
+  if (colsum != nullptr)
+    if (void* d = defer_alloc(vitb_colsum_ws_bytes(rows, cols))) { ws = d; ws_bytes = vitb_colsum_ws_bytes(rows, cols); }
   if (dt == VITB_BF16) return launch_rows_colsum<bf16>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
   return launch_rows_colsum<float>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
 }
@@ -696,6 +756,25 @@ int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int row
   if (dt == VITB_BF16) return launch_rows_colsum<bf16>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
   return launch_rows_colsum<float>(false, x, nullptr, nullptr, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
 }
+
+int vitb_defer_begin(void* arena, size_t arena_bytes) {
+  VITB_REQUIRE(arena != nullptr && arena_bytes >= 256 && (uintptr_t)arena % 256 == 0, "defer_begin: need a 256-byte aligned device arena");
+  // (a begin without a flush — an exception between the two on the host — simply starts over: nothing was launched for the dropped jobs)
+  g_defer.arena = (char*)arena; g_defer.cap = arena_bytes; g_defer.used = 0; g_defer.high = 0; g_defer.active = true;
+  g_defer.plain.clear(); g_defer.tall.clear();
+  return 0;
+}
+
+int vitb_defer_flush(void* stream) {
+  VITB_REQUIRE(g_defer.active, "defer_flush: vitb_defer_begin has not been called");
+  g_defer.active = false;
+  int rc = flush_jobs(g_defer.plain, false, (cudaStream_t)stream);
+  if (rc == 0) rc = flush_jobs(g_defer.tall, true, (cudaStream_t)stream);
+  g_defer.plain.clear(); g_defer.tall.clear();
+  return rc;
+}
+
+size_t vitb_defer_used(void) { return g_defer.high; }
 
 int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip, const float* mean3,
                                      const float* std3, float* out, int B, int S, int pad, void* stream) {

@@ -32,11 +32,6 @@ int simt_pick_splits(int tiles, int K);
 int make_tma_map_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                          uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes);
 
-// EXPERIMENTAL resident-weight GEMM with the weight block in tensor memory (gemm_ts.cu; selected by VITB_GEMM_TS=1 only)
-bool ts_gemm_ok(int M, int Nout, int Kred);
-int ts_gemm_launch(int mode, const void* a, const void* w, const float* bias, const void* in, void* out, void* pre, int M, int Nout, int Kred, int gelu,
-                   bool w_mn_major, cudaStream_t st);
-
 // classifier head (head.cu): N = num_classes <= 128, fp32 logits / dlogits, activations and weight in `dt`
 bool head_shape_ok(int M, int N, int K);
 int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st);

@@ -852,28 +852,16 @@ static bool use_resident_weights(const TcArgs& a) {
   return a.num_m_blocks >= 2 * members;  // enough row blocks per CTA to amortise loading the weight block
 }
 
-// cta_group::2 pairs for the resident-weight kernels: EXPERIMENTAL, off unless tools switch it on.  Correct on 256-row-aligned M
-// (parity with the single-CTA path) and as fast as it (fwd 66560x384x384: 26.1 vs 26.3 us) — the fourth ring stage it buys does not
-// help because these kernels are bound by L2->SM bandwidth, not ring latency.  It still deadlocks when the last
-// pair's peer tile lies entirely beyond M — hence the M % 256 restriction.  profiles/r1_gemm_timeline_cta_pair_experiment.log
-static int g_tc_pair = 0;
-// pair mode needs the resident plan and at least two 256-row blocks per pair
-static bool use_pair(const TcArgs& a, int M) {
-  if (!g_tc_pair || M % (2 * BM) != 0 || !use_resident_weights(a) || a.num_n_blocks > kNumSMs / 2) return false;
-  const int members = (kNumSMs / 2) / a.num_n_blocks;
-  return ceil_div(M, 2 * BM) >= 2 * members;
-}
-
+// cta_group::2 pairs (CG = 2) for the resident-weight kernels were an experiment of round 1: parity-correct on 256-row-aligned M and
+// exactly as fast as the single-CTA kernel (fwd 66560x384x384: 26.1 vs 26.3 us, profiles/r1_gemm_timeline_cta_pair_experiment.log),
+// with an unresolved deadlock when the last pair's peer tile lies entirely beyond M.  The kernel template keeps its CG parameter
+// (the barrier / multicast-commit plumbing is the starting point for full-width tiles), but the library instantiates CG = 1 only:
+// no code ships that the GPU test suite does not run.
 // The smem rings get whatever the resident weights and the epilogue slabs leave free (227 KB per CTA):
 //   slabs per epilogue warp = 1 (output, shared with the input operand) + pre-activation;  0 = fp32 direct-store epilogue (wgrad)
 //   <NS, STAGES, KPS> dual stream: wgrad 2 x 3 x 32 KB;  resident 2 x 3 x 16 KB (2 x 2 with a pre-activation slab);
 //   streaming 2 x 3 x 32 KB (2 x 2 x 32 KB).   g_tc_streams = 1 (tools) selects the single-stream plans.
 static int g_tc_streams = 2;
-// VITB_GEMM_TS=1: route the resident-weight shapes to the experimental TMEM-resident kernel (gemm_ts.cu); default off
-static bool ts_enabled() {
-  static const bool on = getenv("VITB_GEMM_TS") && atoi(getenv("VITB_GEMM_TS")) != 0;
-  return on;
-}
 static int g_tc_wgrad_bn = 192;  // wgrad tile width; tools can force 128
 
 template <int BN, bool A_MN, bool B_MN>
@@ -899,12 +887,6 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
     return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, false>(m, args, st);
   }
   if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 0, false>(m, args, st);
-  if constexpr (!A_MN) {
-    if (res && args.pair) {  // cta_group::2 pairs: half the resident weights per CTA -> 4 ring stages per stream (3 with a pre-activation slab)
-      if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 2, true, 2>(m, args, st);
-      return launch_tc_impl<BN, A_MN, B_MN, 2, 4, 1, 1, true, 2>(m, args, st);
-    }
-  }
   if (res) {
     if (args.has_pre) return launch_tc_impl<BN, A_MN, B_MN, 2, 2, 1, 2, true>(m, args, st);
     return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, true>(m, args, st);
@@ -981,9 +963,7 @@ int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias,
   int rc = launch_tc<kBN, true, true>(m, t, st);
   if (rc) return rc;
   const int64_t n = (int64_t)H * K;
-  const unsigned nb = (unsigned)((n + 127) / 128 + (H + 127) / 128);
-  VITB_LAUNCH((partials_finalize2_kernel<0>), nb, finalize_block(), 0, st, part, n, dw, bpart, H, dbias, splits);
-  VITB_LAUNCH_OK();
+  VITB_CUDA_OK(::vitb::launch_finalize2(part, n, dw, bpart, H, dbias, splits, st));
   return 0;
 }
 
@@ -1005,7 +985,6 @@ int vitb_debug_gemm_timeline(long long* dbg, int mode) {
   g_tc_force_mode = mode & 0xf;
   g_tc_streams = (mode & 0x10) ? 1 : 2;
   g_tc_wgrad_bn = (mode & 0x20) ? 128 : 192;
-  g_tc_pair = (mode & 0x40) ? 1 : 0;
   g_tc_dbg_flags = mode >> 8;
   return 0;
 }
@@ -1019,8 +998,6 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
   EpiParams e = {};
   e.mode = EPI_FWD; e.gelu = (flags & VITB_GEMM_GELU) ? 1 : 0; e.out_f32 = (flags & VITB_GEMM_OUT_F32) ? 1 : 0;
   e.bias = bias; e.residual = residual; e.out = c; e.preact = preact; e.ldc = N;
-  if (dt == VITB_BF16 && !e.out_f32 && ts_enabled() && ts_gemm_ok(M, N, K))  // experimental: weight block in tensor memory
-    return ts_gemm_launch(EPI_FWD, a, w, bias, residual, c, preact, M, N, K, e.gelu, false, st);
   if (dt == VITB_BF16 && tc_shape_ok(M, N, K) && !e.out_f32) {
     TcMaps m;
     if (make_map(&m.a, a, K, M, K, BM)) return -1;
@@ -1033,11 +1010,6 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = N;
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
-    if (use_pair(t, M)) {
-      t.pair = 1;
-      t.num_m_blocks = ceil_div(M, 2 * BM);
-      if (make_map(&m.b, w, K, N, K, kBN / 2)) return -1;  // each CTA of a pair loads half of the weight block's rows
-    }
     return launch_tc<kBN, false, false>(m, t, st);
   }
   if (e.out_f32 && !e.gelu && !residual && !preact && head_shape_ok(M, N, K)) return head_fwd_launch(a, w, bias, (float*)c, M, N, K, dt, st);
@@ -1056,8 +1028,6 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
   EpiParams e = {};
   e.mode = EPI_DGRAD; e.out = dx; e.aux = z; e.ldc = K;
   // GEMM view: C[M, K] = dY[M, N] (K-major, reduction N) x W[N, K] (MN-major: reduction over rows)
-  if (dt == VITB_BF16 && !dy_f32 && ts_enabled() && ts_gemm_ok(M, K, N))
-    return ts_gemm_launch(EPI_DGRAD, dy, w, nullptr, z, dx, nullptr, M, K, N, 0, true, st);
   if (dt == VITB_BF16 && !dy_f32 && tc_shape_ok(M, K, N)) {
     TcMaps m;
     if (make_map(&m.a, dy, N, M, N, BM)) return -1;
@@ -1069,10 +1039,6 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(N, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = K;
     t.has_in = z != nullptr;
-    if (use_pair(t, M)) {  // (the MN-major weight boxes are 64 columns wide already: one per CTA of a pair)
-      t.pair = 1;
-      t.num_m_blocks = ceil_div(M, 2 * BM);
-    }
     return launch_tc<kBN, false, true>(m, t, st);
   }
   if (dy_f32 && !z && head_shape_ok(M, N, K)) return head_dgrad_launch((const float*)dy, w, dx, M, N, K, dt, st);
@@ -1137,6 +1103,8 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   cudaStream_t st = (cudaStream_t)stream;
   const int dy_dt = (flags & VITB_GEMM_DY_F32) ? VITB_F32 : dt;
   int splits;
+  if (wgrad_tc_ok(N, K, flags, dt))  // deferred second pass (vitb_defer_begin): the partials live in the arena until the flush
+    if (void* d = defer_alloc(vitb_gemm_wgrad_ws_bytes(M, N, K, dt))) ws = d;
   float* part = (float*)ws;
   if (wgrad_tc_ok(N, K, flags, dt)) {
     int kb_total, kb_per;
@@ -1158,13 +1126,8 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
     if (rc) return rc;
     if (splits > 1) {
       const int64_t n = (int64_t)N * K;
-      if (dbias) {  // dW and the bias gradient in one launch
-        const unsigned nb = (unsigned)((n + 127) / 128 + (N + 127) / 128);
-        VITB_LAUNCH((partials_finalize2_kernel<0>), nb, finalize_block(), 0, st, part, n, dw, bpart, N, dbias, splits);
-      } else {
-        (void)::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st);
-      }
-      VITB_LAUNCH_OK();
+      if (dbias) VITB_CUDA_OK(::vitb::launch_finalize2(part, n, dw, bpart, N, dbias, splits, st));  // dW and the bias gradient in one launch
+      else VITB_CUDA_OK(::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st));
     }
     return 0;
   }
@@ -1181,8 +1144,7 @@ int vitb_gemm_wgrad_dbias(const void* dy, const void* x, float* dw, float* dbias
   }
   if (splits > 1) {
     const int64_t n = (int64_t)N * K;
-    (void)::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st);
-    VITB_LAUNCH_OK();
+    VITB_CUDA_OK(::vitb::launch_finalize(part, splits, n, dw, nullptr, nullptr, 1, st));
   }
   if (dbias != nullptr) {
     if (N % 128 == 0) {

@@ -160,6 +160,20 @@ class TrainEngine:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._comm_stream = torch.cuda.Stream(device=self.dev) if self.overlap_comm else None
         self.launches_per_step = 0  # filled by the first (eager) step
+        # Deferred second passes of the split reductions (one flush launch before the optimiser instead of ~7 per layer) and weight
+        # gradients on a second stream (they are off the critical path of backward).  Both need every wgrad / LayerNorm-backward
+        # call to own its partial-sum workspace: an arena sized from the library's workspace queries.  bf16 path only; with
+        # per-layer NCCL buckets ("overlap") the gradients must be final layer by layer, so neither applies there.
+        self._defer = (self.act == torch.bfloat16 and not self.overlap_comm and os.environ.get("VITB_DEFER", "1") != "0")
+        self._arena = torch.empty(self._arena_bytes(), dtype=torch.uint8, device=self.dev) if self._defer else None
+        self.defer_bytes_used = 0
+        ws_mode = int(os.environ.get("VITB_WGRAD_STREAM", "1")) if self._defer else 0
+        self._side = None
+        self._main_stream = None
+        if ws_mode >= 1:
+            if ws_mode >= 2:  # critical path on a high-priority stream: its pending CTAs get the SMs first
+                self._main_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._side = Fn.SideStream(torch.cuda.Stream(device=self.dev))
 
     # -- static buffers ---------------------------------------------------------------------------
     def _alloc(self, scope: str):
@@ -172,6 +186,17 @@ class TrainEngine:
                 self._bufs[key] = t
             return t
         return alloc
+
+    def _arena_bytes(self) -> int:
+        from . import _lib
+        lib, dm, m = _lib.load(), self.dm, self.model
+        rows, H, M = dm.rows, dm.H, dm.M
+        ln = int(lib.vitb_layernorm_bwd_ws_bytes(rows, H))
+        per_layer = ops.wgrad_ws_bytes(rows, H, H) + ops.wgrad_ws_bytes(rows, 3 * H, H) + ln
+        if dm.use_mlp:
+            per_layer += ops.wgrad_ws_bytes(rows, H, M) + ops.wgrad_ws_bytes(rows, M, H) + ln + int(lib.vitb_colsum_ws_bytes(rows, H))
+        per_layer += 8 * 256  # alignment of every piece
+        return m.num_layers * per_layer + int(lib.vitb_layernorm_bwd_ws_bytes(self.B, H)) + (1 << 20)
 
     def activation_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -206,20 +231,7 @@ class TrainEngine:
         else:
             ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, n_valid_dev=n_valid_dev)
 
-        g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
-        dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
-                         self._alloc("headb"), dx_prezeroed=True)
-        self._allreduce(self.buckets[-1])
-        for i in reversed(range(m.num_layers)):
-            # backward scratch is shared by all layers; the input-gradient buffer ping-pongs
-            dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i),
-                                drop=self.drops[i] if self.drops else None)
-            self._allreduce(self.buckets[1 + i])
-        g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
-        Fn.stem_bwd(self.img, words, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
-        self._allreduce(self.buckets[0], last=True)
-        if self._comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._backward(hsaved, saved, words)
         n = self.n
         if self._fused_dp is not None:
             f = self._fused_dp
@@ -230,9 +242,57 @@ class TrainEngine:
         else:
             ops.sgd(self.P[:n], self.G[:n], self.Mo[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
 
+    def _backward(self, hsaved, saved, words) -> None:
+        m, dm = self.model, self.dm
+        B, T, H, Cn = self.B, m.num_tokens, m.hidden, m.num_classes
+        ln_w, ln_b, fc_w_c, fc_b = self.head_p
+        if self._main_stream is not None:  # run the critical path on the high-priority stream
+            outer = torch.cuda.current_stream()
+            self._main_stream.wait_stream(outer)
+            with torch.cuda.stream(self._main_stream):
+                self._backward_kernels(hsaved, saved, words, B, T, H, Cn, ln_w, fc_w_c)
+            outer.wait_stream(self._main_stream)
+        else:
+            self._backward_kernels(hsaved, saved, words, B, T, H, Cn, ln_w, fc_w_c)
+
+    def _backward_kernels(self, hsaved, saved, words, B, T, H, Cn, ln_w, fc_w_c) -> None:
+        m, dm, side = self.model, self.dm, self._side
+        if self._defer:
+            ops.defer_begin(self._arena)
+        g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
+        dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
+                         self._alloc("headb"), dx_prezeroed=True)
+        self._allreduce(self.buckets[-1])
+        done = {}
+        for i in reversed(range(m.num_layers)):
+            # backward scratch ping-pongs between two sets; with weight gradients on the side stream a set may only be rewritten
+            # once the side-stream kernels of the layer that used it last (i + 2) have read it
+            if side is not None and (i + 2) in done:
+                torch.cuda.current_stream().wait_event(done[i + 2])
+            dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i),
+                                drop=self.drops[i] if self.drops else None, side=side)
+            if side is not None:
+                done[i] = side.done_event()
+            self._allreduce(self.buckets[1 + i])
+        g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
+        Fn.stem_bwd(self.img, words, dx, g_emb_w, g_emb_b, g_cls, g_pos, m.patch)
+        if side is not None:
+            side.join()
+        if self._defer:
+            ops.defer_flush()
+            used = ops.defer_used()
+            if used > self._arena.numel():
+                raise RuntimeError(f"deferred-reduction arena too small ({self._arena.numel()} < {used} bytes): engine sizing bug")
+            self.defer_bytes_used = used
+        self._allreduce(self.buckets[0], last=True)
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+
     def _bwd_alloc(self, i: int):
         shared = self._alloc("bwd")
         pp = self._alloc(f"bwd{i & 1}")
+        if self._side is not None:  # everything ping-pongs: side-stream wgrads of layer i + 1 still read that layer's scratch
+            return pp
 
         def alloc(name: str, shape: tuple, dtype: torch.dtype) -> torch.Tensor:
             return pp(name, shape, dtype) if name == "dx" else shared(name, shape, dtype)

@@ -58,6 +58,36 @@ class Dims:
             raise ValueError(f"mlp_hidden={self.M} must be a multiple of 128")
 
 
+class SideStream:
+    """Weight-gradient GEMMs are off the backward pass's critical path (nothing reads dW before the optimiser): `run(fn)` issues
+    fn's kernels on a second stream once everything issued so far on the current stream has been ordered before them, so they
+    fill the SMs that the tails / prologues of the critical-path kernels leave idle.  The caller joins with `join()` before the
+    gradients are read and keeps every buffer such a kernel reads untouched until then (or until `done_event()` of that point)."""
+
+    def __init__(self, stream: "torch.cuda.Stream"):
+        self.stream = stream
+
+    def run(self, fn) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+
+    def done_event(self) -> "torch.cuda.Event":
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def join(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def _wgrad(side: Optional["SideStream"], *args, **kw) -> None:
+    if side is None:
+        ops.gemm_wgrad(*args, **kw)
+    else:
+        side.run(lambda: ops.gemm_wgrad(*args, **kw))
+
+
 @dataclass
 class Drop:
     """Training-mode nn.Dropout(p) of one encoder block (layers.py:35, 38, 102).  Its three sites (0: after out_project, 1: after the
@@ -94,7 +124,7 @@ def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: All
 
 
 def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc, bo_done: bool = False,
-             drop: Optional[Drop] = None):
+             drop: Optional[Drop] = None, side: Optional[SideStream] = None):
     """dy (rows,H) = grad of the block's attention branch output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x."""
     x, qkv, o, lse = saved
     rows, H, act = dm.rows, dm.H, dy.dtype
@@ -102,12 +132,12 @@ def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, al
         dya = alloc("dao", (rows, H), act)
         drop(dy, None, dya, 0)
         dy = dya
-    ops.gemm_wgrad(dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
+    _wgrad(side, dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
     do = alloc("do", (rows, H), act)
     ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
     dqkv = alloc("dqkv", (rows, 3 * H), act)
     ops.attn_bwd(qkv, o, do, lse, dqkv, dm.B, dm.T, dm.heads, dm.d, dm.scale)
-    ops.gemm_wgrad(dqkv, x, g.wqkv, g.bqkv, rows, 3 * H, H)
+    _wgrad(side, dqkv, x, g.wqkv, g.bqkv, rows, 3 * H, H)
     dx = alloc("dxn", (rows, H), act)
     ops.gemm_dgrad(dqkv, c.wqkv, None, dx, rows, 3 * H, H)
     return dx
@@ -145,7 +175,7 @@ def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: 
 
 
 def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc,
-                drop: Optional[Drop] = None):
+                drop: Optional[Drop] = None, side: Optional[SideStream] = None):
     """dout = grad of the block output; fills every field of g; returns grad of the block input.  `drop`: the same Drop the
     forward ran with (masks are regenerated, not stored)."""
     x, mean1, rstd1, att_saved, mlp_saved = saved
@@ -158,12 +188,12 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
             dg2 = alloc("dg2", (rows, H), act)
             drop(dout, None, dg2, 2)                                     # mlp[5] backward
         ops.gelu_bwd_colsum(dg2, z2, dz2, g.b2, rows, H)                 # second GELU (layers.py:37) + db2
-        ops.gemm_wgrad(dz2, a1, g.w2, None, rows, H, M)
+        _wgrad(side, dz2, a1, g.w2, None, rows, H, M)
         dz1 = alloc("dz1", (rows, M), act)
         ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)                   # first GELU's backward fused in the epilogue
         if drop is not None:
             drop(dz1, None, dz1, 1)                                      # mlp[2] backward (mask and gelu' commute)
-        ops.gemm_wgrad(dz1, x1n, g.w1, g.b1, rows, M, H)
+        _wgrad(side, dz1, x1n, g.w1, g.b1, rows, M, H)
         dx1n = alloc("dx1n", (rows, H), act)
         ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
         dx1 = alloc("dx1", (rows, H), act)
@@ -174,7 +204,7 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
     else:
         dx1 = dout
         bo_done = False
-    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done, drop=drop)
+    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done, drop=drop, side=side)
     dx = alloc("dx", (rows, H), act)
     ops.layernorm_bwd(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, None, rows, H)
     return dx

@@ -245,6 +245,24 @@ def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1
                                              B, Cn, smoothing, grad_scale, _stream()), "ls_ce_mix_fwd_bwd")
 
 
+def defer_begin(arena: torch.Tensor) -> None:
+    """From here to defer_flush() the second passes of wgrad / LayerNorm-backward / GELU-backward reductions are postponed: their
+    partials go into `arena` (uint8 CUDA tensor that must stay alive and untouched until the flush has executed)."""
+    check(_lib.load().vitb_defer_begin(_ptr(arena), arena.numel()), "defer_begin")
+
+
+def defer_flush() -> None:
+    check(_lib.load().vitb_defer_flush(_stream()), "defer_flush")
+
+
+def defer_used() -> int:
+    return int(_lib.load().vitb_defer_used())
+
+
+def wgrad_ws_bytes(M: int, N: int, K: int, dt: int = BF16) -> int:
+    return int(_lib.load().vitb_gemm_wgrad_ws_bytes(M, N, K, dt))
+
+
 _HyperArr = C.c_float * 16
 
 
