@@ -184,6 +184,16 @@ int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const
                              const float* lam_dev, const int* n_valid_dev, float* loss, float* dlogits, int B, int C,
                              float smoothing, float grad_scale, void* stream);
 
+/* ---- backward of one nn.Linear y = x W^T (W: [N, K] bf16) in a single pass over dY — what autograd runs as two GEMMs
+ * (layers.py:33-37, 85, 102):  dx [M, K] = dy [M, N] W  (times gelu'(z) when z [M, K] != NULL: the Linear's input was GELU(z),
+ * layers.py:34);  dw [N, K] fp32 = dy^T x;  dx_colsum [K] fp32 (may be NULL) = column sums of dx as stored, i.e. the bias gradient
+ * of the Linear that produced z.  dy is read from HBM once and feeds both tensor-core products from the same shared-memory
+ * bytes (csrc/gemm_bwd_fused.cuh).  bf16 only, N in {128, 256, 384}, K a multiple of 128: vitb_gemm_bwd_fused_ws_bytes returns 0
+ * for anything else and the caller uses vitb_gemm_dgrad + vitb_gemm_wgrad_dbias.  ws: fp32 partials (honours vitb_defer_begin). ---- */
+size_t vitb_gemm_bwd_fused_ws_bytes(int M, int N, int K, int dt);
+int vitb_gemm_bwd_fused(const void* dy, const void* x, const void* w, const void* z, void* dx, float* dw, float* dx_colsum,
+                        void* ws, size_t ws_bytes, int M, int N, int K, int dt, void* stream);
+
 /* ---- deferred second passes of split reductions.  Every gradient that is a sum over the batch rows (wgrad dW / db, LayerNorm
  * dgamma / dbeta and the column sums that are a Linear's bias gradient, GELU-backward column sums) is computed as per-CTA fp32
  * partials followed by a fixed-order second pass.  Between vitb_defer_begin and vitb_defer_flush (same host thread) the calls

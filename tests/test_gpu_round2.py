@@ -173,6 +173,47 @@ def test_gemm_wgrad_benchmark_shapes(ops, M, N, K):
     assert rel(db, dy.float().sum(0)) < 1e-3
 
 
+# (rows, N = width of dY = rows of W, K = width of X / dX): ragged and aligned row counts, all three N, the benchmark shapes
+FUSED_SHAPES = [(260, 128, 128), (1000, 384, 384), (1040, 256, 384), (128, 384, 128), (77, 128, 256), (8320, 384, 384), (20000, 384, 384),
+                (66560, 384, 384), (17408, 384, 384)]
+
+
+@pytest.mark.parametrize("M,N,K", FUSED_SHAPES)
+@pytest.mark.parametrize("with_z", [False, True])
+def test_gemm_bwd_fused_vs_fp32_products(ops, M, N, K, with_z):
+    """One-pass backward of a Linear (dgrad + wgrad from the same shared-memory tiles of dY) against fp32 products of the same
+    bf16 operands; the column sums must equal the sums of the bf16 dX the kernel stored (they are a bias gradient)."""
+    assert ops.bwd_fused_ws_bytes(M, N, K) > 0
+    dy = rnd_cuda((M, N), 1); w = rnd_cuda((N, K), 2, 1 / math.sqrt(N)); x = rnd_cuda((M, K), 3); z = rnd_cuda((M, K), 4)
+    ref_dx = mm32(dy, w)
+    if with_z:
+        zz = z.float().requires_grad_(True)
+        F.gelu(zz).sum().backward()
+        ref_dx = ref_dx * zz.grad
+    dx = torch.full((M, K), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dw = torch.full((N, K), float("nan"), dtype=torch.float32, device="cuda")
+    cs = torch.full((K,), float("nan"), dtype=torch.float32, device="cuda")
+    ops.gemm_bwd_fused(dy, x, w, z if with_z else None, dx, dw, cs, M, N, K)
+    assert rel(dx, ref_dx) < 2e-2
+    assert rel(dw, mm32(dy.t(), x)) < 1e-3
+    assert rel(cs, dx.float().sum(0)) < 1e-3
+    # deterministic (fixed-order reductions), and identical to the two-kernel path for dX
+    dx2 = torch.empty_like(dx); dw2 = torch.empty_like(dw)
+    ops.gemm_bwd_fused(dy, x, w, z if with_z else None, dx2, dw2, None, M, N, K)
+    assert torch.equal(dx, dx2) and torch.equal(dw, dw2)
+    dx3 = torch.empty_like(dx)
+    ops.gemm_dgrad(dy, w, z if with_z else None, dx3, M, N, K)
+    assert rel(dx3, dx) < 1e-2
+
+
+def test_gemm_bwd_fused_unsupported_shapes_are_reported(ops):
+    assert ops.bwd_fused_ws_bytes(1024, 1152, 384) == 0   # QKV: the weight slice of a column block does not fit beside the rings
+    assert ops.bwd_fused_ws_bytes(1024, 768, 3072) == 0
+    assert ops.bwd_fused_ws_bytes(1024, 384, 100) == 0
+    from vit_cifar_b200._lib import F32
+    assert ops.bwd_fused_ws_bytes(1024, 384, 384, F32) == 0
+
+
 # ---------------------------------------------------------------------------------------------
 # (d) the fixed-size engine: partial batches, resume, weight reload
 # ---------------------------------------------------------------------------------------------

@@ -59,6 +59,8 @@ SIGNATURES = {
     "vitb_ls_ce_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_mix_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_batch_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _p, _i, _i, _f, _f, _p]),
+    "vitb_gemm_bwd_fused_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "vitb_gemm_bwd_fused": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
     "vitb_defer_begin": (_i, [_p, _sz]),
     "vitb_defer_flush": (_i, [_p]),
     "vitb_defer_used": (_sz, []),

@@ -969,9 +969,85 @@ int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias,
 
 }  // namespace vitb
 
+#include "gemm_bwd_fused.cuh"
+
 using namespace vitb;
 
+// ---------------------------------------------------------------------------------------------
+// fused backward of a Linear (gemm_bwd_fused.cuh): host side
+// ---------------------------------------------------------------------------------------------
+static bool bw_fused_shape_ok(int M, int N, int K) { return M >= 1 && N % 128 == 0 && N >= 128 && N <= 384 && K % 128 == 0 && K / 128 <= kNumSMs; }
+// CTAs per 128-column block of K: every SM gets one CTA, but no CTA without a row block
+static int bw_members(int M, int K) {
+  const int nb = K / 128, mblocks = ceil_div(M, BM);
+  int mem = kNumSMs / nb;
+  if (mem > mblocks) mem = mblocks;
+  return mem < 1 ? 1 : mem;
+}
+
+template <int NB>
+static int launch_bw_fused(const CUtensorMap& m_dy, const CUtensorMap& m_x, const CUtensorMap& m_w, const CUtensorMap& m_out, const CUtensorMap& m_in,
+                           const BwArgs& a, cudaStream_t st) {
+  using S = BwSmem<NB>;
+  static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
+  auto kern = gemm_bwd_fused_kernel<NB>;
+  static bool configured = false;
+  if (!configured) {
+    VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
+    configured = true;
+  }
+  VITB_LAUNCH((kern), (a.K / 128) * a.members, 384, S::kDynBytes, st, m_dy, m_x, m_w, m_out, m_in, a);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" {
+
+size_t vitb_gemm_bwd_fused_ws_bytes(int M, int N, int K, int dt) {
+  if (dt != VITB_BF16 || !bw_fused_shape_ok(M, N, K)) return 0;
+  const size_t mem = (size_t)bw_members(M, K);
+  return align_up(mem * N * K * sizeof(float), 256) + align_up(mem * 4 * K * sizeof(float), 256) + 256;
+}
+
+int vitb_gemm_bwd_fused(const void* dy, const void* x, const void* w, const void* z, void* dx, float* dw, float* dx_colsum, void* ws, size_t ws_bytes,
+                        int M, int N, int K, int dt, void* stream) {
+  VITB_REQUIRE(dy && x && w && dx && dw && ws, "gemm_bwd_fused: null pointer");
+  const size_t need = vitb_gemm_bwd_fused_ws_bytes(M, N, K, dt);
+  VITB_REQUIRE(need != 0, "gemm_bwd_fused: no fused kernel for M=%d N=%d K=%d dt=%d (bf16, N in {128, 256, 384}, K a multiple of 128): use dgrad + wgrad", M,
+               N, K, dt);
+  VITB_REQUIRE(ws_bytes >= need, "gemm_bwd_fused: workspace too small (%zu < %zu)", ws_bytes, need);
+  if (void* d = defer_alloc(need)) ws = d;  // deferred second pass: the partials live in the arena until vitb_defer_flush
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap m_dy, m_x, m_w, m_out, m_in;
+  if (make_map(&m_dy, dy, N, M, N, BM)) return -1;   // boxes of 64 columns x 128 rows
+  if (make_map(&m_x, x, K, M, K, 64)) return -1;     // 64 x 64
+  if (make_map(&m_w, w, K, N, K, 64)) return -1;     // 64 output columns x 64 reduction rows
+  if (make_map(&m_out, dx, K, M, K, 32)) return -1;  // epilogue slabs: 64 x 32
+  m_in = m_out;
+  if (z && make_map(&m_in, z, K, M, K, 32)) return -1;
+  BwArgs a = {};
+  a.M = M; a.N = N; a.K = K;
+  a.num_m_blocks = ceil_div(M, BM);
+  a.members = bw_members(M, K);
+  a.has_in = z != nullptr;
+  a.dw_part = (float*)ws;
+  a.csum_part = dx_colsum ? (float*)((char*)ws + align_up((size_t)a.members * N * K * sizeof(float), 256)) : nullptr;
+  a.pf_tiles = g_tc_pf_tiles;
+  int rc;
+  switch (N / 128) {
+    case 1: rc = launch_bw_fused<1>(m_dy, m_x, m_w, m_out, m_in, a, st); break;
+    case 2: rc = launch_bw_fused<2>(m_dy, m_x, m_w, m_out, m_in, a, st); break;
+    default: rc = launch_bw_fused<3>(m_dy, m_x, m_w, m_out, m_in, a, st); break;
+  }
+  if (rc) return rc;
+  if (a.members > 1) {
+    VITB_CUDA_OK(::vitb::launch_finalize(a.dw_part, a.members, (int64_t)N * K, dw, nullptr, nullptr, 1, st));
+  } else {
+    VITB_CUDA_OK(cudaMemcpyAsync(dw, a.dw_part, (size_t)N * K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  if (dx_colsum) VITB_CUDA_OK(::vitb::launch_finalize(a.csum_part, a.members * 4, K, dx_colsum, nullptr, nullptr, 1, st));
+  return 0;
+}
 
 /* tools only (not in vitb200.h): dbg = device buffer of 148*8 int64 cycle counters, or NULL; mode 0 auto / 1 streaming / 2 resident */
 int vitb_debug_gemm_prefetch(int tiles, int kblocks) {

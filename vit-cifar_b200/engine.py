@@ -192,9 +192,10 @@ class TrainEngine:
         lib, dm, m = _lib.load(), self.dm, self.model
         rows, H, M = dm.rows, dm.H, dm.M
         ln = int(lib.vitb_layernorm_bwd_ws_bytes(rows, H))
-        per_layer = ops.wgrad_ws_bytes(rows, H, H) + ops.wgrad_ws_bytes(rows, 3 * H, H) + ln
+        pair = lambda N, K: max(ops.wgrad_ws_bytes(rows, N, K), ops.bwd_fused_ws_bytes(rows, N, K))  # noqa: E731  (whichever path runs)
+        per_layer = pair(H, H) + ops.wgrad_ws_bytes(rows, 3 * H, H) + ln
         if dm.use_mlp:
-            per_layer += ops.wgrad_ws_bytes(rows, H, M) + ops.wgrad_ws_bytes(rows, M, H) + ln + int(lib.vitb_colsum_ws_bytes(rows, H))
+            per_layer += pair(H, M) + pair(M, H) + ln + int(lib.vitb_colsum_ws_bytes(rows, H))
         per_layer += 8 * 256  # alignment of every piece
         return m.num_layers * per_layer + int(lib.vitb_layernorm_bwd_ws_bytes(self.B, H)) + (1 << 20)
 

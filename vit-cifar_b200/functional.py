@@ -81,6 +81,14 @@ class SideStream:
         torch.cuda.current_stream().wait_stream(self.stream)
 
 
+def _bwd_fused_ok(rows: int, N: int, K: int, t: torch.Tensor) -> bool:
+    """The one-pass backward of a Linear (ops.gemm_bwd_fused) exists for this shape / dtype (bf16, N <= 384)."""
+    import os
+    if os.environ.get("VITB_BWD_FUSED", "1") == "0":
+        return False
+    return ops.bwd_fused_ws_bytes(rows, N, K, ops.dt_of(t)) > 0
+
+
 def _wgrad(side: Optional["SideStream"], *args, **kw) -> None:
     if side is None:
         ops.gemm_wgrad(*args, **kw)
@@ -132,9 +140,12 @@ def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, al
         dya = alloc("dao", (rows, H), act)
         drop(dy, None, dya, 0)
         dy = dya
-    _wgrad(side, dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
     do = alloc("do", (rows, H), act)
-    ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
+    if bo_done and _bwd_fused_ok(rows, H, H, dy):
+        ops.gemm_bwd_fused(dy, o, c.wo, None, do, g.wo, None, rows, H, H)            # out_project: dgrad + wgrad in one pass over dy
+    else:
+        _wgrad(side, dy, o, g.wo, None if bo_done else g.bo, rows, H, H)
+        ops.gemm_dgrad(dy, c.wo, None, do, rows, H, H)
     dqkv = alloc("dqkv", (rows, 3 * H), act)
     ops.attn_bwd(qkv, o, do, lse, dqkv, dm.B, dm.T, dm.heads, dm.d, dm.scale)
     _wgrad(side, dqkv, x, g.wqkv, g.bqkv, rows, 3 * H, H)
@@ -188,14 +199,23 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
             dg2 = alloc("dg2", (rows, H), act)
             drop(dout, None, dg2, 2)                                     # mlp[5] backward
         ops.gelu_bwd_colsum(dg2, z2, dz2, g.b2, rows, H)                 # second GELU (layers.py:37) + db2
-        _wgrad(side, dz2, a1, g.w2, None, rows, H, M)
         dz1 = alloc("dz1", (rows, M), act)
-        ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)                   # first GELU's backward fused in the epilogue
+        b1_done = False
+        if drop is None and _bwd_fused_ok(rows, H, M, dz2):
+            # mlp[3]: dgrad (first GELU's backward in the epilogue) + wgrad in one pass over dz2; the column sums of dz1 are db1
+            ops.gemm_bwd_fused(dz2, a1, c.w2, z1, dz1, g.w2, g.b1, rows, H, M)
+            b1_done = True
+        else:
+            _wgrad(side, dz2, a1, g.w2, None, rows, H, M)
+            ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)               # first GELU's backward fused in the epilogue
         if drop is not None:
             drop(dz1, None, dz1, 1)                                      # mlp[2] backward (mask and gelu' commute)
-        _wgrad(side, dz1, x1n, g.w1, g.b1, rows, M, H)
         dx1n = alloc("dx1n", (rows, H), act)
-        ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
+        if b1_done and _bwd_fused_ok(rows, M, H, dz1):
+            ops.gemm_bwd_fused(dz1, x1n, c.w1, None, dx1n, g.w1, None, rows, M, H)   # mlp[0]
+        else:
+            _wgrad(side, dz1, x1n, g.w1, None if b1_done else g.b1, rows, M, H)
+            ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
         dx1 = alloc("dx1", (rows, H), act)
         # grad of x1 = residual branch (dout) + LN2 backward; its column sums are out_project's bias grad
         # (with dropout the out_project output gradient is the MASKED dx1: its bias gradient then comes from the wgrad instead)

@@ -146,6 +146,21 @@ def gemm_wgrad(dy, x, dw, dbias, M: int, N: int, K: int, dy_f32: bool = False) -
           "gemm_wgrad_dbias")
 
 
+def bwd_fused_ws_bytes(M: int, N: int, K: int, dt: int = BF16) -> int:
+    """Workspace of gemm_bwd_fused, 0 when this shape / dtype has no fused kernel (use gemm_dgrad + gemm_wgrad)."""
+    return int(_lib.load().vitb_gemm_bwd_fused_ws_bytes(M, N, K, dt))
+
+
+def gemm_bwd_fused(dy, x, w_act, z, dx, dw, dx_colsum, M: int, N: int, K: int) -> None:
+    """Backward of y = x W^T in one pass over dy: dx = dy W (* gelu'(z)), dw = dy^T x, dx_colsum = column sums of dx (optional)."""
+    lib = _lib.load()
+    dt = dt_of(x)
+    nb = lib.vitb_gemm_bwd_fused_ws_bytes(M, N, K, dt)
+    ws = workspace(max(int(nb), 256), x.device)
+    check(lib.vitb_gemm_bwd_fused(_ptr(dy), _ptr(x), _ptr(w_act), _ptr(z), _ptr(dx), _ptr(dw), _ptr(dx_colsum), _ptr(ws), ws.numel(), M, N, K, dt,
+                                  _stream()), "gemm_bwd_fused")
+
+
 def attn_fwd(qkv, o, lse, attn_map, B: int, T: int, heads: int, d: int, scale: float) -> None:
     check(_lib.load().vitb_attn_fwd(_ptr(qkv), _ptr(o), _ptr(lse), _ptr(attn_map), B, T, heads, d, scale, dt_of(qkv), _stream()), "attn_fwd")
 
