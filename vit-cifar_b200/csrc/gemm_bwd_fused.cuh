@@ -12,10 +12,15 @@
 // load, tail) replaces two plus a split-K second pass per row block.  Tensor memory holds the dX tile (128 columns) and the CTA's
 // whole dW slice (N/128 accumulators of 128 columns, accumulated over all of its row blocks): 512 columns exactly at N = 384.
 //
-// Warps: 0 TMA producer, 1 dgrad MMA issuer, 2 wgrad MMA issuer (two issuing threads keep the pipe busy at this tile width,
-// see gemm_tc.cu), 3 idle, 4-11 epilogue (dX tiles through swizzled slabs and TMA stores as in gemm_tc_kernel; dW slice once at the end).
-// Shared memory: W block | dY ring: 2 stages of a 128-row x 128-column pair of 64-column sub-tiles (32 KB) | X ring: 2 stages of
-// 64 rows x 128 columns (16 KB) | 8 epilogue slabs | barriers.
+// Warps: 0 TMA producer of dY (and W), 1 dgrad MMA issuer, 2 wgrad MMA issuer (two issuing threads keep the pipe busy at this tile
+// width, see gemm_tc.cu), 3 TMA producer of X, 4-11 epilogue (dX tiles through swizzled slabs and TMA stores as in gemm_tc_kernel;
+// dW slice once at the end).
+// Shared memory (227 KB): W block 96 KB | dY ring: 2 stages of a 128-row x 128-column pair of 64-column sub-tiles (2 x 32 KB) |
+// X: 2 buffers of 128 rows x 128 columns (2 x 32 KB) | barriers.  X of a row block is live for the whole row block (every dY pair
+// multiplies it), so it must be double-buffered or the wgrad issuer waits a full load latency per row block (the first version
+// of this kernel, 12k cycles per row block against a 3k MMA floor); there is no room left for epilogue slabs, so the epilogue of
+// row block t stages its tile in the X buffer of row block t, which the wgrad MMAs have just finished reading, and hands the
+// buffer to the X producer (for row block t + 2) when its TMA store has read it.
 #pragma once
 
 namespace vitb {
@@ -33,15 +38,16 @@ template <int NB>  // N / 128
 struct BwSmem {
   static constexpr uint32_t kSub = 128 * 64 * 2;               // one 128-row x 64-column bf16 sub-tile (128B swizzle)
   static constexpr uint32_t kWBytes = 2 * NB * kSub;           // N/64 reduction blocks of [64 n-rows x 128 k-columns]
-  static constexpr int kDyStages = 2, kXStages = 2;
+  static constexpr int kDyStages = 2, kXBufs = 2;
   static constexpr uint32_t kDyStage = 2 * kSub;               // a pair: 128 rows x 128 columns of dY
-  static constexpr uint32_t kXStage = kSub;                    // 64 rows x 128 columns of X (two 64-column atoms of 64 rows)
+  static constexpr uint32_t kXHalf = kSub;                     // 64 rows x 128 columns of X (two 64-column atoms of 64 rows)
+  static constexpr uint32_t kXBuf = 2 * kXHalf;                // X of one row block; afterwards the 8 epilogue slabs of that row block
+  static_assert(kXBuf == kEpiWarps * kSlabBytes, "the epilogue slabs alias one X buffer exactly");
   static constexpr uint32_t kDyOff = kWBytes;
   static constexpr uint32_t kXOff = kDyOff + kDyStages * kDyStage;
-  static constexpr uint32_t kEpiOff = kXOff + kXStages * kXStage;
-  static constexpr uint32_t kBarOff = kEpiOff + kEpiWarps * kSlabBytes;
-  // dy_full[2] dy_empty[2] x_full[2] x_empty[2] tfull tempty wfull d2full in[8]
-  static constexpr uint32_t kNumBars = 2 * kDyStages + 2 * kXStages + 4 + kEpiWarps;
+  static constexpr uint32_t kBarOff = kXOff + kXBufs * kXBuf;
+  // dy_full[2] dy_empty[2] xb_full[2] xb_gdone[2] xb_free[2] tfull tempty wfull d2full in[8]
+  static constexpr uint32_t kNumBars = 2 * kDyStages + 3 * kXBufs + 4 + kEpiWarps;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr uint32_t kDynBytes = kTotal + 1024;
 };
@@ -59,14 +65,14 @@ __global__ void __launch_bounds__(384, 1)
 
   auto w_res = [&](int kb) { return smem_base + (uint32_t)kb * S::kSub; };          // reduction block kb of the resident W slice
   auto dy_stage = [&](int s) { return smem_base + S::kDyOff + (uint32_t)s * S::kDyStage; };
-  auto x_stage = [&](int s) { return smem_base + S::kXOff + (uint32_t)s * S::kXStage; };
-  const uint32_t epi_base = smem_base + S::kEpiOff;
+  auto x_buf = [&](int b) { return smem_base + S::kXOff + (uint32_t)b * S::kXBuf; };
   const uint32_t bar_base = smem_base + S::kBarOff;
   auto dy_full = [&](int s) { return bar_base + (uint32_t)s * 8; };
   auto dy_empty = [&](int s) { return bar_base + (uint32_t)(S::kDyStages + s) * 8; };
-  auto x_full = [&](int s) { return bar_base + (uint32_t)(2 * S::kDyStages + s) * 8; };
-  auto x_empty = [&](int s) { return bar_base + (uint32_t)(2 * S::kDyStages + S::kXStages + s) * 8; };
-  const uint32_t misc = bar_base + (uint32_t)(2 * S::kDyStages + 2 * S::kXStages) * 8;
+  auto xb_full = [&](int b) { return bar_base + (uint32_t)(2 * S::kDyStages + b) * 8; };                  // X of a row block has landed
+  auto xb_gdone = [&](int b) { return bar_base + (uint32_t)(2 * S::kDyStages + S::kXBufs + b) * 8; };     // the wgrad MMAs have read it
+  auto xb_free = [&](int b) { return bar_base + (uint32_t)(2 * S::kDyStages + 2 * S::kXBufs + b) * 8; };  // the epilogue is done with it
+  const uint32_t misc = bar_base + (uint32_t)(2 * S::kDyStages + 3 * S::kXBufs) * 8;
   const uint32_t tfull_bar = misc, tempty_bar = misc + 8, wfull_bar = misc + 16, d2full_bar = misc + 24;
   auto in_bar = [&](int w) { return misc + 32 + (uint32_t)w * 8; };
   const uint32_t tmem_slot = bar_base + S::kNumBars * 8;
@@ -81,9 +87,10 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(dy_full(s), 1);
       mbar_init(dy_empty(s), 2);  // one tcgen05.commit of each issuing warp
     }
-    for (int s = 0; s < S::kXStages; ++s) {
-      mbar_init(x_full(s), 1);
-      mbar_init(x_empty(s), 1);
+    for (int b = 0; b < S::kXBufs; ++b) {
+      mbar_init(xb_full(b), 1);
+      mbar_init(xb_gdone(b), 1);
+      mbar_init(xb_free(b), kEpiWarps);
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, kEpiWarps);
@@ -123,18 +130,23 @@ __global__ void __launch_bounds__(384, 1)
     }
     __syncwarp();
     int stage = 0;
-    uint32_t phase = 0, xphase = 0;
+    uint32_t phase = 0;
     for (int it = 0; it < my_blocks; ++it) {
       const int m0 = (member + it * p.members) * BM;
       if (leader && p.pf_tiles > 0 && it + p.pf_tiles < my_blocks) {
-        // ask L2 for a row block further ahead than the ring reaches; the CTAs that share the row block (one per column block)
+        // ask L2 for a row block further ahead than the rings reach; the CTAs that share the row block (one per column block)
         // split its 64-column pieces of dY between them
         const int pm0 = (member + (it + p.pf_tiles) * p.members) * BM;
         for (int kb = jblock; kb < 2 * NB; kb += nblocks) tma_prefetch_2d(&tma_dy, kb * 64, pm0);
-        tma_prefetch_2d(&tma_x, jblock * 128, pm0);
-        tma_prefetch_2d(&tma_x, jblock * 128, pm0 + 64);
-        tma_prefetch_2d(&tma_x, jblock * 128 + 64, pm0);
-        tma_prefetch_2d(&tma_x, jblock * 128 + 64, pm0 + 64);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tma_prefetch_2d(&tma_x, jblock * 128 + 64 * c, pm0);
+          tma_prefetch_2d(&tma_x, jblock * 128 + 64 * c, pm0 + 64);
+          if (p.has_in) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) tma_prefetch_2d(&tma_in, jblock * 128 + 64 * c, pm0 + 32 * r);
+          }
+        }
       }
 #pragma unroll 1
       for (int q = 0; q < NB; ++q) {
@@ -146,20 +158,25 @@ __global__ void __launch_bounds__(384, 1)
         }
         __syncwarp();
         if (++stage == S::kDyStages) { stage = 0; phase ^= 1u; }
-        if (q == 0) {  // X of this row block right behind its first dY pair (the wgrad issuer needs both before its first MMA)
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(x_empty(h), xphase ^ 1u);
-            if (leader) {
-              mbar_arrive_expect_tx(x_full(h), S::kXStage);
-              tma_load_2d(x_stage(h), &tma_x, x_full(h), jblock * 128, m0 + 64 * h);
-              tma_load_2d(x_stage(h) + kLbo64, &tma_x, x_full(h), jblock * 128 + 64, m0 + 64 * h);
-            }
-            __syncwarp();
-          }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= TMA producer of X: row block `it` goes to buffer it & 1 once the epilogue of row block it - 2 has
+    // released it (its own producer so that a late release never holds up the dY ring) =================
+    const bool leader = elect_one();
+    for (int it = 0; it < my_blocks; ++it) {
+      const int m0 = (member + it * p.members) * BM;
+      const int b = it & 1;
+      mbar_wait(xb_free(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      if (leader) {
+        mbar_arrive_expect_tx(xb_full(b), S::kXBuf);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(x_buf(b) + (uint32_t)h * S::kXHalf, &tma_x, xb_full(b), jblock * 128, m0 + 64 * h);
+          tma_load_2d(x_buf(b) + (uint32_t)h * S::kXHalf + kLbo64, &tma_x, xb_full(b), jblock * 128 + 64, m0 + 64 * h);
         }
       }
-      xphase ^= 1u;
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================= dgrad issuer: dX tile += dY pair (K-major A) · resident W blocks (MN-major B) =================
@@ -198,35 +215,32 @@ __global__ void __launch_bounds__(384, 1)
     //                   · X rows (MN-major B), in two halves of 64 rows =================
     const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t a_lo0 = desc_lo(dy_stage(0), kLboDy), b_lo0 = desc_lo(x_stage(0), kLbo64);
+    const uint32_t a_lo0 = desc_lo(dy_stage(0), kLboDy), b_lo0 = desc_lo(x_buf(0), kLbo64);
     int stage = 0;
-    uint32_t phase = 0, xphase = 0;
+    uint32_t phase = 0;
     for (int it = 0; it < my_blocks; ++it) {
+      const int xb = it & 1;
 #pragma unroll 1
       for (int q = 0; q < NB; ++q) {
         mbar_wait(dy_full(stage), phase);
-        if (q == 0) {
-          mbar_wait(x_full(0), xphase);
-          mbar_wait(x_full(1), xphase);
-        }
+        if (q == 0) mbar_wait(xb_full(xb), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
         if (leader) {
           const uint32_t d2 = tmem_base + 128u * (uint32_t)(q + 1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint32_t a_lo = a_lo0 + (uint32_t)stage * (S::kDyStage >> 4) + (uint32_t)h * (8192u >> 4);  // rows 64 h .. of both atoms
-            const uint32_t b_lo = b_lo0 + (uint32_t)h * (S::kXStage >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)xb * (S::kXBuf >> 4) + (uint32_t)h * (S::kXHalf >> 4);
 #pragma unroll
             for (int kk = 0; kk < 64 / UK; ++kk)
               tc_mma_bf16(d2, desc_from_lo(a_lo + kk * kStepMN), desc_from_lo(b_lo + kk * kStepMN), idesc, (it | h | kk) != 0 ? 1u : 0u);
-            if (q == NB - 1) tc_commit(x_empty(h));  // last use of this half of X
           }
           tc_commit(dy_empty(stage));
+          if (q == NB - 1) tc_commit(xb_gdone(xb));  // last use of this row block's X: the buffer becomes the epilogue's staging area
         }
         __syncwarp();
         if (++stage == S::kDyStages) { stage = 0; phase ^= 1u; }
       }
-      xphase ^= 1u;
     }
     if (leader) tc_commit(d2full_bar);  // the CTA's dW slice is complete
     __syncwarp();
@@ -234,18 +248,13 @@ __global__ void __launch_bounds__(384, 1)
     // ================= epilogue: TMEM lane quarter = warp % 4, column half = ew / 4 =================
     const int ew = warp - 4;
     const int quarter = warp & 3, half = ew >> 2;
-    const uint32_t slab = epi_base + (uint32_t)ew * kSlabBytes;  // z in, dX out
     const int n0 = jblock * 128 + half * 64;
     uint32_t in_phase = 0;
-    bool stores_pending = false;
     float cs0 = 0.f, cs1 = 0.f;  // column sums of columns n0 + 2 lane, + 1 over this warp's rows of every tile
     for (int it = 0; it < my_blocks; ++it) {
       const int m0 = (member + it * p.members) * BM;
-      if (p.has_in && lane == 0) {
-        if (stores_pending) tma_store_wait_read();
-        mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
-        tma_load_2d(slab, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
-      }
+      const int xb = it & 1;
+      const uint32_t slab = x_buf(xb) + (uint32_t)ew * kSlabBytes;  // z in, dX out — once the wgrad MMAs have read X from this buffer
       mbar_wait(tfull_bar, (uint32_t)(it & 1));
       tc_fence_after();
       uint32_t raw0[32], raw1[32];
@@ -255,14 +264,19 @@ __global__ void __launch_bounds__(384, 1)
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive(tempty_bar);  // the dX accumulator is in registers: the dgrad issuer may start the next row block
       float v[64];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         v[j] = __uint_as_float(raw0[j]);
         v[32 + j] = __uint_as_float(raw1[j]);
       }
+      mbar_wait(xb_gdone(xb), (uint32_t)(it >> 1) & 1u);
       if (p.has_in) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
+          tma_load_2d(slab, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
+        }
         mbar_wait(in_bar(ew), in_phase);
         in_phase ^= 1u;
 #pragma unroll
@@ -270,14 +284,10 @@ __global__ void __launch_bounds__(384, 1)
           float z[8];
           slab_load_chunk8(slab, lane, j, z);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_f(z[i]);
+          for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_bf16_f(z[i]);
         }
-        __syncwarp();  // every lane has read its z row before any lane overwrites the slab
-      } else if (stores_pending) {
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
       }
-      slab_store_row64(slab, lane, v);
+      slab_store_row64(slab, lane, v);  // (a lane reads and writes only its own row of the slab)
       __syncwarp();
       if (p.csum_part != nullptr) {
         // column sums of the bf16-rounded tile (what a later reader of dX sees): lane l owns columns 2l, 2l+1; rows beyond M are
@@ -297,8 +307,10 @@ __global__ void __launch_bounds__(384, 1)
       if (lane == 0) {
         tma_store_2d(&tma_out, slab, n0, m0 + quarter * 32);  // rows >= M are clipped by the tensor map
         tma_store_commit();
+        tma_store_wait_read();         // the store has read the slab:
+        mbar_arrive(xb_free(xb));      // the buffer may receive X of row block it + 2
       }
-      stores_pending = true;
+      __syncwarp();
     }
     if (p.csum_part != nullptr) {
       float* o = p.csum_part + (size_t)(member * 4 + quarter) * p.K + n0 + 2 * lane;
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(384, 1)
                                                                  __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
       }
     }
-    if (stores_pending && lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

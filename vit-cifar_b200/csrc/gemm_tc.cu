@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
         if (p.has_pre) slab_store_row64(slab_pre, lane, v);
         if (e.gelu) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = gelu_f(v[j]);
+          for (int j = 0; j < 64; ++j) v[j] = gelu_bf16_f(v[j]);
         }
         if (p.has_in) {
           mbar_wait(in_bar(ew), in_phase);
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
             float z[8];
             slab_load_chunk8(slab_in, lane, j, z);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_f(z[i]);
+            for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_bf16_f(z[i]);
           }
         }
       }
