@@ -82,9 +82,12 @@ class SideStream:
 
 
 def _bwd_fused_ok(rows: int, N: int, K: int, t: torch.Tensor) -> bool:
-    """The one-pass backward of a Linear (ops.gemm_bwd_fused) exists for this shape / dtype (bf16, N <= 384)."""
+    """Use the one-pass backward of a Linear (ops.gemm_bwd_fused) for this shape / dtype (bf16, N <= 384)?  Opt-in
+    (VITB_BWD_FUSED=1): measured on B200 it only equals dgrad + wgrad (66.5 vs 67.4 us at 66560 x 384 x 384) — with the
+    weight slice resident, 131 KB of shared memory are left to stream 128 KB of operands per row block, too little to cover the
+    load latency — and it is slower at 8,320 rows, where its 29 MB of per-CTA dW partials dominate."""
     import os
-    if os.environ.get("VITB_BWD_FUSED", "1") == "0":
+    if os.environ.get("VITB_BWD_FUSED", "0") == "0":
         return False
     return ops.bwd_fused_ws_bytes(rows, N, K, ops.dt_of(t)) > 0
 
