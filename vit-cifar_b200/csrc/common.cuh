@@ -45,14 +45,14 @@ void count_launch();
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch (opt-in: VITB_PDL=1).  Every kernel calls pdl_wait() before its first access to memory another
-// kernel may have written or may still read (griddepcontrol.wait returns when the preceding grid has completed and its memory is
-// visible), so it is safe to launch it with the programmatic-stream-serialization attribute, which lets block scheduling,
-// barrier initialisation, TMEM allocation and tensor-map prefetch overlap the predecessor's tail.  Measured on the 199-node
-// training graph (B200, round 1): neutral without an early trigger (6.24-6.27 vs 6.27-6.29 ms/step), 3 % SLOWER with
-// griddepcontrol.launch_dependents at kernel entry (6.48-6.53 ms) — the graph's kernel-to-kernel gaps are already small and
-// early-resident dependents get in the way.  Hence off by default and no early trigger; both instructions are no-ops in a
-// plain launch.
+// Programmatic dependent launch (on by default; VITB_PDL=0 switches it off).  Every kernel calls pdl_wait() before its first access
+// to memory another kernel may have written or may still read (griddepcontrol.wait returns when the preceding grid has completed
+// and its memory is visible), so it is safe to launch it with the programmatic-stream-serialization attribute, which lets block
+// scheduling, barrier initialisation, TMEM allocation and tensor-map prefetch overlap the predecessor's tail.  There is no early
+// trigger (griddepcontrol.launch_dependents at kernel entry was measured 3 % SLOWER in round 1: early-resident dependents get in
+// the way of the multi-wave attention kernels).  Measured in round 2 on the captured training graph (profiles/r2_pdl_ab.md):
+// batch 1024 neutral (6.04 vs 6.05 ms/step), batch 128 1.609 -> 1.481 ms (+8.6 %), T = 17 / batch 1024 2.448 -> 2.280 ms (+7 %):
+// the shorter the kernels, the more the launch-to-first-instruction latency matters.  Both instructions are no-ops in a plain launch.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() {}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

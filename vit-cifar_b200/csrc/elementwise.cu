@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...) {
 }
 
 bool pdl_enabled() {
-  static const bool on = getenv("VITB_PDL") && atoi(getenv("VITB_PDL")) != 0;
+  static const bool on = getenv("VITB_PDL") ? atoi(getenv("VITB_PDL")) != 0 : true;  // default on since round 2 (VITB_PDL=0 switches it off)
   return on;
 }
 static PersistWindow g_persist = {nullptr, 0, 1.0f};

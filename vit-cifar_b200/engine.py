@@ -167,7 +167,7 @@ class TrainEngine:
         self._defer = (self.act == torch.bfloat16 and not self.overlap_comm and os.environ.get("VITB_DEFER", "1") != "0")
         self._arena = torch.empty(self._arena_bytes(), dtype=torch.uint8, device=self.dev) if self._defer else None
         self.defer_bytes_used = 0
-        ws_mode = int(os.environ.get("VITB_WGRAD_STREAM", "1")) if self._defer else 0
+        ws_mode = int(os.environ.get("VITB_WGRAD_STREAM", "2")) if self._defer else 0
         self._side = None
         self._main_stream = None
         if ws_mode >= 1:
