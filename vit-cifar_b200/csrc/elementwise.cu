@@ -110,58 +110,6 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
 // ---------------------------------------------------------------------------------------------
 // LayerNorm forward: one warp per row, VEC float4-groups per lane (H = 128*VEC)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, int64_t xs,
-                                                     const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, T* __restrict__ y,
-                                                     float* __restrict__ mean, float* __restrict__ rstd,
-                                                     int rows, float eps) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int H = VEC * 128;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const T* xr = x + (int64_t)row * xs;
-  float4 v[VEC];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = ld4(xr + (i * 32 + lane) * 4);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mu = warp_sum(s) * (1.0f / H);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rs = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
-  T* yr = y + (int64_t)row * H;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    const float4 g = ld4(gamma + c), b = ld4(beta + c);
-    float4 o;
-    o.x = (v[i].x - mu) * rs * g.x + b.x;
-    o.y = (v[i].y - mu) * rs * g.y + b.y;
-    o.z = (v[i].z - mu) * rs * g.z + b.z;
-    o.w = (v[i].w - mu) * rs * g.w + b.w;
-    st4(yr + c, o);
-  }
-  if (lane == 0) {
-    mean[row] = mu;
-    rstd[row] = rs;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// LayerNorm backward (+ residual gradient add, + dgamma/dbeta/colsum(dx) partials)
-// grid-stride over rows, one warp per row; per-block partials -> ws[3][gridDim.x][H]
-// ---------------------------------------------------------------------------------------------
-constexpr int kLnBwdWarps = 8;
-
 // raw (storage-type) 4-element groups, so that the next row can be prefetched without converting it yet
 template <typename T> struct Raw4;
 template <> struct Raw4<float> { float4 v; };
@@ -173,6 +121,75 @@ __device__ __forceinline__ float4 cvt4(const Raw4<bf16>& r) {
   const float2 a = unpack_bf16x2(r.v.x), b = unpack_bf16x2(r.v.y);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+
+// A warp takes kLnFwdRows consecutive rows and issues the loads of all of them before the first reduction: a row is only
+// 768 bytes at H = 384 (24 bytes per lane), so one row per warp leaves too few bytes in flight per SM between block launches.
+constexpr int kLnFwdRows = 4;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const T* __restrict__ x, int64_t xs,
+                                                     const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd,
+                                                     int rows, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int H = VEC * 128;
+  constexpr int R = kLnFwdRows;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  Raw4<T> raw[R][VEC];  // storage type until used: 4 rows of bf16 are 24 registers
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = min(row0 + r, rows - 1);  // rows past the end re-read the last row (never stored)
+    const T* xr = x + (int64_t)row * xs;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) raw[r][i] = ldraw(xr + (i * 32 + lane) * 4);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = cvt4(raw[r][i]);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rs = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+    if (row < rows) {
+      T* yr = y + (int64_t)row * H;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float4 g = ld4(gamma + (i * 32 + lane) * 4), bt = ld4(beta + (i * 32 + lane) * 4);  // L1 hits after the first row
+        float4 o;
+        o.x = (v[i].x - mu) * rs * g.x + bt.x;
+        o.y = (v[i].y - mu) * rs * g.y + bt.y;
+        o.z = (v[i].z - mu) * rs * g.z + bt.z;
+        o.w = (v[i].w - mu) * rs * g.w + bt.w;
+        st4(yr + (i * 32 + lane) * 4, o);
+      }
+      if (lane == 0) {
+        mean[row] = mu;
+        rstd[row] = rs;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward (+ residual gradient add, + dgamma/dbeta/colsum(dx) partials)
+// grid-stride over rows, one warp per row; per-block partials -> ws[3][gridDim.x][H]
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnBwdWarps = 8;
+
 
 template <typename T, int VEC, bool HAS_RES, bool COLSUM>
 __global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must be one wave: keep <= 128 registers
@@ -693,7 +710,7 @@ int vitb_layernorm_fwd(const void* x, int64_t xs, const float* gamma, const floa
   VITB_REQUIRE(rows >= 0 && H % 128 == 0 && xs % 4 == 0, "layernorm_fwd: bad shape rows=%d H=%d stride=%lld", rows, H, (long long)xs);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = ceil_div(rows, 8);
+  const int blocks = ceil_div(rows, 8 * kLnFwdRows);
   if (dt == VITB_BF16) {
     VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_fwd_kernel<bf16, VEC>), blocks, 256, 0, st, (const bf16*)x, xs, gamma, beta, (bf16*)y, mean, rstd, rows, eps)));
   } else {
