@@ -9,7 +9,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvitb200.so")
+LIB_PATH = os.environ.get("VITB_LIB_PATH") or os.path.join(HERE, "libvitb200.so")  # (override: A/B builds of experiments)
 
 F32 = 0
 BF16 = 1

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(HERE, "build")
-LIB_PATH = os.path.join(HERE, "libvitb200.so")
+LIB_PATH = os.environ.get("VITB_BUILD_OUT") or os.path.join(HERE, "libvitb200.so")
 
 SOURCES = ["elementwise.cu", "loss_adam.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "head.cu", "dp.cu"]
 HEADERS = ["common.cuh", "gemm_internal.h"]
@@ -48,9 +48,12 @@ def needs_build() -> bool:
     return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _newest_input()
 
 
+EXTRA_DEFINES = [d for d in os.environ.get("VITB_BUILD_DEFINES", "").split() if d]  # e.g. "-DVITB_PDL_EARLY_CTAS=0" (experiments)
+
+
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_DEFINES, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJ_DIR, src.replace(".cu", ".ptxas.log"))
     with open(log, "w") as f:

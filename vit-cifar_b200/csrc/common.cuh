@@ -54,7 +54,16 @@ void count_launch();
 // batch 1024 neutral (6.04 vs 6.05 ms/step), batch 128 1.609 -> 1.481 ms (+8.6 %), T = 17 / batch 1024 2.448 -> 2.280 ms (+7 %):
 // the shorter the kernels, the more the launch-to-first-instruction latency matters.  Both instructions are no-ops in a plain launch.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_trigger() {}
+// Kernels whose whole grid is resident at once (persistent GEMMs: <= 148 CTAs; small elementwise grids) release their dependents
+// at entry: the dependent grid's launch processing and its pre-wait prologue then hide behind this kernel instead of starting
+// when its last CTA exits.  Multi-wave grids never trigger early (their later waves would compete with early-resident
+// dependents for SM slots — the 3 % loss measured in round 1 came from the 12,288-CTA attention backward).
+#ifndef VITB_PDL_EARLY_CTAS
+#define VITB_PDL_EARLY_CTAS 296
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+  if (VITB_PDL_EARLY_CTAS > 0 && gridDim.x * gridDim.y * gridDim.z <= (unsigned)VITB_PDL_EARLY_CTAS) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();  // VITB_PDL=1 in the environment switches the launch attribute on
