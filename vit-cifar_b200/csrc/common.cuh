@@ -54,12 +54,13 @@ void count_launch();
 // batch 1024 neutral (6.04 vs 6.05 ms/step), batch 128 1.609 -> 1.481 ms (+8.6 %), T = 17 / batch 1024 2.448 -> 2.280 ms (+7 %):
 // the shorter the kernels, the more the launch-to-first-instruction latency matters.  Both instructions are no-ops in a plain launch.
 // ---------------------------------------------------------------------------------------------
-// Kernels whose whole grid is resident at once (persistent GEMMs: <= 148 CTAs; small elementwise grids) release their dependents
-// at entry: the dependent grid's launch processing and its pre-wait prologue then hide behind this kernel instead of starting
-// when its last CTA exits.  Multi-wave grids never trigger early (their later waves would compete with early-resident
-// dependents for SM slots — the 3 % loss measured in round 1 came from the 12,288-CTA attention backward).
+// No early trigger (griddepcontrol.launch_dependents): measured twice.  Round 1: at kernel entry, every kernel, 3 % slower at
+// batch 1024.  Round 2: at entry only for grids that are resident at once (<= 296 CTAs, so that later waves never compete with
+// early-resident dependents): 6.25 vs 5.97 ms at batch 1024, 1.60 vs 1.48 ms at batch 128, 2.57 vs 2.27 ms at T = 17
+// (profiles/r2_pdl_ab.md) — dependents that become resident early sit in griddepcontrol.wait holding registers and shared
+// memory the running kernel's neighbours could use.  -DVITB_PDL_EARLY_CTAS=296 rebuilds that experiment.
 #ifndef VITB_PDL_EARLY_CTAS
-#define VITB_PDL_EARLY_CTAS 296
+#define VITB_PDL_EARLY_CTAS 0
 #endif
 __device__ __forceinline__ void pdl_trigger() {
   if (VITB_PDL_EARLY_CTAS > 0 && gridDim.x * gridDim.y * gridDim.z <= (unsigned)VITB_PDL_EARLY_CTAS) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
