@@ -7,7 +7,6 @@
 // only the per-row log-sum-exp is kept for backward, which recomputes P.  fp32 path (check mode):
 // plain FFMA with the score tile in shared memory.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_internal.h"
@@ -499,193 +498,6 @@ __global__ void __launch_bounds__(32 * NT16, (D == 32 ? (NT16 <= 2 ? 8 : (NT16 <
   }
 }
 
-// Persistent form of the backward kernel (head_dim 32): a CTA walks (image, head) items; one thread streams the NEXT item's
-// Q, K, V, dO tiles into the other half of a double buffer (and its O tile into a single buffer, as soon as D of the current
-// item has been formed) while the CTA computes, so no warp ever waits a full load latency with nothing to do — the one-shot
-// kernel above spends about a third of every CTA's life in its prologue (barrier set-up, five TMA loads, lse).  The current
-// item's Q / K / V tiles double as the staging tiles of dQ / dK / dV, exactly as above; they are reloaded two items later, after
-// the stores have read them.  Shared memory: 2 x 4 input tiles + O + P + dS + D = 73 KB at T = 65: three CTAs per SM.
-template <int D, int NT16>
-__global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 3 : 1)))
-    attn_bwd_bf16_pers_kernel(const __grid_constant__ CUtensorMap m_qkv, const __grid_constant__ CUtensorMap m_o, const __grid_constant__ CUtensorMap m_do,
-                              const __grid_constant__ CUtensorMap m_dqkv, const float* __restrict__ lse, int n_items, int T, int heads, float scale) {
-  constexpr int TP = 16 * NT16, LP = TP + 8, CH = D / 8;
-  constexpr uint32_t TILE_B = TP * D * 2;
-  constexpr uint32_t kAlign = D == 32 ? 512u : 1024u;  // the swizzle pattern of the tiles repeats every 512 B (64B swizzle) / 1024 B
-  extern __shared__ uint8_t smem_attn_raw[];
-  const uint32_t sbase = (smem_u32(smem_attn_raw) + (kAlign - 1)) & ~(kAlign - 1);
-  uint8_t* gen = smem_attn_raw + (sbase - smem_u32(smem_attn_raw));
-  // [2][Q K V dO] [O] [P] [dS] [D] [3 barriers]
-  const uint32_t sO = sbase + 8 * TILE_B;
-  bf16* sP = reinterpret_cast<bf16*>(gen + 9 * TILE_B);   // [TP][LP]
-  bf16* sdS = sP + TP * LP;                               // [TP][LP]
-  float* sD = reinterpret_cast<float*>(sdS + TP * LP);    // [TP]
-  const uint32_t bars = smem_u32(sD + TP);                // full[0], full[1], fullO
-  const int Hd = heads * D;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_trigger();
-  if (tid == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qkv) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_do) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_o) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_dqkv) : "memory");
-    mbar_init(bars, 1);
-    mbar_init(bars + 8, 1);
-    mbar_init(bars + 16, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_wait();  // inputs come from the preceding kernels
-  auto issue_in = [&](int item, int buf) {  // one thread: Q, K, V, dO of `item`
-    const int b = item / heads, h = item % heads;
-    const uint32_t dst = sbase + (uint32_t)buf * 4 * TILE_B, bar = bars + 8 * buf;
-    mbar_arrive_expect_tx(bar, 4 * TILE_B);
-    tma_load_3d(dst, &m_qkv, bar, h * D, 0, b);
-    tma_load_3d(dst + TILE_B, &m_qkv, bar, Hd + h * D, 0, b);
-    tma_load_3d(dst + 2 * TILE_B, &m_qkv, bar, 2 * Hd + h * D, 0, b);
-    tma_load_3d(dst + 3 * TILE_B, &m_do, bar, h * D, 0, b);
-  };
-  auto issue_o = [&](int item) {
-    mbar_arrive_expect_tx(bars + 16, TILE_B);
-    tma_load_3d(sO, &m_o, bars + 16, (item % heads) * D, 0, item / heads);
-  };
-  int item = blockIdx.x;
-  if (tid == 0 && item < n_items) {
-    issue_in(item, 0);
-    issue_o(item);
-  }
-  const int g = lane >> 2;
-  const int r0 = 16 * warp + g, r1 = r0 + 8;
-  const float sl2 = scale * kLog2e;
-  const KeyMask km = make_key_mask(T, lane);
-  const LaneAddr<D> la(lane);
-  // lse * log2(e) of this thread's two query rows (0 beyond T), fetched one item ahead
-  auto load_lse = [&](int it_item, float& a, float& b2) {
-    a = 0.f; b2 = 0.f;
-    if (it_item < n_items) {
-      const float* lrow = lse + (int64_t)it_item * T;  // (b * heads + h) * T
-      if (r0 < T) a = lrow[r0] * kLog2e;
-      if (r1 < T) b2 = lrow[r1] * kLog2e;
-    }
-  };
-  float l0n, l1n;
-  load_lse(item, l0n, l1n);
-  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
-    const int cur = it & 1;
-    const uint32_t sQ = sbase + (uint32_t)cur * 4 * TILE_B, sK = sQ + TILE_B, sV = sK + TILE_B, sdO = sV + TILE_B;
-    const int b = item / heads, h = item % heads;
-    const int nxt = item + gridDim.x;
-    if (tid == 0 && nxt < n_items) {
-      // the other half held item it - 1, whose Q / K / V tiles were the staging tiles of its gradient stores
-      tma_store_wait_read();
-      issue_in(nxt, cur ^ 1);
-    }
-    const float l0 = l0n, l1 = l1n;
-    load_lse(nxt, l0n, l1n);
-    mbar_wait(bars + 8 * cur, (uint32_t)(it >> 1) & 1u);
-    mbar_wait(bars + 16, (uint32_t)it & 1u);
-    // D_i = sum_d dO_id * O_id, each warp for its own 16 query rows (zero rows give D = 0)
-    for (int idx = lane; idx < 16 * CH; idx += 32) {
-      const int r = 16 * warp + idx / CH, c = idx % CH;
-      uint32_t a0, a1, a2, a3, q0, q1, q2, q3;
-      const uint32_t off = tile_off<D>(r, c);
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sdO + off));
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(sO + off));
-      const float2 x0 = unpack_bf16x2(a0), x1 = unpack_bf16x2(a1), x2 = unpack_bf16x2(a2), x3 = unpack_bf16x2(a3);
-      const float2 y0 = unpack_bf16x2(q0), y1 = unpack_bf16x2(q1), y2 = unpack_bf16x2(q2), y3 = unpack_bf16x2(q3);
-      float v = (x0.x * y0.x + x0.y * y0.y) + (x1.x * y1.x + x1.y * y1.y) + (x2.x * y2.x + x2.y * y2.y) + (x3.x * y3.x + x3.y * y3.y);
-#pragma unroll
-      for (int off2 = CH / 2; off2 > 0; off2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off2);
-      if (c == 0) sD[r] = v;
-    }
-    __syncwarp();
-    const float d0 = sD[r0], d1 = sD[r1];
-    uint32_t aq[D / 16][4], ado[D / 16][4];
-#pragma unroll
-    for (int kk = 0; kk < D / 16; ++kk) {
-      ldsm_x4_s(aq[kk], sQ + la.a(16 * warp, kk));
-      ldsm_x4_s(ado[kk], sdO + la.a(16 * warp, kk));
-    }
-    float dq[D / 8][4];
-#pragma unroll
-    for (int jn = 0; jn < D / 8; ++jn) dq[jn][0] = dq[jn][1] = dq[jn][2] = dq[jn][3] = 0.f;
-#pragma unroll
-    for (int jc = 0; jc < NT16; ++jc) {  // 16 keys per chunk
-      float s[2][4], dp[2][4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = 2 * jc + u;
-        s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f;
-        dp[u][0] = dp[u][1] = dp[u][2] = dp[u][3] = 0.f;
-        if (j < km.nfull || (j == km.nfull && km.rem != 0)) {  // warp-uniform: key tiles beyond T contribute P = dS = 0
-#pragma unroll
-          for (int k2 = 0; k2 < D / 32; ++k2) {
-            uint32_t bk[4], bv[4];
-            ldsm_x4_s(bk, sK + la.b(8 * j, k2));
-            ldsm_x4_s(bv, sV + la.b(8 * j, k2));
-            mma_bf16(s[u], aq[2 * k2], bk[0], bk[1]);
-            mma_bf16(s[u], aq[2 * k2 + 1], bk[2], bk[3]);
-            mma_bf16(dp[u], ado[2 * k2], bv[0], bv[1]);
-            mma_bf16(dp[u], ado[2 * k2 + 1], bv[2], bv[3]);
-          }
-          if (j == km.nfull) {
-            s[u][0] += km.pm0; s[u][2] += km.pm0;
-            s[u][1] += km.pm1; s[u][3] += km.pm1;
-          }
-          s[u][0] = ex2_fast(fmaf(s[u][0], sl2, -l0));
-          s[u][1] = ex2_fast(fmaf(s[u][1], sl2, -l0));
-          s[u][2] = ex2_fast(fmaf(s[u][2], sl2, -l1));
-          s[u][3] = ex2_fast(fmaf(s[u][3], sl2, -l1));
-          dp[u][0] = s[u][0] * (dp[u][0] - d0) * scale;
-          dp[u][1] = s[u][1] * (dp[u][1] - d0) * scale;
-          dp[u][2] = s[u][2] * (dp[u][2] - d1) * scale;
-          dp[u][3] = s[u][3] * (dp[u][3] - d1) * scale;
-        }
-      }
-      uint32_t pa[4], da[4];
-      pa[0] = pack_bf16x2(s[0][0], s[0][1]); pa[1] = pack_bf16x2(s[0][2], s[0][3]);
-      pa[2] = pack_bf16x2(s[1][0], s[1][1]); pa[3] = pack_bf16x2(s[1][2], s[1][3]);
-      da[0] = pack_bf16x2(dp[0][0], dp[0][1]); da[1] = pack_bf16x2(dp[0][2], dp[0][3]);
-      da[2] = pack_bf16x2(dp[1][0], dp[1][1]); da[3] = pack_bf16x2(dp[1][2], dp[1][3]);
-      const int srow = 16 * warp + ((lane >> 3) & 1) * 8 + (lane & 7), scol = 16 * jc + (lane >> 4) * 8;
-      stsm_x4(sP + srow * LP + scol, pa[0], pa[1], pa[2], pa[3]);
-      stsm_x4(sdS + srow * LP + scol, da[0], da[1], da[2], da[3]);
-#pragma unroll
-      for (int jp = 0; jp < D / 16; ++jp) {
-        uint32_t bb[4];
-        ldsm_x4_t_s(bb, sK + la.t(16 * jc, jp));
-        mma_bf16(dq[2 * jp], da, bb[0], bb[1]);
-        mma_bf16(dq[2 * jp + 1], da, bb[2], bb[3]);
-      }
-    }
-    __syncthreads();  // sP / sdS complete; every warp has formed its D rows: the O tile is free for the next item
-    if (tid == 0 && nxt < n_items) issue_o(nxt);
-
-    float dv[D / 8][4], dk[D / 8][4];
-#pragma unroll
-    for (int jn = 0; jn < D / 8; ++jn) {
-      dv[jn][0] = dv[jn][1] = dv[jn][2] = dv[jn][3] = 0.f;
-      dk[jn][0] = dk[jn][1] = dk[jn][2] = dk[jn][3] = 0.f;
-    }
-    tn_tile<D, NT16>(dv, sP, sdO, warp, lane, la);
-    tn_tile<D, NT16>(dk, sdS, sQ, warp, lane, la);
-    __syncthreads();  // everyone is done reading this item's tiles (and sP / sdS): Q / K / V become the staging tiles
-
-    stage_rows16<D>(dq, sQ, 16 * warp, lane);
-    stage_rows16<D>(dk, sK, 16 * warp, lane);
-    stage_rows16<D>(dv, sV, 16 * warp, lane);
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_store_3d(&m_dqkv, sQ, h * D, 0, b);  // token rows >= T are clipped by the tensor map
-      tma_store_3d(&m_dqkv, sK, Hd + h * D, 0, b);
-      tma_store_3d(&m_dqkv, sV, 2 * Hd + h * D, 0, b);
-      tma_store_commit();
-    }
-  }
-  if (tid == 0) tma_store_wait_read();  // shared memory must stay alive until the last stores have read it
-}
-
 // ---------------------------------------------------------------------------------------------
 // fp32 check-mode kernels (FFMA, score tile in shared memory)
 // ---------------------------------------------------------------------------------------------
@@ -830,29 +642,6 @@ template <int D, int NT16>
 static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int T, int heads, float scale,
                            cudaStream_t st) {
   constexpr int TP = 16 * NT16, LP = TP + 8;
-  const int Hd = heads * D;
-  CUtensorMap m_qkv, m_o, m_do, m_dqkv;
-  if (head_tile_map<D, NT16>(&m_qkv, qkv, 3 * Hd, T, B)) return -1;
-  if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
-  if (head_tile_map<D, NT16>(&m_do, d_o, Hd, T, B)) return -1;
-  if (head_tile_map<D, NT16>(&m_dqkv, dqkv, 3 * Hd, T, B)) return -1;
-  static const bool one_shot = getenv("VITB_ATTN_BWD_ONESHOT") && atoi(getenv("VITB_ATTN_BWD_ONESHOT")) != 0;  // A/B hook
-  if (D == 32 && !one_shot) {
-    // persistent, double-buffered (head_dim 64 would leave one CTA per SM: it keeps the one-shot kernel)
-    constexpr size_t smem = (size_t)9 * TP * D * 2 + (size_t)2 * TP * LP * 2 + (size_t)TP * sizeof(float) + 24 + 512;
-    auto kern = attn_bwd_bf16_pers_kernel<D, NT16>;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-      VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VITB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NT16, smem));
-      if (per_sm < 1) per_sm = 1;
-    }
-    const int items = B * heads;
-    const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-    VITB_LAUNCH((kern), grid, 32 * NT16, smem, st, m_qkv, m_o, m_do, m_dqkv, lse, items, T, heads, scale);
-    VITB_LAUNCH_OK();
-    return 0;
-  }
   constexpr size_t smem = (size_t)5 * TP * D * 2 + (size_t)2 * TP * LP * 2 + (size_t)2 * TP * sizeof(float) + 16 + 1024;
   auto kern = attn_bwd_bf16_kernel<D, NT16>;
   static bool configured = false;
@@ -860,6 +649,12 @@ static int launch_bwd_bf16(const void* qkv, const void* o, const void* d_o, cons
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  const int Hd = heads * D;
+  CUtensorMap m_qkv, m_o, m_do, m_dqkv;
+  if (head_tile_map<D, NT16>(&m_qkv, qkv, 3 * Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_o, o, Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_do, d_o, Hd, T, B)) return -1;
+  if (head_tile_map<D, NT16>(&m_dqkv, dqkv, 3 * Hd, T, B)) return -1;
   int per_sm = 1;
   VITB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NT16, smem));
   VITB_LAUNCH((kern), B * heads, 32 * NT16, smem, st, m_qkv, m_o, m_do, m_dqkv, lse, T, heads, scale, kNumSMs * (per_sm > 0 ? per_sm : 1));
