@@ -185,7 +185,9 @@ def attn_ref(qkv, B, T, heads, d, scale, do=None):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("B,T,heads,d", [(3, 65, 12, 32), (2, 17, 12, 32), (2, 16, 4, 32), (2, 64, 2, 64), (1, 65, 12, 64), (1, 100, 2, 32)])
+@pytest.mark.parametrize("B,T,heads,d", [(3, 65, 12, 32), (2, 17, 12, 32), (2, 16, 4, 32), (2, 64, 2, 64), (1, 65, 12, 64), (1, 100, 2, 32),
+                                         # many (image, head) items per persistent forward CTA: 1,560 / 4,800 items on <= 592 / 1,184 CTAs
+                                         (130, 65, 12, 32), (400, 17, 12, 32)])
 def test_attention_fwd_bwd(ops, dtype, B, T, heads, d):
     H = heads * d
     scale = 1.0 / math.sqrt(H)
