@@ -205,7 +205,7 @@ def eager_gpu_images_per_s(mode: str, batch: int, steps: int, warmup: int, compi
     tot = sum(ms)
     return {"mode": mode + ("+compile" if compile_ else ""), "img_s": round(batch * len(ms) / (tot * 1e-3), 1), "ms_per_step": round(tot / len(ms), 4),
             "p10_ms": round(pctl(ms, 0.1), 4), "p50_ms": round(pctl(ms, 0.5), 4), "p90_ms": round(pctl(ms, 0.9), 4), "batch": batch, "kind": kind,
-            "final_loss": float(loss)}
+            "final_loss": float(loss.detach())}
 
 
 def run_eager(args):
