@@ -204,8 +204,15 @@ __device__ __forceinline__ void stage_rows16(const float (&acc)[D / 8][4], uint3
 // bf16 forward: persistent CTAs walk (image, head) items; one thread streams the next item's Q/K/V tiles in with TMA
 // (double buffer, mbarrier) while the CTA computes the current one; the output tile leaves through a TMA store
 // ---------------------------------------------------------------------------------------------
+// CTAs per SM of the forward kernel at 3-5 row tiles (T = 33..80).  5 fit in shared memory (5 x 42 KB) if the kernel stays within
+// 80 registers, and ptxas gets there from 93 with 20 bytes of spills — measured SLOWER (74.8 vs 67.8 us at B = 1024, T = 65,
+// profiles/r2_attn_experiments.md): the kernel is bound by its dependent ldmatrix / mma.sync / shuffle chains, which the tighter
+// register allocation lengthens by more than the fifth CTA hides.
+#ifndef VITB_ATTN_FWD_CTAS
+#define VITB_ATTN_FWD_CTAS 4
+#endif
 template <int D, int NT16>
-__global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1)))
+__global__ void __launch_bounds__(32 * NT16, (NT16 <= 2 ? 8 : (NT16 <= 5 ? (D == 32 ? VITB_ATTN_FWD_CTAS : 2) : 1)))
     attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap m_qkv, const __grid_constant__ CUtensorMap m_o, float* __restrict__ lse,
                          float* __restrict__ attn_map, int n_items, int T, int heads, float scale) {
   constexpr int TP = 16 * NT16;
@@ -621,12 +628,12 @@ template <int D, int NT16>
 static int launch_fwd_bf16(const void* qkv, void* o, float* lse, float* am, int B, int T, int heads, float scale, cudaStream_t st) {
   constexpr int TP = 16 * NT16;
   constexpr size_t smem = (size_t)8 * TP * D * 2 + 16 + 1024;
-  constexpr int per_sm = NT16 <= 2 ? 8 : (NT16 <= 5 ? 4 : 1);
   auto kern = attn_fwd_bf16_kernel<D, NT16>;
-  static bool configured = false;
-  if (!configured) {
+  static int per_sm = 0;  // resident CTAs per SM of this instantiation (the kernel is persistent: the grid is exactly one wave)
+  if (per_sm == 0) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    VITB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * NT16, smem));
+    if (per_sm < 1) per_sm = 1;
   }
   const int Hd = heads * D;
   CUtensorMap m_qkv, m_o;
