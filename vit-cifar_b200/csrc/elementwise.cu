@@ -53,21 +53,39 @@ void defer_add(const float* src, int nparts, int64_t cols, float* dst) {
   (finalize_is_tall(nparts, cols) ? g_defer.tall : g_defer.plain).push_back(j);
 }
 
-// block (32, 8): the plain fixed-order pass of common.cuh for the job that owns this block
+// the job that owns block `bid`: binary search over the first-block table (a linear scan over up to 120 entries cost more than
+// the reduction itself when a step has hundreds of thousands of small blocks — the scaled ViT lost 1 ms per step to it)
+__device__ __forceinline__ int find_job(const ReduceBatch& b, int bid) {
+  int lo = 0, hi = b.njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bid >= b.block_start[mid]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// columns chunks (of 128) per block of the plain pass: few partials -> many chunks, so that a block always has ~12k floats to add
+__host__ __device__ __forceinline__ int plain_chunks_per_block(int nparts) {
+  const int c = 96 / (nparts > 0 ? nparts : 1);
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+// block (32, 8): the plain fixed-order pass of common.cuh, chunk by chunk, for the job that owns this block
 __global__ void __launch_bounds__(256) reduce_jobs_plain_kernel(const ReduceBatch b) {
   pdl_trigger();
   pdl_wait();
-  int j = 0;
-  while (j + 1 < b.njobs && (int)blockIdx.x >= b.block_start[j + 1]) ++j;
+  const int j = find_job(b, (int)blockIdx.x);
   const ReduceJob& job = b.jobs[j];
-  finalize_block_cols(job.src, job.nparts, job.cols, job.dst, (int)blockIdx.x - b.block_start[j], b.block_start[j + 1] - b.block_start[j]);
+  const int nchunks = (job.cols + 127) / 128, per = plain_chunks_per_block(job.nparts);
+  const int c0 = ((int)blockIdx.x - b.block_start[j]) * per;
+  for (int c = c0; c < c0 + per && c < nchunks; ++c) {
+    finalize_block_cols(job.src, job.nparts, job.cols, job.dst, c, nchunks);
+    __syncthreads();  // the shared reduction buffer is reused by the next chunk
+  }
 }
 // block (8, 64): the tall pass
 __global__ void __launch_bounds__(512) reduce_jobs_tall_kernel(const ReduceBatch b) {
   pdl_trigger();
   pdl_wait();
-  int j = 0;
-  while (j + 1 < b.njobs && (int)blockIdx.x >= b.block_start[j + 1]) ++j;
+  const int j = find_job(b, (int)blockIdx.x);
   const ReduceJob& job = b.jobs[j];
   finalize_tall_block(job.src, job.nparts, job.cols, job.dst, (int)blockIdx.x - b.block_start[j]);
 }
@@ -81,7 +99,8 @@ static int flush_jobs(const std::vector<ReduceJob>& jobs, bool tall, cudaStream_
     for (size_t i = 0; i < n; ++i) {
       b.jobs[i] = jobs[i0 + i];
       b.block_start[i] = blocks;
-      blocks += tall ? (b.jobs[i].cols + 31) / 32 : (b.jobs[i].cols + 127) / 128;
+      const int chunks = (b.jobs[i].cols + 127) / 128, per = plain_chunks_per_block(b.jobs[i].nparts);
+      blocks += tall ? (b.jobs[i].cols + 31) / 32 : (chunks + per - 1) / per;
     }
     b.block_start[n] = blocks;
     if (tall) VITB_LAUNCH((reduce_jobs_tall_kernel), blocks, dim3(8, 64), 0, st, b);
