@@ -318,7 +318,8 @@ def probe_kernels(eng, steps=3):
 
 
 def ncu_traffic(kernel_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), or None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round's final
+    build (profiles/ncu_traffic.json, rows in profiles/r2_ncu_full_summary.csv), or None."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
@@ -342,8 +343,11 @@ def _kernel_roofline(row, pk, B, T, H):
     if op in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"):
         M, N, K = sh[:3]
         fl = 2.0 * M * N * K
-        return {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["tf_sust"],
-                "traffic": None, "kernel": f"{op} M={M} N={N} K={K} {' '.join(row['flags'])}".strip(), "peak_kind": f"{pk['src']} sustained bf16"}
+        r = {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["tf_sust"],
+             "traffic": None, "kernel": f"{op} M={M} N={N} K={K} {' '.join(row['flags'])}".strip(), "peak_kind": f"{pk['src']} sustained bf16"}
+        if op == "gemm_wgrad":
+            r["note"] = "split-K GEMM launch only: its fixed-order second pass runs in the step's deferred flush (vitb_defer_flush)"
+        return r
     rows = B * T
     by = {
         "layernorm_fwd": 2 * rows * H * E, "layernorm_bwd": 4 * rows * H * E, "attn_fwd": 4 * rows * H * E, "attn_bwd": 8 * rows * H * E,

@@ -40,11 +40,13 @@ int head_wgrad_launch(const float* dy, const void* x, float* dw, float* dbias, i
 int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t ld, int x_dt, cudaStream_t st);
 
 // tensor-core pieces of the patch embedding (gemm_tc.cu), bf16 only
-//   fwd:  tmp[M, H] = words[M, K] · w[H, K]ᵀ + bias        (K = 48 / 192: partial k-block, TMA zero-fills)
+//   fwd:  out[b, off + n, :] = words[b PP + n, :] · w[H, K]ᵀ + bias + pos[off + n, :]   (K = 48 / 192: partial k-block, TMA zero-fills;
+//         stored straight into the (B, Tn, H) tensor through a 3-D tensor map)
 //   bwd:  dw[H, K] = sum_m dout[b, off + n, :]ᵀ words[m, :] (A read through a 3-D tensor map that skips the cls rows),
 //         dbias[H] = column sums of those rows (ones-operand MMA)
 bool tc_patch_ok(int PP, int H, int K);
-int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, void* tmp, int M, int H, int K, cudaStream_t st);
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, void* out, int B, int PP, int Tn, int off, int H, int K,
+                 cudaStream_t st);
 size_t tc_patch_wgrad_ws_bytes(int B, int PP, int H, int K);
 int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias, void* ws, size_t ws_bytes, int B, int Tn, int PP,
                    int has_cls, int H, int K, cudaStream_t st);

@@ -268,36 +268,6 @@ __global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restric
   }
 }
 
-// out[b, off+n, :] = tmp[b*PP+n, :] + pos[off+n, :];  out[b, 0, :] = cls + pos[0, :]   (vit.py:68-70), 8 columns per thread
-__global__ void patch_assemble_kernel(const bf16* __restrict__ tmp, const float* __restrict__ cls, const float* __restrict__ pos,
-                                      bf16* __restrict__ out, int B, int PP, int Tn, int H, int has_cls) {
-  pdl_trigger();
-  pdl_wait();
-  const int H8 = H / 8;
-  const int64_t total = (int64_t)B * Tn * H8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H8) * 8;
-    const int64_t bt = i / H8;
-    const int t = (int)(bt % Tn);
-    const int64_t b = bt / Tn;
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * H + c));
-    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)t * H + c + 4));
-    float v[8];
-    if (has_cls && t == 0) {
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + c)), c1 = __ldg(reinterpret_cast<const float4*>(cls + c + 4));
-      v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
-    } else {
-      const uint4 u = *reinterpret_cast<const uint4*>(tmp + ((size_t)b * PP + (t - has_cls)) * H + c);
-      const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y), e = unpack_bf16x2(u.z), f = unpack_bf16x2(u.w);
-      v[0] = a.x; v[1] = a.y; v[2] = d.x; v[3] = d.y; v[4] = e.x; v[5] = e.y; v[6] = f.x; v[7] = f.y;
-    }
-    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
-  }
-}
-
 }  // namespace vitb
 
 using namespace vitb;
@@ -311,8 +281,8 @@ static bool patch_tc_path(const void* words, const void* w_act, int P, int S, in
 }
 
 size_t vitb_patch_embed_fwd_ws_bytes(int B, int S, int P, int H, int dt) {
-  if (dt != VITB_BF16 || P <= 0) return 0;
-  return align_up((size_t)B * P * P * H * sizeof(bf16), 256);  // un-assembled GEMM output of the tensor-core path
+  (void)B; (void)S; (void)P; (void)H; (void)dt;
+  return 0;  // (round 1 staged the GEMM output here; the epilogue now writes the (B, T, H) tensor directly)
 }
 
 int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, const float* bias, const float* cls, const float* pos,
@@ -322,18 +292,20 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
   VITB_REQUIRE(!has_cls || cls, "patch_embed_fwd: has_cls without cls pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int ps = S / P, K = ps * ps * 3, PP = P * P, Tn = PP + (has_cls ? 1 : 0);
-  if (patch_tc_path(words, w_act, P, S, H, dt) && ws != nullptr && ws_bytes >= vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)) {
-    // tensor-core path: words (bf16) -> tcgen05 GEMM (+bias) -> assemble with cls / pos_emb
+  (void)ws; (void)ws_bytes;
+  if (patch_tc_path(words, w_act, P, S, H, dt)) {
+    // tensor-core path: patch gather (bf16 words, kept for the backward wgrad) -> tcgen05 GEMM whose epilogue adds bias and
+    // pos_emb[token] and stores into the token rows of (B, T, H) -> the B cls rows
     int blocks = (int)ceil_div64((int64_t)B * PP * (K / 8), 256);
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
     VITB_LAUNCH((words_bf16_kernel), blocks, 256, 0, st, img, (bf16*)words, B, S, P);
     VITB_LAUNCH_OK();
-    int rc = tc_patch_fwd(words, w_act, bias, ws, B * PP, H, K, st);
+    int rc = tc_patch_fwd(words, w_act, bias, pos, out, B, PP, Tn, has_cls ? 1 : 0, H, K, st);
     if (rc) return rc;
-    blocks = (int)ceil_div64((int64_t)B * Tn * (H / 8), 256);
-    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-    VITB_LAUNCH((patch_assemble_kernel), blocks, 256, 0, st, (const bf16*)ws, cls, pos, (bf16*)out, B, PP, Tn, H, has_cls ? 1 : 0);
-    VITB_LAUNCH_OK();
+    if (has_cls) {
+      VITB_LAUNCH((cls_rows_kernel<bf16>), B, 128, 0, st, cls, pos, (bf16*)out, B, Tn, H);
+      VITB_LAUNCH_OK();
+    }
     return 0;
   }
   SimtGemmArgs g = {};

@@ -48,6 +48,8 @@ struct TcArgs {
   int pf_tiles;      // fwd/dgrad: prefetch the A tile this many tiles (per stream) ahead into L2; 0 = off
   int pf_kblocks;    // wgrad: prefetch operands this many k-blocks ahead into L2; 0 = off
   int dbg_flags;     // tools only: 1 = epilogue skips its work (accumulator handed straight back), 2 = producer loads nothing
+  int out3;          // EPI_FWD: tma_out is a 3-D (columns, tokens, images) map of a (B, T, H) tensor — the patch embedding writes GEMM
+                     // row m to token e.rm_offset + m % e.rm_group of image m / e.rm_group and adds e.pos[token] (vit.py:68-70)
   EpiParams e;
 };
 
@@ -104,6 +106,11 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -667,6 +674,15 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
+        if (p.out3 && e.pos != nullptr) {  // + pos_emb[token] (fp32), token of this thread's row
+          const int tok = e.rm_offset + grow % e.rm_group;
+          const float4* p4 = reinterpret_cast<const float4*>(e.pos + (size_t)tok * p.N + n0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 q = __ldg(p4 + j);
+            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+          }
+        }
         if (p.has_pre && NSLAB > 1) slab_store_row64(slab_pre, lane, v);
         if (p.has_pre && NSLAB == 1) {
           // ONE slab per warp (a second one would cost every stream a ring stage, and ring depth is what bounds these kernels):
@@ -688,9 +704,8 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
           if (lane == 0) {
             tma_store_2d(&tma_pre, slab_out, n0, m0 + quarter * 32);
             tma_store_commit();
-            tma_store_wait_read();
           }
-          __syncwarp();
+          // the GELU arithmetic runs while the TMA engine reads the pre-activation out of the slab
           if (e.gelu) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = gelu_bf16_f(v[j]);
@@ -703,6 +718,8 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
               v[2 * j + 1] += r.y;
             }
           }
+          if (lane == 0) tma_store_wait_read();  // ... which must be done before the output is staged in the same slab
+          __syncwarp();
         } else {
         if (e.gelu) {
 #pragma unroll
@@ -737,7 +754,12 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&tma_out, slab_out, n0, m0 + quarter * 32);  // rows >= M are clipped by the tensor map
+        if (p.out3) {  // the slab's 32 rows are whole tokens of one image, or all tokens of 32 / rm_group consecutive images
+          const int row0 = m0 + quarter * 32;
+          tma_store_3d(&tma_out, slab_out, n0, e.rm_offset + row0 % e.rm_group, row0 / e.rm_group);  // images >= B are clipped
+        } else {
+          tma_store_2d(&tma_out, slab_out, n0, m0 + quarter * 32);  // rows >= M are clipped by the tensor map
+        }
         if (p.has_pre && NSLAB > 1) tma_store_2d(&tma_pre, slab_pre, n0, m0 + quarter * 32);
         tma_store_commit();
       }
@@ -939,19 +961,26 @@ static int check_dt(int dt) {
 // patch embedding on the tensor cores (called from gemm_simt.cu's front end)
 // ---------------------------------------------------------------------------------------------
 bool tc_patch_ok(int PP, int H, int K) {
-  return H % 128 == 0 && K % 8 == 0 && K <= 256 && ((PP >= 64 && PP % 64 == 0) || (PP < 64 && 64 % PP == 0));
+  // (the 32-row epilogue slabs must be whole tokens of one image or whole images: PP a multiple or a divisor of 32)
+  return H % 128 == 0 && K % 8 == 0 && K <= 256 && ((PP >= 64 && PP % 64 == 0) || (PP < 64 && 64 % PP == 0)) && (PP % 32 == 0 || 32 % PP == 0);
 }
 
-int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, void* tmp, int M, int H, int K, cudaStream_t st) {
+// out (B, Tn, H) bf16: token rows off .. off + PP - 1 of every image = words · wᵀ + bias + pos[token]  (vit.py:66-70; the cls row is
+// written by the caller).  The epilogue stores straight into the (B, T, H) tensor through a 3-D map: no intermediate buffer.
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, void* out, int B, int PP, int Tn, int off, int H, int K,
+                 cudaStream_t st) {
+  const int M = B * PP;
   TcMaps m;
   if (make_map(&m.a, words, K, M, K, BM)) return -1;
   if (make_map(&m.b, w_bf16, K, H, K, kBN)) return -1;
-  if (make_map(&m.out, tmp, H, M, H, 32)) return -1;
+  const uint32_t toks = PP >= 32 ? 32 : (uint32_t)PP, imgs = PP >= 32 ? 1 : (uint32_t)(32 / PP);
+  if (make_tma_map_3d_bf16(&m.out, out, (uint64_t)H, (uint64_t)Tn, (uint64_t)B, (uint64_t)H * 2, (uint64_t)Tn * H * 2, 64, toks, imgs, 128)) return -1;
   m.pre = m.out; m.in = m.out;
   TcArgs t = {};
   t.M = M; t.N = H; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = H / kBN; t.splits = 1;
   t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.valid_n = H;
-  t.e.mode = EPI_FWD; t.e.bias = bias; t.e.out = tmp; t.e.ldc = H;
+  t.e.mode = EPI_FWD; t.e.bias = bias; t.e.out = out; t.e.ldc = H;
+  t.out3 = 1; t.e.rm_group = PP; t.e.rm_stride = Tn; t.e.rm_offset = off; t.e.pos = pos;
   return launch_tc<kBN, false, false>(m, t, st);
 }
 
