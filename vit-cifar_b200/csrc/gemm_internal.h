@@ -45,8 +45,8 @@ int colsum_small_launch(const void* x, float* out, int rows, int cols, int64_t l
 //   bwd:  dw[H, K] = sum_m dout[b, off + n, :]ᵀ words[m, :] (A read through a 3-D tensor map that skips the cls rows),
 //         dbias[H] = column sums of those rows (ones-operand MMA)
 bool tc_patch_ok(int PP, int H, int K);
-int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, void* out, int B, int PP, int Tn, int off, int H, int K,
-                 cudaStream_t st);
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, const void* pos_bf16, void* out, int B, int PP, int Tn,
+                 int off, int H, int K, cudaStream_t st);
 size_t tc_patch_wgrad_ws_bytes(int B, int PP, int H, int K);
 int tc_patch_wgrad(const void* dout, const void* words, float* dw, float* dbias, void* ws, size_t ws_bytes, int B, int Tn, int PP,
                    int has_cls, int H, int K, cudaStream_t st);

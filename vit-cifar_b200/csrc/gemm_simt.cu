@@ -281,8 +281,9 @@ static bool patch_tc_path(const void* words, const void* w_act, int P, int S, in
 }
 
 size_t vitb_patch_embed_fwd_ws_bytes(int B, int S, int P, int H, int dt) {
-  (void)B; (void)S; (void)P; (void)H; (void)dt;
-  return 0;  // (round 1 staged the GEMM output here; the epilogue now writes the (B, T, H) tensor directly)
+  (void)B; (void)S;
+  if (dt != VITB_BF16 || P <= 0) return 0;
+  return align_up((size_t)(P * P + 1) * H * sizeof(bf16), 256);  // bf16 copy of pos_emb for the GEMM epilogue's TMA loads
 }
 
 int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, const float* bias, const float* cls, const float* pos,
@@ -292,7 +293,6 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
   VITB_REQUIRE(!has_cls || cls, "patch_embed_fwd: has_cls without cls pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int ps = S / P, K = ps * ps * 3, PP = P * P, Tn = PP + (has_cls ? 1 : 0);
-  (void)ws; (void)ws_bytes;
   if (patch_tc_path(words, w_act, P, S, H, dt)) {
     // tensor-core path: patch gather (bf16 words, kept for the backward wgrad) -> tcgen05 GEMM whose epilogue adds bias and
     // pos_emb[token] and stores into the token rows of (B, T, H) -> the B cls rows
@@ -300,7 +300,13 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
     VITB_LAUNCH((words_bf16_kernel), blocks, 256, 0, st, img, (bf16*)words, B, S, P);
     VITB_LAUNCH_OK();
-    int rc = tc_patch_fwd(words, w_act, bias, pos, out, B, PP, Tn, has_cls ? 1 : 0, H, K, st);
+    const void* pos_bf16 = nullptr;
+    if (PP % 32 == 0 && ws != nullptr && ws_bytes >= vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)) {
+      int rc0 = vitb_cast_f32_to_bf16(pos, ws, (int64_t)Tn * H, stream);
+      if (rc0) return rc0;
+      pos_bf16 = ws;
+    }
+    int rc = tc_patch_fwd(words, w_act, bias, pos, pos_bf16, out, B, PP, Tn, has_cls ? 1 : 0, H, K, st);
     if (rc) return rc;
     if (has_cls) {
       VITB_LAUNCH((cls_rows_kernel<bf16>), B, 128, 0, st, cls, pos, (bf16*)out, B, Tn, H);

@@ -602,7 +602,9 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
         if (lane == 0) {
           if (stores_pending) tma_store_wait_read();  // the slab doubles as the output slab of the previous tile
           mbar_arrive_expect_tx(in_bar(ew), kSlabBytes);
-          tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, m0 + quarter * 32);
+          // (patch embedding: the "residual" is pos_emb, whose row is the token of the GEMM row, not the GEMM row itself)
+          const int in_row = p.out3 ? e.rm_offset + (m0 + quarter * 32) % e.rm_group : m0 + quarter * 32;
+          tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, in_row);
         }
       }
       const long long e0 = (p.dbg && ew == 0 && lane == 0) ? clock64() : 0;
@@ -967,8 +969,8 @@ bool tc_patch_ok(int PP, int H, int K) {
 
 // out (B, Tn, H) bf16: token rows off .. off + PP - 1 of every image = words · wᵀ + bias + pos[token]  (vit.py:66-70; the cls row is
 // written by the caller).  The epilogue stores straight into the (B, T, H) tensor through a 3-D map: no intermediate buffer.
-int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, void* out, int B, int PP, int Tn, int off, int H, int K,
-                 cudaStream_t st) {
+int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const float* pos, const void* pos_bf16, void* out, int B, int PP, int Tn,
+                 int off, int H, int K, cudaStream_t st) {
   const int M = B * PP;
   TcMaps m;
   if (make_map(&m.a, words, K, M, K, BM)) return -1;
@@ -980,7 +982,16 @@ int tc_patch_fwd(const void* words, const void* w_bf16, const float* bias, const
   t.M = M; t.N = H; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = H / kBN; t.splits = 1;
   t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.valid_n = H;
   t.e.mode = EPI_FWD; t.e.bias = bias; t.e.out = out; t.e.ldc = H;
-  t.out3 = 1; t.e.rm_group = PP; t.e.rm_stride = Tn; t.e.rm_offset = off; t.e.pos = pos;
+  t.out3 = 1; t.e.rm_group = PP; t.e.rm_stride = Tn; t.e.rm_offset = off;
+  if (pos_bf16 != nullptr && PP % 32 == 0) {
+    // pos_emb rides in like a residual: each epilogue warp TMA-loads the 32 token rows of its slab from the bf16 copy (the
+    // kernel has next to no L1 beside its shared memory: per-thread fp32 loads of pos cost more than the GEMM, 45 vs 20 us)
+    if (make_map(&m.in, pos_bf16, H, Tn, H, 32)) return -1;
+    t.has_in = 1;
+    t.e.residual = pos_bf16;
+  } else {
+    t.e.pos = pos;  // 32 rows of a slab span several images (PP < 32): per-thread fp32 loads
+  }
   return launch_tc<kBN, false, false>(m, t, st);
 }
 
