@@ -82,3 +82,20 @@ def test_oracle_is_never_imported_by_the_product_or_the_tools():
         if re.search(r"^\s*(import|from)\s+oracle\b", open(path).read(), re.M):
             offenders.append(os.path.relpath(path, root))
     assert offenders == []
+
+
+def test_round2_host_side_entry_points(built):
+    """Pure host functions added in round 2: workspace queries of the one-pass backward GEMM, argument checks of the deferred-
+    reduction window and of the data-parallel flag-wait bound (no device work)."""
+    lib = built.load_library()
+    bf16, f32 = 1, 0
+    assert lib.vitb_gemm_bwd_fused_ws_bytes(66560, 384, 384, bf16) >= 49 * 384 * 384 * 4   # one fp32 dW slice per CTA of a column block
+    assert lib.vitb_gemm_bwd_fused_ws_bytes(1000, 128, 256, bf16) > 0
+    for M, N, K, dt in ((66560, 1152, 384, bf16), (66560, 384, 100, bf16), (66560, 384, 384, f32), (66560, 768, 3072, bf16)):
+        assert lib.vitb_gemm_bwd_fused_ws_bytes(M, N, K, dt) == 0   # caller falls back to dgrad + wgrad
+    assert lib.vitb_defer_begin(None, 0) < 0 and b"arena" in lib.vitb_last_error()
+    assert lib.vitb_defer_flush(None) < 0          # no window open
+    assert lib.vitb_defer_used() == 0
+    assert lib.vitb_dp_set_timeout(0.0) < 0
+    assert lib.vitb_dp_set_timeout(600.0) == 0
+    assert lib.vitb_patch_embed_fwd_ws_bytes(128, 32, 8, 384, bf16) >= 65 * 384 * 2   # bf16 copy of pos_emb for the GEMM epilogue
