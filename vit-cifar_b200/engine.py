@@ -1,11 +1,20 @@
-"""``TrainEngine``: the whole training step (forward + LS-CE + backward + gradient all-reduce + Adam) of a packed
+"""``TrainEngine``: the whole training step (forward + LS-CE + backward + gradient averaging + Adam) of a packed
 ``ViT`` as ONE static kernel sequence, captured into a CUDA graph.
 
 This is the caller the reference gets from Lightning (network.py:149-208 + automatic optimisation + DDP,
-SURVEY.md §3.1) reduced to the hot loop: no autograd, no allocation, no host sync inside a step.  Data-parallel
-across ranks (one process per GPU): each encoder layer's gradients are one contiguous bucket of the flat gradient
-buffer, all-reduced (NCCL, sum) on a side stream as soon as that layer's backward has been issued, so the
-exchange overlaps the remaining backward; the 1/world_size of DDP's mean is folded into Adam's gradient scale.
+SURVEY.md §3.1) reduced to the hot loop: no autograd, no allocation, no host sync inside a step.
+
+* Batches of 1..batch_size images (the reference's DataLoader keeps the partial last batch of an epoch): the loss kernel reads
+  the number of valid rows from device memory.
+* Backward: the weight-gradient GEMMs run on a second stream (nothing reads dW before the optimiser), the critical path on a
+  high-priority stream; the second passes of all split reductions are deferred to one flush before the optimiser
+  (``vitb_defer_begin`` / ``vitb_defer_flush``), every call owning its slice of a partial-sum arena.
+* Data parallel (one process per GPU): by default gradient averaging and the optimiser are one peer-memory kernel
+  (csrc/dp.cu; ``VITB_DP_MODE=fused``); ``single`` = one NCCL all-reduce of the flat gradient buffer after backward, ``overlap`` =
+  per-layer buckets on a side stream as soon as that layer's backward has been issued.  The 1/world_size of DDP's mean is folded
+  into the optimiser's gradient scale.
+* ``checkpoint()`` / ``load_checkpoint()`` / ``sync_weights()``: Lightning-format checkpoints with optimiser state, and the hook
+  to call after writing weights from outside the step.
 """
 from __future__ import annotations
 
