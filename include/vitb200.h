@@ -205,6 +205,10 @@ int vitb_gemm_bwd_fused(const void* dy, const void* x, const void* w, const void
  * have held in the last begin..flush window. ---- */
 int vitb_defer_begin(void* arena, size_t arena_bytes);
 int vitb_defer_flush(void* stream);
+/* runs the second passes recorded so far on `stream` (which the caller has ordered after every kernel that produced those
+ * partials) and keeps the window open: lets a training step reduce layer i's gradients on a side stream while layer i - 1's
+ * backward runs */
+int vitb_defer_flush_partial(void* stream);
 size_t vitb_defer_used(void);
 
 /* ---- Adam with coupled L2 over a flat buffer: torch.optim.Adam as configured at network.py:71-77

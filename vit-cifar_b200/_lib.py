@@ -63,6 +63,7 @@ SIGNATURES = {
     "vitb_gemm_bwd_fused": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
     "vitb_defer_begin": (_i, [_p, _sz]),
     "vitb_defer_flush": (_i, [_p]),
+    "vitb_defer_flush_partial": (_i, [_p]),
     "vitb_defer_used": (_sz, []),
     "vitb_adam_multi": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "vitb_sgd_multi": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p]),

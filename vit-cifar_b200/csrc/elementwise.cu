@@ -810,6 +810,14 @@ int vitb_defer_flush(void* stream) {
   return rc;
 }
 
+int vitb_defer_flush_partial(void* stream) {
+  VITB_REQUIRE(g_defer.active, "defer_flush_partial: vitb_defer_begin has not been called");
+  int rc = flush_jobs(g_defer.plain, false, (cudaStream_t)stream);
+  if (rc == 0) rc = flush_jobs(g_defer.tall, true, (cudaStream_t)stream);
+  g_defer.plain.clear(); g_defer.tall.clear();  // the window stays open; the arena keeps growing
+  return rc;
+}
+
 size_t vitb_defer_used(void) { return g_defer.high; }
 
 int vitb_augment_crop_flip_normalize(const uint8_t* img_u8, const int32_t* dx, const int32_t* dy, const uint8_t* flip, const float* mean3,

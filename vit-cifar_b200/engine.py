@@ -179,6 +179,11 @@ class TrainEngine:
         ws_mode = int(os.environ.get("VITB_WGRAD_STREAM", "2")) if self._defer else 0
         self._side = None
         self._main_stream = None
+        # second passes of a layer's reductions on the side stream right after that layer's backward (instead of all at the end):
+        # +0.4-1.1 % on the 384-wide models (B = 1024 / 128, T = 65 / 17), -1.4 % on the 768 / 3072 model, whose flushes are large
+        # enough to compete with the critical path (profiles/r2_flush_per_layer_ab.md) -> on for small weight matrices only
+        env = os.environ.get("VITB_FLUSH_PER_LAYER")
+        self._flush_per_layer = (env != "0") if env is not None else (model.hidden * max(model.hidden, model.mlp_hidden) <= 384 * 1536)
         if ws_mode >= 1:
             if ws_mode >= 2:  # critical path on a high-priority stream: its pending CTAs get the SMs first
                 self._main_stream = torch.cuda.Stream(device=self.dev, priority=-1)
@@ -282,6 +287,10 @@ class TrainEngine:
             dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i),
                                 drop=self.drops[i] if self.drops else None, side=side)
             if side is not None:
+                if self._defer and self._flush_per_layer:
+                    # this layer's second passes on the side stream (ordered after everything issued so far on both streams),
+                    # while the main stream goes on with the next layer's backward
+                    side.run(ops.defer_flush_partial)
                 done[i] = side.done_event()
             self._allreduce(self.buckets[1 + i])
         g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g

@@ -270,6 +270,11 @@ def defer_flush() -> None:
     check(_lib.load().vitb_defer_flush(_stream()), "defer_flush")
 
 
+def defer_flush_partial() -> None:
+    """Second passes recorded so far, on the current stream (ordered after the kernels that produced the partials); window stays open."""
+    check(_lib.load().vitb_defer_flush_partial(_stream()), "defer_flush_partial")
+
+
 def defer_used() -> int:
     return int(_lib.load().vitb_defer_used())
 
