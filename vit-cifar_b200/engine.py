@@ -184,6 +184,9 @@ class TrainEngine:
         # enough to compete with the critical path (profiles/r2_flush_per_layer_ab.md) -> on for small weight matrices only
         env = os.environ.get("VITB_FLUSH_PER_LAYER")
         self._flush_per_layer = (env != "0") if env is not None else (model.hidden * max(model.hidden, model.mlp_hidden) <= 384 * 1536)
+        # ... and, on one GPU, the optimiser step of that layer's parameters right behind it (with several GPUs the exchange comes first)
+        self._opt_per_layer = self._flush_per_layer and self.world == 1 and os.environ.get("VITB_OPT_PER_LAYER", "1") != "0"
+        self._opt_done_from = 0
         if ws_mode >= 1:
             if ws_mode >= 2:  # critical path on a high-priority stream: its pending CTAs get the SMs first
                 self._main_stream = torch.cuda.Stream(device=self.dev, priority=-1)
@@ -246,16 +249,25 @@ class TrainEngine:
         else:
             ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, n_valid_dev=n_valid_dev)
 
+        self._opt_done_from = self.n  # elements [_opt_done_from, n) have had their optimiser step on the side stream
         self._backward(hsaved, saved, words)
         n = self.n
         if self._fused_dp is not None:
             f = self._fused_dp
             ops.dp_reduce_adam(f["g"], f["p"], f["c"], f["flags"], self.Mo, self.V, f["sync"], n, f["rank"], self.world, hyper_dev=self.hyper_dev,
                                optimizer=0 if self.optimizer == "adam" else 1)
-        elif self.optimizer == "adam":
-            ops.adam(self.P[:n], self.G[:n], self.Mo[:n], self.V[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
         else:
-            ops.sgd(self.P[:n], self.G[:n], self.Mo[:n], self.C[:n] if self.C is not self.P else None, hyper_dev=self.hyper_dev)
+            self._optimizer_slice(0, self._opt_done_from)
+
+    def _optimizer_slice(self, lo: int, hi: int) -> None:
+        """Optimiser step on elements [lo, hi) of the flat buffers (slot boundaries: 64-element aligned)."""
+        if hi <= lo:
+            return
+        shadow = self.C[lo:hi] if self.C is not self.P else None
+        if self.optimizer == "adam":
+            ops.adam(self.P[lo:hi], self.G[lo:hi], self.Mo[lo:hi], self.V[lo:hi], shadow, hyper_dev=self.hyper_dev)
+        else:
+            ops.sgd(self.P[lo:hi], self.G[lo:hi], self.Mo[lo:hi], shadow, hyper_dev=self.hyper_dev)
 
     def _backward(self, hsaved, saved, words) -> None:
         m, dm = self.model, self.dm
@@ -289,8 +301,14 @@ class TrainEngine:
             if side is not None:
                 if self._defer and self._flush_per_layer:
                     # this layer's second passes on the side stream (ordered after everything issued so far on both streams),
-                    # while the main stream goes on with the next layer's backward
+                    # while the main stream goes on with the next layer's backward; on one GPU the optimiser step of the
+                    # layer's slice of the flat buffers follows at once (its gradients are final, its weights no longer read)
                     side.run(ops.defer_flush_partial)
+                    if self._opt_per_layer:
+                        lo = self.buckets[1 + i][0]
+                        hi = self._opt_done_from
+                        side.run(lambda lo=lo, hi=hi: self._optimizer_slice(lo, hi))
+                        self._opt_done_from = lo
                 done[i] = side.done_event()
             self._allreduce(self.buckets[1 + i])
         g_emb_w, g_emb_b, g_cls, g_pos = self.stem_g
