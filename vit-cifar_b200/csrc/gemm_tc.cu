@@ -947,6 +947,12 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 0, false>(m, args, st);
   // (a pre-activation output shares the output slab, see the epilogue: every variant keeps 3 ring stages per stream)
   if (res) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, true>(m, args, st);
+  // Small problems (at most two tiles per SM, K <= 384: batch 128, T = 17): the kernel is one load latency + one tile of MMAs +
+  // one epilogue long.  One stream with the WHOLE reduction of a tile in flight (3 stages x 2 k-blocks = 192 KB) needs a single
+  // round trip to memory where two 3 x 1 rings need two (VITB_GEMM_SMALL_DEEP=0 switches it off).
+  static const bool small_deep = getenv("VITB_GEMM_SMALL_DEEP") ? atoi(getenv("VITB_GEMM_SMALL_DEEP")) != 0 : true;
+  if (small_deep && args.kblocks_total <= 6 && args.num_m_blocks * args.num_n_blocks * args.splits <= 2 * kNumSMs)
+    return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, false>(m, args, st);
   return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, false>(m, args, st);
   }
 }
