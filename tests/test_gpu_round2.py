@@ -128,7 +128,9 @@ def mm32(a, b):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-BENCH_FWD = [(66560, 1152, 384), (66560, 384, 384), (33280, 768, 3072), (33280, 3072, 768), (33280, 2304, 768), (8320, 1152, 384), (8320, 384, 384)]
+BENCH_FWD = [(66560, 1152, 384), (66560, 384, 384), (33280, 768, 3072), (33280, 3072, 768), (33280, 2304, 768), (8320, 1152, 384), (8320, 384, 384),
+             # 128 x 192 tiles (one wave instead of two): 8,320 x 384 above, and a ragged / an N = 1152 case
+             (7000, 384, 128), (2560, 1152, 384)]
 
 
 @pytest.mark.parametrize("M,N,K", BENCH_FWD)
@@ -148,7 +150,8 @@ def test_gemm_fwd_benchmark_shapes(ops, M, N, K):
 
 
 # (rows, N = width of dY, K = width of dX)
-BENCH_DGRAD = [(66560, 1152, 384), (66560, 384, 384), (33280, 3072, 768), (33280, 768, 3072), (33280, 2304, 768), (8320, 1152, 384)]
+BENCH_DGRAD = [(66560, 1152, 384), (66560, 384, 384), (33280, 3072, 768), (33280, 768, 3072), (33280, 2304, 768), (8320, 1152, 384),
+               (8320, 384, 384), (7000, 128, 384)]  # (the last three run on 128 x 192 tiles)
 
 
 @pytest.mark.parametrize("M,N,K", BENCH_DGRAD)

@@ -28,7 +28,10 @@ constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 along the contiguous dimension
 constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarps = 8;
-constexpr int tc_threads(int ns) { return (2 * ns + kEpiWarps) * 32; }  // NS TMA warps + NS MMA warps + 8 epilogue warps
+// epilogue warps of an instantiation: 4 TMEM lane quarters x (BN / 64) column groups of 64 in the slab epilogue of the 192-wide
+// forward / dgrad tiles (12 warps), 8 everywhere else
+constexpr int epi_warps_for(int bn, int nslab) { return (bn == 192 && nslab > 0) ? 12 : kEpiWarps; }
+constexpr int tc_threads(int ns, int ew = kEpiWarps) { return (2 * ns + ew) * 32; }  // NS TMA warps + NS MMA warps + the epilogue warps
 constexpr uint32_t kTmemCols = 512;  // NS x ACC accumulators of 128 columns (+ 16-column bias-gradient accumulators in wgrad)
 constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16, 128B swizzle
 
@@ -224,6 +227,7 @@ constexpr int kMaxResKB = 6;  // resident-B mode keeps up to 6 k-blocks (K <= 38
 template <int BN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG = 1>
 struct TcSmem {
   static constexpr int kAcc = (NS == 2 && NSLAB == 0) ? 1 : 2;  // TMEM accumulator stages per stream (wgrad items are long: 1 is enough)
+  static constexpr int kEW = epi_warps_for(BN, NSLAB);
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;  // a CTA of a pair holds half of the B tile
   static constexpr uint32_t kSubBytes = W_RES ? kABytes : kABytes + kBBytes;  // one k-block
@@ -232,10 +236,10 @@ struct TcSmem {
   static constexpr uint32_t kRingOff = kResBytes;
   static constexpr uint32_t kRingBytes = STAGES * kStageBytes;  // per stream
   static constexpr uint32_t kEpiOff = kRingOff + NS * kRingBytes;
-  static constexpr uint32_t kEpiBytes = NSLAB > 0 ? kEpiWarps * NSLAB * kSlabBytes : 2048;  // NSLAB slabs per epilogue warp, or the all-ones wgrad operand
+  static constexpr uint32_t kEpiBytes = NSLAB > 0 ? kEW * NSLAB * kSlabBytes : 2048;  // NSLAB slabs per epilogue warp, or the all-ones wgrad operand
   static constexpr uint32_t kBarOff = kEpiOff + kEpiBytes;
   static constexpr uint32_t kBarsPerStream = 2 * STAGES + 4;  // full[STAGES] empty[STAGES] tfull[2] tempty[2]
-  static constexpr uint32_t kNumBars = NS * kBarsPerStream + kEpiWarps + 1;
+  static constexpr uint32_t kNumBars = NS * kBarsPerStream + kEW + 1;
   static constexpr uint32_t kTotal = kBarOff + kNumBars * 8 + 16;
   static constexpr uint32_t kDynBytes = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
@@ -275,18 +279,20 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // for both; full / accumulator-empty barriers live in the leader (the peer's TMA loads and epilogue warps signal them remotely),
 // empty / accumulator-full barriers exist in both CTAs and are signalled by multicast tcgen05.commit.
 template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG>
-__global__ void __launch_bounds__(tc_threads(NS), 1)
+__global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                    const __grid_constant__ CUtensorMap tma_in, const TcArgs p) {
   using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
   constexpr int ACC = S::kAcc;
+  constexpr int EW = S::kEW;
   constexpr bool PAIR = CG == 2;
   static_assert(!PAIR || (W_RES && !A_MN && NSLAB > 0 && KPS == 1), "pair mode: resident-weight fwd / dgrad kernels only");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   static_assert(NS * ACC * BN + NS * 16 <= (int)kTmemCols || NSLAB > 0, "TMEM plan");
-  static_assert(BN == 128 || (NSLAB == 0 && BN % 64 == 0 && BN <= 256), "the slab epilogue assumes two 64-column halves; the fp32 direct-store epilogue takes any BN = 64 j");
+  static_assert(BN == 128 || (BN == 192 && NSLAB > 0 && !W_RES && CG == 1) || (NSLAB == 0 && BN % 64 == 0 && BN <= 256),
+                "slab epilogue: one warp per TMEM lane quarter and 64-column group (BN = 128: 8 warps, BN = 192: 12); the fp32 direct-store epilogue takes any BN = 64 j");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   auto tfull_bar = [&](int st, int a) { return bar_base + (uint32_t)(st * S::kBarsPerStream + 2 * STAGES + a) * 8; };
   auto tempty_bar = [&](int st, int a) { return bar_base + (uint32_t)(st * S::kBarsPerStream + 2 * STAGES + 2 + a) * 8; };
   auto in_bar = [&](int w) { return bar_base + (uint32_t)(NS * S::kBarsPerStream + w) * 8; };
-  const uint32_t wfull_bar = bar_base + (uint32_t)(NS * S::kBarsPerStream + kEpiWarps) * 8;
+  const uint32_t wfull_bar = bar_base + (uint32_t)(NS * S::kBarsPerStream + EW) * 8;
   // TMEM columns: accumulator a of stream st, and the stream's 16-column bias-gradient accumulator (wgrad)
   auto acc_col = [&](int st, int a) { return (uint32_t)((st * ACC + a) * BN); };
   auto bias_col = [&](int st, int a) { return (uint32_t)(NS * ACC * BN + (st * ACC + a) * 16); };
@@ -328,10 +334,10 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(st, a), 1);
-        mbar_init(tempty_bar(st, a), kEpiWarps * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
+        mbar_init(tempty_bar(st, a), EW * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
       }
     }
-    for (int w = 0; w < kEpiWarps; ++w) mbar_init(in_bar(w), 1);
+    for (int w = 0; w < EW; ++w) mbar_init(in_bar(w), 1);
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
   if (want_dbias && warp >= 2 * NS) {
     // all-ones bf16 operand (16 rows x 128 B, any layout reads ones); overlays the unused epilogue slabs
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + S::kEpiOff);
-    for (int i = threadIdx.x - 64 * NS; i < 2048 / 4; i += kEpiWarps * 32) ones[i] = 0x3F803F80u;
+    for (int i = threadIdx.x - 64 * NS; i < 2048 / 4; i += EW * 32) ones[i] = 0x3F803F80u;
     fence_async_smem();
   }
   tc_fence_before();
@@ -582,7 +588,8 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
     // the CTA's tile order, alternating between the streams ==========
     const int ew = warp - 2 * NS;
     const int quarter = warp & 3;
-    const int half = ew >> 2;
+    const int half = ew >> 2;                         // column group of this warp: 64 columns in the slab epilogue, BN / 2 in the fp32 one
+    constexpr int kColW = NSLAB > 0 ? 64 : BN / 2;
     const int row_in_tile = quarter * 32 + lane;
     // slab 0: output — and, before that, the input operand (residual / z), which is consumed in place; slab 1: pre-activation
     const uint32_t slab_out = epi_base + (uint32_t)(ew * NSLAB + 0) * kSlabBytes;
@@ -596,7 +603,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
       const int st_ = it % NS, jt = it / NS;           // stream, and the tile's index inside the stream
       const int acc = jt % ACC;
       const uint32_t acc_phase = (uint32_t)(jt / ACC) & 1u;
-      const int n0 = nb0 + half * (BN / 2);
+      const int n0 = nb0 + half * kColW;
       const int grow = m0 + row_in_tile;
       if (p.has_in) {  // fetch this warp's residual / z slab while the MMAs of the tile run
         if (lane == 0) {
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(tc_threads(NS), 1)
         continue;
       }
       if (p.dbg && ew == 0 && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] += clock64() - e0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col(st_, acc) + (uint32_t)(half * (BN / 2));
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col(st_, acc) + (uint32_t)(half * kColW);
       if constexpr (NSLAB == 0) {
         // fp32 split-K partials straight from registers: this warp owns 32 rows x BN/2 columns, drained 32 columns at a time
         const bool do_bias = want_dbias && nblk == 0 && half == 0;
@@ -870,7 +877,7 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
       if (max_clusters < 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kNumSMs / 2 * 2);
-        cfg.blockDim = dim3(tc_threads(NS));
+        cfg.blockDim = dim3(tc_threads(NS, S::kEW));
         cfg.dynamicSmemBytes = S::kDynBytes;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -890,9 +897,9 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
     grid = tiles < kNumSMs ? tiles : kNumSMs;
   }
   if (CG == 2) {
-    VITB_CUDA_OK(::vitb::launch_kernel_cluster(kern, grid, tc_threads(NS), S::kDynBytes, st, 2, m.a, m.b, m.out, m.pre, m.in, args));
+    VITB_CUDA_OK(::vitb::launch_kernel_cluster(kern, grid, tc_threads(NS, S::kEW), S::kDynBytes, st, 2, m.a, m.b, m.out, m.pre, m.in, args));
   } else {
-    VITB_LAUNCH((kern), grid, tc_threads(NS), S::kDynBytes, st, m.a, m.b, m.out, m.pre, m.in, args);
+    VITB_LAUNCH((kern), grid, tc_threads(NS, S::kEW), S::kDynBytes, st, m.a, m.b, m.out, m.pre, m.in, args);
   }
   VITB_LAUNCH_OK();
   return 0;
@@ -934,9 +941,11 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   args.pf_tiles = g_tc_pf_tiles;
   args.pf_kblocks = g_tc_pf_kblocks;
   if constexpr (BN != 128) {
-    // wide wgrad tiles (BN = 192): a 128x192x16 MMA holds the pipe for 96 cycles, which one issuing thread can sustain, and the
-    // operand bytes per FLOP drop by a sixth; single stream, 5 stages x 40 KB
-    return launch_tc_impl<BN, A_MN, B_MN, 1, 5, 1, 0, false>(m, args, st);
+    // wide tiles (BN = 192): a 128x192x16 MMA holds the pipe for 96 cycles, which one issuing thread can sustain, and the
+    // operand bytes per FLOP drop by a sixth; single stream.  wgrad: 5 stages x 40 KB, fp32 direct-store epilogue;
+    // forward / dgrad (A K-major): 4 stages x 40 KB and a 12-warp slab epilogue
+    if constexpr (A_MN) return launch_tc_impl<BN, A_MN, B_MN, 1, 5, 1, 0, false>(m, args, st);
+    else return launch_tc_impl<BN, A_MN, B_MN, 1, 4, 1, 1, false>(m, args, st);
   } else {
   const bool res = !A_MN && use_resident_weights(args);
   if (g_tc_streams == 1) {
@@ -959,6 +968,20 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
 
 // K needs only a 16-byte row pitch: a partial last k-block is zero-filled by TMA
 static bool tc_shape_ok(int M, int N, int K) { return M >= 32 && N % kBN == 0 && K % 8 == 0; }
+
+// 128 x 192 output tiles for forward / dgrad (12-warp slab epilogue).  Used (a) when they turn a problem of more than one
+// wave of 128 x 128 tiles into a single wave (8,320 rows x 384 columns: 130 tiles instead of 195 on 148 SMs — the kernel is then one
+// tile long instead of two), and (b) VITB_GEMM_BN192_STREAM=1 (experiment): for outputs whose weight slice cannot be resident
+// (reduction > 384, e.g. the QKV dgrad), where two column blocks instead of three read A twice instead of three times.
+static bool use_bn192(int M, int Nout, int Kred) {
+  static const int mode = getenv("VITB_GEMM_BN192") ? atoi(getenv("VITB_GEMM_BN192")) : 1;
+  static const bool stream = getenv("VITB_GEMM_BN192_STREAM") && atoi(getenv("VITB_GEMM_BN192_STREAM")) != 0;
+  if (mode == 0 || Nout % 192 != 0) return false;
+  const int mb = ceil_div(M, BM);
+  if (mb * (Nout / 192) <= kNumSMs && mb * (Nout / 128) > kNumSMs) return true;
+  if (stream && Kred > kMaxResKB * BK && mb * (Nout / 192) >= 4 * kNumSMs) return true;
+  return false;
+}
 
 static int check_dt(int dt) {
   VITB_REQUIRE(dt == VITB_F32 || dt == VITB_BF16, "dt must be VITB_F32 or VITB_BF16 (got %d)", dt);
@@ -1163,6 +1186,11 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = N;
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
+    if (use_bn192(M, N, K)) {
+      if (make_map(&m.b, w, K, N, K, 192)) return -1;
+      t.num_n_blocks = N / 192;
+      return launch_tc<192, false, false>(m, t, st);
+    }
     return launch_tc<kBN, false, false>(m, t, st);
   }
   if (e.out_f32 && !e.gelu && !residual && !preact && head_shape_ok(M, N, K)) return head_fwd_launch(a, w, bias, (float*)c, M, N, K, dt, st);
@@ -1192,6 +1220,10 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(N, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = K;
     t.has_in = z != nullptr;
+    if (use_bn192(M, K, N)) {  // (the MN-major weight boxes are 64 columns wide: the same map serves both tile widths)
+      t.num_n_blocks = K / 192;
+      return launch_tc<192, false, true>(m, t, st);
+    }
     return launch_tc<kBN, false, true>(m, t, st);
   }
   if (dy_f32 && !z && head_shape_ok(M, N, K)) return head_dgrad_launch((const float*)dy, w, dx, M, N, K, dt, st);
