@@ -266,7 +266,7 @@ def workload_name(n, batch=None):
 def probe_kernels(eng, steps=3):
     import torch
     from vit_cifar_b200 import ops
-    names = ["patch_embed_fwd", "patch_embed_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_fwd", "gemm_dgrad", "gemm_wgrad",
+    names = ["patch_embed_fwd", "patch_embed_bwd", "layernorm_fwd", "layernorm_bwd", "layernorm_bwd_fused", "gemm_fwd", "gemm_dgrad", "gemm_wgrad",
              "attn_fwd", "attn_bwd", "gelu_bwd_colsum", "colsum", "pool_fwd", "pool_bwd", "ls_ce", "adam"]
     rec = []
     orig = {}
@@ -350,7 +350,9 @@ def _kernel_roofline(row, pk, B, T, H):
         return r
     rows = B * T
     by = {
-        "layernorm_fwd": 2 * rows * H * E, "layernorm_bwd": 4 * rows * H * E, "attn_fwd": 4 * rows * H * E, "attn_bwd": 8 * rows * H * E,
+        "layernorm_fwd": 2 * rows * H * E, "layernorm_bwd": 4 * rows * H * E,
+        "layernorm_bwd_fused": 6 * rows * H * E,  # + z2 read and dz2 written (the next block's GELU backward)
+        "attn_fwd": 4 * rows * H * E, "attn_bwd": 8 * rows * H * E,
         "gelu_bwd_colsum": 3 * rows * H * E, "colsum": (sh[0] * sh[1] * E) if len(sh) >= 2 else 0,
         "patch_embed_fwd": B * 12288 + rows * H * E, "patch_embed_bwd": B * 12288 + rows * H * E,
     }.get(op)
@@ -468,7 +470,7 @@ def run_ours(args):
 
     vb.set_precision("bf16")
     torch.manual_seed(2045)  # main.py:150
-    model = vb.ViT(3, MODEL["num_classes"], img_size=32, patch=MODEL["patch"], dropout=0.0, num_layers=MODEL["num_layers"],
+    model = vb.ViT(3, MODEL["num_classes"], img_size=32, patch=MODEL["patch"], dropout=args.dropout, num_layers=MODEL["num_layers"],
                    hidden=MODEL["hidden"], mlp_hidden=MODEL["mlp_hidden"], head=MODEL["head"]).to(dev)
     B = args.batch
     eng = vb.TrainEngine(model, B, smoothing=SMOOTHING, process_group=pg, use_graph=not args.no_graph, **ADAM)
@@ -572,7 +574,8 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": round(ms_dev / args.steps, 4), "step_ms": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(world, B), "per_gpu_batch": B, "cuda_graph": not args.no_graph,
+            "config": {"workload": workload_name(world, B) + (f", dropout {args.dropout}" if args.dropout else ""), "per_gpu_batch": B,
+                       "cuda_graph": not args.no_graph,
                        "l2": "working set per step (>4 GB of activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}",
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
@@ -622,6 +625,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's, 1024 for the headline)")
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS), help="model shape (default: BASELINE.json's headline configuration)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="nn.Dropout probability of the encoder blocks (the reference's default and the headline: 0)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")

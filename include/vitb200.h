@@ -157,6 +157,39 @@ uint32_t vitb_dropout_threshold(float p);
 int vitb_dropout(const void* x, const void* residual, void* out, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step,
                  const uint32_t* step_dev, int dt, void* stream);
 
+/* ---- nn.Dropout fused into the kernel that produces (forward) or consumes (backward) the tensor it acts on, instead of a
+ * separate elementwise pass per site: the three Dropouts of an encoder block sit right behind a Linear / GELU (layers.py:35, 38,
+ * 102), and their backward right in front of the next backward kernel.  A site is described by a vitb_dropout_t; the mask is the
+ * one vitb_dropout draws for the same (p, seed, site, step) over the flattened output tensor, so fused and unfused calls are
+ * interchangeable element for element.  drop == NULL or p == 0: no dropout (the call equals its plain namesake).
+ *   vitb_gemm_bias_act_fwd_drop:  C = dropout(act(A W^T + bias)) + residual   (the pre-activation is stored before GELU, undropped)
+ *   vitb_gemm_dgrad_drop:         dX = dropout(dY W * gelu'(z))               (mask and gelu' commute: backward of GELU -> Dropout)
+ *   vitb_gelu_bwd_colsum_drop:    dz = dropout(dy) * gelu'(z); colsum over dz (backward of GELU -> Dropout, layers.py:37-38)
+ *   vitb_layernorm_bwd_fused:     dx as vitb_layernorm_bwd (dres required), plus a second output
+ *                                 dx2 (rows, H) = dropout(dx [* gelu'(z) if z != NULL]) and dx2_colsum (H) = its column sums:
+ *                                 z == NULL: the gradient entering out_project through its Dropout (layers.py:102) with out_project's
+ *                                 bias gradient; z != NULL: the gradient entering the PREVIOUS block's second MLP Linear through
+ *                                 Dropout and GELU (layers.py:36-38) with that Linear's bias gradient — dx is that block's output gradient.
+ * bf16 tensor-core shapes apply the mask in the epilogue; every other shape / fp32 runs the plain kernel followed by vitb_dropout
+ * (same result, one more launch). ---- */
+typedef struct vitb_dropout {
+  float p;                  /* drop probability, 0 <= p < 1 */
+  uint64_t seed;            /* Philox key */
+  uint32_t site;            /* which Dropout module (counter word 2) */
+  uint32_t step;            /* optimisation step (counter word 3) ... */
+  const uint32_t* step_dev; /* ... read from this device word instead when != NULL (CUDA-graph replays) */
+} vitb_dropout_t;
+int vitb_gemm_bias_act_fwd_drop(const void* a, const void* w_act, const float* bias, const void* residual, void* c, void* preact,
+                                int M, int N, int K, int flags, int dt, const vitb_dropout_t* drop, void* stream);
+int vitb_gemm_dgrad_drop(const void* dy, const void* w_act, const void* z, void* dx, int M, int N, int K, int flags, int dt,
+                         const vitb_dropout_t* drop, void* stream);
+int vitb_gelu_bwd_colsum_drop(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes, int rows, int cols,
+                              int dt, const vitb_dropout_t* drop, void* stream);
+int vitb_layernorm_bwd_fused(const void* dy, const void* x, int64_t x_row_stride, const float* gamma, const float* mean,
+                             const float* rstd, const void* dres, void* dx, int64_t dx_row_stride, float* dgamma, float* dbeta,
+                             const void* z, void* dx2, float* dx2_colsum, const vitb_dropout_t* drop, void* ws, size_t ws_bytes,
+                             int rows, int H, int dt, void* stream);
+
 /* ---- token pooling for the head: vit.py:72-75.  mode 0: y[b] = x[b,0] (cls); mode 1: mean over T.
  * bwd: dx (B,T,H) fully written (zeros where no gradient flows); mode 2 = cls pooling into a dx whose other rows the caller
  * keeps zero (a static buffer zeroed once): only the B cls rows are written. */

@@ -99,3 +99,22 @@ def test_round2_host_side_entry_points(built):
     assert lib.vitb_dp_set_timeout(0.0) < 0
     assert lib.vitb_dp_set_timeout(600.0) == 0
     assert lib.vitb_patch_embed_fwd_ws_bytes(128, 32, 8, 384, bf16) >= 65 * 384 * 2   # bf16 copy of pos_emb for the GEMM epilogue
+
+
+def test_dropout_descriptor_layout_matches_the_header(tmp_path):
+    """vitb_dropout_t is passed by pointer from ctypes: its field offsets in _lib.DropoutDesc must be the C compiler's."""
+    import ctypes
+    import subprocess
+    import vit_cifar_b200  # noqa: F401
+    from vit_cifar_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vitb200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(vitb_dropout_t), offsetof(vitb_dropout_t, p),\n'
+                   '  offsetof(vitb_dropout_t, seed), offsetof(vitb_dropout_t, site), offsetof(vitb_dropout_t, step), offsetof(vitb_dropout_t, step_dev));\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(t) for t in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    D = _lib.DropoutDesc
+    assert got == [ctypes.sizeof(D), D.p.offset, D.seed.offset, D.site.offset, D.step.offset, D.step_dev.offset]

@@ -389,3 +389,144 @@ def test_full_model_all_gradients_vs_oracle_at_batch_48(vb, cfg, precision):
             if e > worst[1]:
                 worst = (k, e)
         assert worst[1] < tol, (use_graph, worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# (e) nn.Dropout inside the producing / consuming kernels (layers.py:35, 38, 102) and the LayerNorm -> GELU-backward fusion
+# ---------------------------------------------------------------------------------------------
+DROP = dict(p=0.2, seed=0x1234ABCD5678EF01, step=7)
+
+
+def keep_mask(shape, site, p=DROP["p"]):
+    n = shape[0] * shape[1]
+    return torch.from_numpy(oracle.dropout_keep_mask(n, p, DROP["seed"], site, DROP["step"])).view(shape).cuda()
+
+
+def gelu_grad(z):
+    zz = z.float().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    return zz.grad
+
+
+# (M, N, K): resident-weight plan (K <= 384), streaming plan (K = 1536), a ragged M, and a shape that would otherwise take 128 x 192 tiles
+@pytest.mark.parametrize("M,N,K", [(4096 + 37, 384, 384), (4096, 384, 1536), (8320, 384, 384), (20000, 1152, 384)])
+def test_gemm_fwd_dropout_in_epilogue(ops, M, N, K):
+    """C = dropout(act(A W^T + b)) + residual with the mask applied in the tcgen05 epilogue: the kept positions are exactly the
+    oracle's Philox mask over the flattened output, values match the fp32 product, and the pre-activation is stored undropped."""
+    a = rnd_cuda((M, K), 1); w = rnd_cuda((N, K), 2, 1 / math.sqrt(K)); bias = rnd_cuda((N,), 3).float(); res = rnd_cuda((M, N), 4)
+    z_ref = mm32(a, w.t()) + bias
+    keep = keep_mask((M, N), 1).float() / (1 - DROP["p"])
+    d = ops.drop_desc(DROP["p"], DROP["seed"], 1, DROP["step"])
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda"); pre = torch.empty_like(out)
+    ops.gemm_fwd(a, w, bias, None, out, None, M, N, K, drop=d)
+    assert torch.equal(out != 0, (keep != 0) & (out != 0)) and ((out == 0) & (keep != 0)).float().mean() < 1e-3  # dropped <=> zero
+    assert rel(out, z_ref * keep) < 2e-2
+    ops.gemm_fwd(a, w, bias, res, out, pre, M, N, K, gelu=True, drop=d)
+    assert rel(pre, z_ref) < 2e-2
+    assert rel(out, F.gelu(z_ref) * keep + res.float()) < 2e-2
+    assert torch.equal(out[keep == 0], res[keep == 0])                    # a dropped element is exactly the residual
+    # step read from device memory (graph replays) draws the same mask as the host value
+    step_dev = torch.tensor([DROP["step"]], dtype=torch.int32, device="cuda")
+    out2 = torch.empty_like(out)
+    ops.gemm_fwd(a, w, bias, res, out2, None, M, N, K, gelu=True, drop=ops.drop_desc(DROP["p"], DROP["seed"], 1, 0, step_dev))
+    assert torch.equal(out, out2)
+    # and the unfused composition (plain GEMM, then vitb_dropout) agrees to bf16 rounding (it rounds once more)
+    ops.gemm_fwd(a, w, bias, None, out2, None, M, N, K, gelu=True)
+    ops.dropout(out2, res, out2, DROP["p"], DROP["seed"], 1, DROP["step"])
+    assert rel(out, out2) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(4096 + 37, 384, 384), (4096, 1536, 384), (8320, 384, 384)])
+def test_gemm_dgrad_dropout_in_epilogue(ops, M, N, K):
+    dy = rnd_cuda((M, N), 1); w = rnd_cuda((N, K), 2, 1 / math.sqrt(N)); z = rnd_cuda((M, K), 3)
+    ref = mm32(dy, w)
+    keep = keep_mask((M, K), 1).float() / (1 - DROP["p"])
+    d = ops.drop_desc(DROP["p"], DROP["seed"], 1, DROP["step"])
+    dx = torch.empty((M, K), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_dgrad(dy, w, None, dx, M, N, K, drop=d)
+    assert rel(dx, ref * keep) < 2e-2 and bool((dx[keep == 0] == 0).all())
+    ops.gemm_dgrad(dy, w, z, dx, M, N, K, drop=d)
+    assert rel(dx, ref * gelu_grad(z) * keep) < 2e-2 and bool((dx[keep == 0] == 0).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,cols", [(4133, 384), (1000, 768), (300, 256)])
+def test_gelu_backward_with_dropout_mask(ops, dtype, rows, cols):
+    dy = rnd_cuda((rows, cols), 1).to(dtype); z = rnd_cuda((rows, cols), 2).to(dtype)
+    keep = keep_mask((rows, cols), 2).float() / (1 - DROP["p"])
+    dz = torch.empty_like(dy); cs = torch.empty(cols, dtype=torch.float32, device="cuda")
+    ops.gelu_bwd_colsum(dy, z, dz, cs, rows, cols, drop=ops.drop_desc(DROP["p"], DROP["seed"], 2, DROP["step"]))
+    ref = dy.float() * keep * gelu_grad(z)
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-5
+    assert rel(dz, ref) < tol and rel(cs, ref.sum(0)) < tol
+    assert bool((dz[keep == 0] == 0).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,H", [(4133, 384), (999, 768), (130, 128)])
+def test_layernorm_backward_second_output(ops, dtype, rows, H):
+    """vitb_layernorm_bwd_fused: dx / dgamma / dbeta are those of vitb_layernorm_bwd bit for bit; dx2 computed from the stored dx
+    equals the stand-alone kernels' result bit for bit where they round at the same points (mask only, gelu' only) and to rounding
+    where the stand-alone chain rounds once more (mask, then gelu')."""
+    x = rnd_cuda((rows, H), 1).to(dtype); dy = rnd_cuda((rows, H), 2).to(dtype); dres = rnd_cuda((rows, H), 3).to(dtype)
+    z = rnd_cuda((rows, H), 4).to(dtype)
+    gamma = (1 + 0.1 * rnd_cuda((H,), 5).float()); beta = rnd_cuda((H,), 6).float()
+    y = torch.empty_like(x); mean = torch.empty(rows, device="cuda"); rstd = torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, H, gamma, beta, y, mean, rstd, rows, H)
+    f32 = lambda: torch.empty(H, dtype=torch.float32, device="cuda")  # noqa: E731
+    dx0 = torch.empty_like(x); dg0, db0, cs0 = f32(), f32(), f32()
+    ops.layernorm_bwd(dy, x, H, gamma, mean, rstd, dres, dx0, H, dg0, db0, cs0, rows, H)
+    d = ops.drop_desc(DROP["p"], DROP["seed"], 0, DROP["step"])
+    tol = 6e-3 if dtype == torch.bfloat16 else 1e-5
+    for use_z, use_drop in [(False, True), (True, False), (True, True)]:
+        dx = torch.empty_like(x); dx2 = torch.empty_like(x); dg, db, cs = f32(), f32(), f32()
+        ops.layernorm_bwd_fused(dy, x, H, gamma, mean, rstd, dres, dx, H, dg, db, z if use_z else None, dx2, cs, rows, H,
+                                drop=d if use_drop else None)
+        assert torch.equal(dx, dx0) and torch.equal(dg, dg0) and torch.equal(db, db0)
+        ref = torch.empty_like(x); cs_ref = f32()
+        if use_drop and not use_z:
+            ops.dropout(dx0, None, ref, DROP["p"], DROP["seed"], 0, DROP["step"])
+            assert torch.equal(dx2, ref)
+            assert rel(cs, ref.float().sum(0)) < tol
+        elif use_z and not use_drop:
+            ops.gelu_bwd_colsum(dx0, z, ref, cs_ref, rows, H)
+            assert torch.equal(dx2, ref)
+            assert rel(cs, cs_ref) < 1e-5
+        else:
+            ops.gelu_bwd_colsum(dx0, z, ref, cs_ref, rows, H, drop=d)
+            assert torch.equal(dx2, ref)                                   # same arithmetic: mask on the stored dx, then gelu'
+            assert rel(cs, cs_ref) < 1e-5
+            keep = keep_mask((rows, H), 0).float() / (1 - DROP["p"])
+            assert rel(dx2, dx0.float() * keep * gelu_grad(z)) < tol
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_engine_fused_and_unfused_backward_chains_agree(vb, monkeypatch, p_drop):
+    """The cross-block fusion (LayerNorm-1 backward of block i + 1 writes block i's dz2) and the in-kernel dropout masks against
+    the stand-alone passes (VITB_LN_GELU_FUSED=0, VITB_DROP_FUSED=0): same gradients to bf16 rounding after one step, and for
+    p = 0 every gradient except the b2 column sums (another partial-sum grouping) bit for bit."""
+    cfg, B = TINY65, 16
+    x = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    y = torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(6))
+
+    def run(fused: bool):
+        monkeypatch.setenv("VITB_LN_GELU_FUSED", "1" if fused else "0")
+        monkeypatch.setenv("VITB_DROP_FUSED", "1" if fused else "0")
+        vb.set_precision("bf16")
+        torch.manual_seed(0)
+        m = vb.ViT(3, cfg.num_classes, img_size=cfg.img_size, patch=cfg.patch, dropout=p_drop, num_layers=cfg.num_layers,
+                   hidden=cfg.hidden, mlp_hidden=cfg.mlp_hidden, head=cfg.head, is_cls_token=cfg.is_cls_token).cuda()
+        eng = vb.TrainEngine(m, B, smoothing=0.1, use_graph=False, **ADAM)
+        loss = eng.step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        return float(loss), eng.G.clone(), eng.store.layout
+
+    l1, g1, layout = run(True)
+    l0, g0, _ = run(False)
+    assert abs(l1 - l0) < 5e-3 * abs(l0)
+    assert rel(g1, g0) < (1e-6 if p_drop == 0.0 else 2e-2)
+    if p_drop == 0.0:
+        diff = (g1 != g0)
+        for i in range(cfg.num_layers - 1):  # b2 of every block but the last comes from another kernel's partial sums
+            layout.view(diff, f"enc.{i}.mlp.3.bias").fill_(False)
+        assert not bool(diff.any())

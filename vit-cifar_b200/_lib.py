@@ -26,6 +26,13 @@ _i64 = C.c_int64
 _f = C.c_float
 _sz = C.c_size_t
 
+class DropoutDesc(C.Structure):
+    """vitb_dropout_t (include/vitb200.h): one nn.Dropout site for the fused kernels."""
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64), ("site", C.c_uint32), ("step", C.c_uint32), ("step_dev", C.c_void_p)]
+
+
+_dp = C.POINTER(DropoutDesc)
+
 # name -> (restype, argtypes); mirrors include/vitb200.h exactly (checked by tests/test_abi.py)
 SIGNATURES = {
     "vitb_version": (_i, []),
@@ -59,6 +66,10 @@ SIGNATURES = {
     "vitb_ls_ce_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_mix_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _i, _i, _f, _f, _p]),
     "vitb_ls_ce_batch_fwd_bwd": (_i, [_p, _p, _p, _f, _p, _p, _p, _p, _i, _i, _f, _f, _p]),
+    "vitb_gemm_bias_act_fwd_drop": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _dp, _p]),
+    "vitb_gemm_dgrad_drop": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _dp, _p]),
+    "vitb_gelu_bwd_colsum_drop": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _dp, _p]),
+    "vitb_layernorm_bwd_fused": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _dp, _p, _sz, _i, _i, _i, _p]),
     "vitb_gemm_bwd_fused_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "vitb_gemm_bwd_fused": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
     "vitb_defer_begin": (_i, [_p, _sz]),

@@ -448,6 +448,71 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float& buf, const Ada
 }
 
 // ---------------------------------------------------------------------------------------------
+// nn.Dropout keep masks (layers.py:35, 38, 102), shared by the stand-alone pass (elementwise.cu) and the fused sites (GEMM
+// epilogues, GELU backward, LayerNorm backward).  The mask is never stored: it is a pure function of (seed, site, step, element
+// index) — Philox4x32-10 with key = seed and counter = (group lo, group hi, site, step), one call per group of eight consecutive
+// elements of the flattened (rows, cols) tensor, sixteen bits per element (element j of the group uses bits 16 (j & 1) .. of word
+// j >> 1; kept iff that value >= round(p * 65536)).  `step` comes from device memory when step_dev != NULL, so a captured CUDA
+// graph draws a fresh mask on every replay.
+// ---------------------------------------------------------------------------------------------
+struct DropParams {
+  uint32_t thr;   // 0 = no dropout at this site
+  float scale;    // 1 / (1 - p)
+  uint2 key;
+  uint32_t site, step;
+  const uint32_t* step_dev;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint32_t drop_step(const DropParams& d) { return d.step_dev != nullptr ? *d.step_dev : d.step; }
+// the four mask words of element group g (elements 8 g .. 8 g + 7)
+__device__ __forceinline__ uint4 drop_words(const DropParams& d, uint32_t step, uint64_t g) {
+  return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), d.site, step), d.key);
+}
+// element j (0..7) of the group whose words are w
+__device__ __forceinline__ float drop_one(float v, uint32_t word, int j, uint32_t thr, float scale) {
+  return ((word >> (16 * (j & 1))) & 0xffffu) >= thr ? v * scale : 0.f;
+}
+__device__ __forceinline__ void drop_apply8(float* f, const uint4& r, uint32_t thr, float scale) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = drop_one(f[j], w[j >> 1], j, thr, scale);
+}
+// four consecutive elements starting at flat element index e (a multiple of 4): half a mask group
+__device__ __forceinline__ void drop_apply4(float4& v, const DropParams& d, uint32_t step, uint64_t e) {
+  const uint4 r = drop_words(d, step, e >> 3);
+  const bool hi = ((e >> 2) & 1) != 0;
+  const uint32_t w0 = hi ? r.z : r.x, w1 = hi ? r.w : r.y;
+  v.x = drop_one(v.x, w0, 0, d.thr, d.scale);
+  v.y = drop_one(v.y, w0, 1, d.thr, d.scale);
+  v.z = drop_one(v.z, w1, 0, d.thr, d.scale);
+  v.w = drop_one(v.w, w1, 1, d.thr, d.scale);
+}
+// host: the kernel-side description of a vitb_dropout_t (NULL or p == 0: off).  Returns false on a bad p.
+static inline bool make_drop_params(const vitb_dropout_t* d, DropParams* out) {
+  *out = DropParams{};
+  if (d == nullptr || d->p == 0.f) return true;
+  if (!(d->p > 0.f && d->p < 1.f)) return false;
+  out->thr = vitb_dropout_threshold(d->p);
+  out->scale = 1.0f / (1.0f - d->p);
+  out->key = make_uint2((uint32_t)d->seed, (uint32_t)(d->seed >> 32));
+  out->site = d->site;
+  out->step = d->step;
+  out->step_dev = d->step_dev;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT (fp32 check mode / small shapes) and tcgen05 paths
 // ---------------------------------------------------------------------------------------------
 enum EpiMode { EPI_FWD = 0, EPI_DGRAD = 1, EPI_RAW_F32 = 2 };

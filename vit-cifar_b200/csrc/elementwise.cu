@@ -210,15 +210,25 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const T* __restrict__ x,
 constexpr int kLnBwdWarps = 8;
 
 
-template <typename T, int VEC, bool HAS_RES, bool COLSUM>
+// value as it reads back from a tensor of type T
+__device__ __forceinline__ float round_as(float v, const float*) { return v; }
+__device__ __forceinline__ float round_as(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// OUT2: a second output dx2 = dropout(dx) [* gelu'(z2)] with the column sums over dx2 instead of dx — the first kernel of the
+// next backward stage folded into this one (vitb_layernorm_bwd_fused); dx2 is computed from dx AS STORED, so it equals what the
+// stand-alone kernels (vitb_dropout / vitb_gelu_bwd_colsum_drop) produce from this kernel's dx bit for bit.
+template <typename T, int VEC, bool HAS_RES, bool COLSUM, bool OUT2 = false>
 __global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must be one wave: keep <= 128 registers
     ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t xs,
                   const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx,
-                  int64_t dxs, float* __restrict__ ws, int rows) {
+                  int64_t dxs, float* __restrict__ ws, int rows, const T* __restrict__ z2 = nullptr, T* __restrict__ dx2 = nullptr,
+                  DropParams dp = DropParams{}) {
   pdl_trigger();
   pdl_wait();
   constexpr int H = VEC * 128;
+  const bool dropping = OUT2 && dp.thr != 0;
+  const uint32_t dstep = dropping ? drop_step(dp) : 0u;
   __shared__ float red[kLnBwdWarps][H];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -234,6 +244,7 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must b
   int row = blockIdx.x * kLnBwdWarps + warp;
   Raw4<T> rx[VEC], rdy[VEC], rdr[VEC];
   float mu = 0.f, rs = 0.f;
+  const bool has_z = OUT2 && z2 != nullptr;
   auto fetch = [&](int r) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -275,6 +286,13 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must b
       c1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       c2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
     }
+    // z2 of the current row: issued before the reductions, whose shuffles cover part of the latency.  (Prefetching it one row
+    // ahead with the other operands was measured slower: 6.21 vs 6.19 ms per step, 14 B of spills at the 128-register cap.)
+    Raw4<T> rz[VEC];
+    if (has_z) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) rz[i] = ldraw(z2 + (int64_t)cur * H + (i * 32 + lane) * 4);
+    }
     c1 = warp_sum(c1) * (1.0f / H);
     c2 = warp_sum(c2) * (1.0f / H);
     T* dxr = dx + (int64_t)cur * dxs;
@@ -288,7 +306,19 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32, 2)  // grid = 2 x SMs must b
       o.w = crs * (d[i].w - c1 - xh[i].w * c2);
       if (HAS_RES) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
       st4(dxr + c, o);
-      if (COLSUM) { dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w; }
+      if (OUT2) {
+        const T* tag = nullptr;
+        float4 q = make_float4(round_as(o.x, tag), round_as(o.y, tag), round_as(o.z, tag), round_as(o.w, tag));
+        if (dropping) drop_apply4(q, dp, dstep, (uint64_t)cur * H + c);
+        if (has_z) {
+          const float4 zz = cvt4(rz[i]);
+          q.x *= gelu_grad_f(zz.x); q.y *= gelu_grad_f(zz.y); q.z *= gelu_grad_f(zz.z); q.w *= gelu_grad_f(zz.w);
+        }
+        st4(dx2 + (int64_t)cur * H + c, q);
+        if (COLSUM) { dc[i].x += q.x; dc[i].y += q.y; dc[i].z += q.z; dc[i].w += q.w; }
+      } else if (COLSUM) {
+        dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w;
+      }
     }
   }
   // block reduction of the partial vectors, one at a time through the same smem
@@ -323,9 +353,11 @@ static int ln_bwd_blocks(int rows) {
 template <typename T, bool GELU_BWD>
 __global__ void __launch_bounds__(256)
     rows_colsum_kernel(const T* __restrict__ a, const T* __restrict__ z, T* __restrict__ out,
-                       float* __restrict__ ws, int rows, int cols) {
+                       float* __restrict__ ws, int rows, int cols, DropParams dp) {
   pdl_trigger();
   pdl_wait();
+  const bool dropping = GELU_BWD && dp.thr != 0;  // dropout backward on the incoming gradient (GELU -> Dropout, layers.py:37-38)
+  const uint32_t dstep = dropping ? drop_step(dp) : 0u;
   __shared__ float4 red[256];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int c = (blockIdx.y * TX + tx) * 4;
@@ -336,6 +368,10 @@ __global__ void __launch_bounds__(256)
     const size_t off0 = (size_t)r * cols + c, off1 = (size_t)(r + step) * cols + c;
     float4 v0 = ld4(a + off0), v1 = ld4(a + off1);
     if (GELU_BWD) {
+      if (dropping) {
+        drop_apply4(v0, dp, dstep, off0);
+        drop_apply4(v1, dp, dstep, off1);
+      }
       const float4 z0 = ld4(z + off0), z1 = ld4(z + off1);
       v0.x *= gelu_grad_f(z0.x); v0.y *= gelu_grad_f(z0.y); v0.z *= gelu_grad_f(z0.z); v0.w *= gelu_grad_f(z0.w);
       v1.x *= gelu_grad_f(z1.x); v1.y *= gelu_grad_f(z1.y); v1.z *= gelu_grad_f(z1.z); v1.w *= gelu_grad_f(z1.w);
@@ -348,6 +384,7 @@ __global__ void __launch_bounds__(256)
     const size_t off = (size_t)r * cols + c;
     float4 v = ld4(a + off);
     if (GELU_BWD) {
+      if (dropping) drop_apply4(v, dp, dstep, off);
       const float4 zz = ld4(z + off);
       v.x *= gelu_grad_f(zz.x); v.y *= gelu_grad_f(zz.y); v.z *= gelu_grad_f(zz.z); v.w *= gelu_grad_f(zz.w);
       st4(out + off, v);
@@ -373,9 +410,12 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __global__ void __launch_bounds__(512)
-    gelu_bwd_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z, bf16* __restrict__ out, float* __restrict__ ws, int rows, int cols) {
+    gelu_bwd_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ z, bf16* __restrict__ out, float* __restrict__ ws, int rows, int cols,
+                           DropParams dp) {
   pdl_trigger();
   pdl_wait();
+  const bool dropping = dp.thr != 0;
+  const uint32_t dstep = dropping ? drop_step(dp) : 0u;
   extern __shared__ float red8[];  // [TY][cols]
   const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
   const int c = tx * 8;
@@ -383,10 +423,11 @@ __global__ void __launch_bounds__(512)
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const int step = gridDim.x * TY;
-  auto one = [&](const uint4& av, const uint4& zv) -> uint4 {
+  auto one = [&](const uint4& av, const uint4& zv, size_t off) -> uint4 {
     float x[8], g[8];
     unpack8(av, x);
     unpack8(zv, g);
+    if (dropping) drop_apply8(x, drop_words(dp, dstep, (uint64_t)off >> 3), dp.thr, dp.scale);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       x[i] *= gelu_grad_f(g[i]);
@@ -405,13 +446,13 @@ __global__ void __launch_bounds__(512)
       zv[k] = __ldg(reinterpret_cast<const uint4*>(z + off));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ov[k] = one(av[k], zv[k]);
+    for (int k = 0; k < 4; ++k) ov[k] = one(av[k], zv[k], (size_t)(r + k * step) * cols + c);
 #pragma unroll
     for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + (size_t)(r + k * step) * cols + c) = ov[k];
   }
   for (; r < rows; r += step) {
     const size_t off = (size_t)r * cols + c;
-    *reinterpret_cast<uint4*>(out + off) = one(__ldg(reinterpret_cast<const uint4*>(a + off)), __ldg(reinterpret_cast<const uint4*>(z + off)));
+    *reinterpret_cast<uint4*>(out + off) = one(__ldg(reinterpret_cast<const uint4*>(a + off)), __ldg(reinterpret_cast<const uint4*>(z + off)), off);
   }
   if (ws == nullptr) return;
 #pragma unroll
@@ -461,14 +502,14 @@ static bool rows_geom(int rows, int cols, RowsGeom* g) {
 
 template <typename T>
 static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out, float* colsum,
-                              void* ws, size_t ws_bytes, int rows, int cols, cudaStream_t st) {
+                              void* ws, size_t ws_bytes, int rows, int cols, cudaStream_t st, const DropParams& dp = DropParams{}) {
   RowsGeom g;
   VITB_REQUIRE(rows_geom(rows, cols, &g), "colsum: cols=%d must be a multiple of 128", cols);
   int ty8 = 0, gx8 = 0;
   if (gelu && sizeof(T) == 2 && gelu8_geom(rows, cols, &ty8, &gx8) && ((uintptr_t)a | (uintptr_t)z | (uintptr_t)out) % 16 == 0 &&
       (colsum == nullptr || (ws != nullptr && ws_bytes >= (size_t)gx8 * cols * sizeof(float)))) {
     float* w8 = colsum != nullptr ? (float*)ws : nullptr;
-    VITB_LAUNCH((gelu_bwd_bf16x8_kernel), gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st, (const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols);
+    VITB_LAUNCH((gelu_bwd_bf16x8_kernel), gx8, dim3(cols / 8, ty8), (size_t)ty8 * cols * sizeof(float), st, (const bf16*)a, (const bf16*)z, (bf16*)out, w8, rows, cols, dp);
     VITB_LAUNCH_OK();
     if (colsum != nullptr) VITB_CUDA_OK(::vitb::launch_finalize(w8, gx8, cols, colsum, nullptr, nullptr, 1, st));
     return 0;
@@ -481,9 +522,9 @@ static int launch_rows_colsum(bool gelu, const void* a, const void* z, void* out
   }
   dim3 grid(g.gx, g.gy), block(g.tx, g.ty);
   if (gelu)
-    VITB_LAUNCH((rows_colsum_kernel<T, true>), grid, block, 0, st, (const T*)a, (const T*)z, (T*)out, wsf, rows, cols);
+    VITB_LAUNCH((rows_colsum_kernel<T, true>), grid, block, 0, st, (const T*)a, (const T*)z, (T*)out, wsf, rows, cols, dp);
   else
-    VITB_LAUNCH((rows_colsum_kernel<T, false>), grid, block, 0, st, (const T*)a, nullptr, nullptr, wsf, rows, cols);
+    VITB_LAUNCH((rows_colsum_kernel<T, false>), grid, block, 0, st, (const T*)a, nullptr, nullptr, wsf, rows, cols, DropParams{});
   VITB_LAUNCH_OK();
   if (colsum != nullptr) VITB_CUDA_OK(::vitb::launch_finalize(wsf, g.gx, cols, colsum, nullptr, nullptr, 1, st));
   return 0;
@@ -616,24 +657,9 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 // dropout (nn.Dropout at layers.py:35, 38, 102): out = x * keep / (1 - p) (+ residual)
 //
-// The keep mask is never stored: it is a pure function of (seed, site, step, element index) — Philox4x32-10 with key = seed
-// and counter = (group lo, group hi, site, step), one call per group of eight consecutive elements, sixteen bits per element
-// (element j of the group uses bits 16 (j & 1) .. of word j >> 1; kept iff that value >= round(p * 65536)).  Backward calls
-// the same function on the gradient with the same (seed, site, step) and regenerates the mask.  `step` comes from device
-// memory when step_dev != NULL, so a captured CUDA graph draws a fresh mask on every replay.
+// The keep mask (common.cuh: DropParams, philox4x32_10) is a pure function of (seed, site, step, element index); the backward
+// pass calls the same function on the gradient with the same (seed, site, step) and regenerates it.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
     dropout_kernel(const T* x, const T* residual, T* out, int64_t groups,  // no __restrict__: in-place (out == x) is allowed
@@ -743,6 +769,31 @@ size_t vitb_layernorm_bwd_ws_bytes(int rows, int H) {
   return (size_t)3 * ln_bwd_blocks(rows) * H * sizeof(float);
 }
 
+int vitb_layernorm_bwd_fused(const void* dy, const void* x, int64_t xs, const float* gamma, const float* mean, const float* rstd,
+                             const void* dres, void* dx, int64_t dxs, float* dgamma, float* dbeta, const void* z, void* dx2,
+                             float* dx2_colsum, const vitb_dropout_t* drop, void* ws, size_t ws_bytes, int rows, int H, int dt,
+                             void* stream) {
+  VITB_REQUIRE(dy && x && gamma && mean && rstd && dres && dx && dgamma && dbeta && dx2 && dx2_colsum && ws, "layernorm_bwd_fused: null pointer");
+  VITB_REQUIRE(rows > 0 && H % 128 == 0 && xs % 4 == 0 && dxs % 4 == 0, "layernorm_bwd_fused: bad shape");
+  VITB_REQUIRE(ws_bytes >= vitb_layernorm_bwd_ws_bytes(rows, H), "layernorm_bwd_fused: workspace too small");
+  VITB_REQUIRE(dx2 != dx && dx2 != dy && dx2 != dres, "layernorm_bwd_fused: dx2 must not alias another operand");
+  DropParams dp;
+  VITB_REQUIRE(make_drop_params(drop, &dp), "layernorm_bwd_fused: dropout p = %f outside [0, 1)", (double)drop->p);
+  if (void* d = defer_alloc(vitb_layernorm_bwd_ws_bytes(rows, H))) ws = d;  // deferred second pass: the partials must outlive this call
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ln_bwd_blocks(rows);
+  if (dt == VITB_BF16) {
+    VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_bwd_kernel<bf16, VEC, true, true, true>), blocks, kLnBwdWarps * 32, 0, st, (const bf16*)dy, (const bf16*)x, xs,
+                                      gamma, mean, rstd, (const bf16*)dres, (bf16*)dx, dxs, (float*)ws, rows, (const bf16*)z, (bf16*)dx2, dp)));
+  } else {
+    VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_bwd_kernel<float, VEC, true, true, true>), blocks, kLnBwdWarps * 32, 0, st, (const float*)dy, (const float*)x,
+                                      xs, gamma, mean, rstd, (const float*)dres, (float*)dx, dxs, (float*)ws, rows, (const float*)z, (float*)dx2, dp)));
+  }
+  VITB_LAUNCH_OK();
+  VITB_CUDA_OK(::vitb::launch_finalize((const float*)ws, blocks, H, dgamma, dbeta, dx2_colsum, 3, st));
+  return 0;
+}
+
 int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* gamma, const float* mean,
                        const float* rstd, const void* dres, void* dx, int64_t dxs, float* dgamma,
                        float* dbeta, float* dx_colsum, void* ws, size_t ws_bytes, int rows, int H, int dt,
@@ -756,7 +807,7 @@ int vitb_layernorm_bwd(const void* dy, const void* x, int64_t xs, const float* g
   const bool res = dres != nullptr, cs = dx_colsum != nullptr;
 #define VITB_LN_BWD(T, RES, CS)                                                                                              \
   VITB_DISPATCH_VEC(H, (VITB_LAUNCH((ln_bwd_kernel<T, VEC, RES, CS>), blocks, kLnBwdWarps * 32, 0, st, (const T*)dy, (const T*)x, xs, gamma, mean, rstd, \
-                                                                                         (const T*)dres, (T*)dx, dxs, (float*)ws, rows)))
+                                                                                         (const T*)dres, (T*)dx, dxs, (float*)ws, rows, nullptr, nullptr, DropParams{})))
   if (dt == VITB_BF16) {
     if (res && cs) { VITB_LN_BWD(bf16, true, true); } else if (res) { VITB_LN_BWD(bf16, true, false); }
     else if (cs) { VITB_LN_BWD(bf16, false, true); } else { VITB_LN_BWD(bf16, false, false); }
@@ -780,11 +831,19 @@ size_t vitb_colsum_ws_bytes(int rows, int cols) {
 
 int vitb_gelu_bwd_colsum(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes,
                          int rows, int cols, int dt, void* stream) {
+  return vitb_gelu_bwd_colsum_drop(dy, z, dz, colsum, ws, ws_bytes, rows, cols, dt, nullptr, stream);
+}
+
+int vitb_gelu_bwd_colsum_drop(const void* dy, const void* z, void* dz, float* colsum, void* ws, size_t ws_bytes, int rows, int cols,
+                              int dt, const vitb_dropout_t* drop, void* stream) {
   VITB_REQUIRE(dy && z && dz && rows > 0, "gelu_bwd: null pointer / empty");
+  DropParams dp;
+  VITB_REQUIRE(make_drop_params(drop, &dp), "gelu_bwd: dropout p = %f outside [0, 1)", (double)drop->p);
+  VITB_REQUIRE(dp.thr == 0 || cols % 8 == 0, "gelu_bwd: dropout needs cols %% 8 == 0");
   if (colsum != nullptr)
     if (void* d = defer_alloc(vitb_colsum_ws_bytes(rows, cols))) { ws = d; ws_bytes = vitb_colsum_ws_bytes(rows, cols); }
-  if (dt == VITB_BF16) return launch_rows_colsum<bf16>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
-  return launch_rows_colsum<float>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream);
+  if (dt == VITB_BF16) return launch_rows_colsum<bf16>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream, dp);
+  return launch_rows_colsum<float>(true, dy, z, dz, colsum, ws, ws_bytes, rows, cols, (cudaStream_t)stream, dp);
 }
 
 int vitb_colsum(const void* x, float* colsum, void* ws, size_t ws_bytes, int rows, int cols, int dt, void* stream) {

@@ -51,6 +51,7 @@ struct TcArgs {
   int pf_tiles;      // fwd/dgrad: prefetch the A tile this many tiles (per stream) ahead into L2; 0 = off
   int pf_kblocks;    // wgrad: prefetch operands this many k-blocks ahead into L2; 0 = off
   int dbg_flags;     // tools only: 1 = epilogue skips its work (accumulator handed straight back), 2 = producer loads nothing
+  DropParams drop;   // thr != 0: nn.Dropout on the output, after GELU / gelu' and before the residual (mask over the flattened [M, N] output)
   int out3;          // EPI_FWD: tma_out is a 3-D (columns, tokens, images) map of a (B, T, H) tensor — the patch embedding writes GEMM
                      // row m to token e.rm_offset + m % e.rm_group of image m / e.rm_group and adds e.pos[token] (vit.py:68-70)
   EpiParams e;
@@ -278,7 +279,7 @@ __device__ __forceinline__ void slab_load_chunk8(uint32_t slab, int r, int j, fl
 // buys every stream a fourth ring stage (ring depth is what bounds these kernels).  The leader CTA issues the MMAs
 // for both; full / accumulator-empty barriers live in the leader (the peer's TMA loads and epilogue warps signal them remotely),
 // empty / accumulator-full barriers exist in both CTAs and are signalled by multicast tcgen05.commit.
-template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG>
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG, bool DROP>
 __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
@@ -598,6 +599,16 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
     uint32_t in_phase = 0;
     const EpiParams& e = p.e;
     bool stores_pending = false;
+    // (DROP is a template parameter, not only a run-time flag: the mask arithmetic inside the epilogue costs the p = 0 kernels
+    // a few spilled registers otherwise)
+    const bool dropping = DROP && NSLAB > 0 && p.drop.thr != 0;
+    const uint32_t drop_st = dropping ? drop_step(p.drop) : 0u;
+    // this thread's 64 values of output row `grow`, columns n0 .. n0 + 63: eight mask groups of the flattened [M, N] output
+    auto drop64 = [&](float (&v)[64], int grow, int n0) {
+      const uint64_t g0 = ((uint64_t)grow * (uint64_t)p.N + (uint64_t)n0) >> 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) drop_apply8(&v[8 * j], drop_words(p.drop, drop_st, g0 + j), p.drop.thr, p.drop.scale);
+    };
     int m0, nb0, nblk, split;
     for (int it = 0; get_tile(it, m0, nb0, nblk, split); ++it) {
       const int st_ = it % NS, jt = it / NS;           // stream, and the tile's index inside the stream
@@ -719,6 +730,7 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = gelu_bf16_f(v[j]);
           }
+          if constexpr (DROP) { if (dropping) drop64(v, grow, n0); }
           if (p.has_in) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -734,6 +746,7 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = gelu_bf16_f(v[j]);
         }
+        if constexpr (DROP) { if (dropping) drop64(v, grow, n0); }
         if (p.has_in) {
           mbar_wait(in_bar(ew), in_phase);
           in_phase ^= 1u;
@@ -758,6 +771,7 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
             for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_grad_bf16_f(z[i]);
           }
         }
+        if constexpr (DROP) { if (dropping) drop64(v, grow, n0); }
       }
       slab_store_row64(slab_out, lane, v);
       fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -858,11 +872,11 @@ struct TcMaps {
   CUtensorMap a, b, out, pre, in;
 };
 
-template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG = 1>
+template <int BN, bool A_MN, bool B_MN, int NS, int STAGES, int KPS, int NSLAB, bool W_RES, int CG = 1, bool DROP = false>
 static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) {
   using S = TcSmem<BN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
   static_assert(S::kDynBytes <= 232448, "shared memory plan exceeds 227 KB");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NS, STAGES, KPS, NSLAB, W_RES, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NS, STAGES, KPS, NSLAB, W_RES, CG, DROP>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VITB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kDynBytes));
@@ -948,6 +962,12 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
     else return launch_tc_impl<BN, A_MN, B_MN, 1, 4, 1, 1, false>(m, args, st);
   } else {
   const bool res = !A_MN && use_resident_weights(args);
+  if constexpr (!A_MN) {
+    if (args.drop.thr != 0) {  // dropout in the epilogue: the two dual-stream plans carry it
+      if (res) return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, true, 1, true>(m, args, st);
+      return launch_tc_impl<BN, A_MN, B_MN, 2, 3, 1, 1, false, 1, true>(m, args, st);
+    }
+  }
   if (g_tc_streams == 1) {
     if (args.e.mode == EPI_RAW_F32) return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 0, false>(m, args, st);
     if (res) return launch_tc_impl<BN, A_MN, B_MN, 1, 3, 2, 1, true>(m, args, st);
@@ -1167,10 +1187,24 @@ int vitb_debug_gemm_timeline(long long* dbg, int mode) {
 
 int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, const void* residual, void* c, void* preact,
                            int M, int N, int K, int flags, int dt, void* stream) {
+  return vitb_gemm_bias_act_fwd_drop(a, w, bias, residual, c, preact, M, N, K, flags, dt, nullptr, stream);
+}
+
+int vitb_gemm_bias_act_fwd_drop(const void* a, const void* w, const float* bias, const void* residual, void* c, void* preact,
+                                int M, int N, int K, int flags, int dt, const vitb_dropout_t* drop, void* stream) {
   VITB_REQUIRE(a && w && c, "gemm_fwd: null pointer");
   VITB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_fwd: bad shape M=%d N=%d K=%d", M, N, K);
   if (check_dt(dt)) return -1;
+  DropParams dp;
+  VITB_REQUIRE(make_drop_params(drop, &dp), "gemm_fwd: dropout p = %f outside [0, 1)", (double)drop->p);
+  VITB_REQUIRE(dp.thr == 0 || (!(flags & VITB_GEMM_OUT_F32) && N % 8 == 0), "gemm_fwd: dropout needs an activation-type output with N %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dp.thr != 0 && !(dt == VITB_BF16 && tc_shape_ok(M, N, K))) {
+    // no tensor-core epilogue for this shape / type: the plain kernel without the residual, then the stand-alone pass adds mask and residual
+    int rc = vitb_gemm_bias_act_fwd(a, w, bias, nullptr, c, preact, M, N, K, flags, dt, stream);
+    if (rc) return rc;
+    return vitb_dropout(c, residual, c, (int64_t)M * N, drop->p, drop->seed, drop->site, drop->step, drop->step_dev, dt, stream);
+  }
   EpiParams e = {};
   e.mode = EPI_FWD; e.gelu = (flags & VITB_GEMM_GELU) ? 1 : 0; e.out_f32 = (flags & VITB_GEMM_OUT_F32) ? 1 : 0;
   e.bias = bias; e.residual = residual; e.out = c; e.preact = preact; e.ldc = N;
@@ -1186,7 +1220,8 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
     t.M = M; t.N = N; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = N / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(K, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = N;
     t.has_in = residual != nullptr; t.has_pre = preact != nullptr;
-    if (use_bn192(M, N, K)) {
+    t.drop = dp;
+    if (dp.thr == 0 && use_bn192(M, N, K)) {
       if (make_map(&m.b, w, K, N, K, 192)) return -1;
       t.num_n_blocks = N / 192;
       return launch_tc<192, false, false>(m, t, st);
@@ -1201,11 +1236,24 @@ int vitb_gemm_bias_act_fwd(const void* a, const void* w, const float* bias, cons
 }
 
 int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int M, int N, int K, int flags, int dt, void* stream) {
+  return vitb_gemm_dgrad_drop(dy, w, z, dx, M, N, K, flags, dt, nullptr, stream);
+}
+
+int vitb_gemm_dgrad_drop(const void* dy, const void* w, const void* z, void* dx, int M, int N, int K, int flags, int dt,
+                         const vitb_dropout_t* drop, void* stream) {
   VITB_REQUIRE(dy && w && dx, "gemm_dgrad: null pointer");
   VITB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_dgrad: bad shape M=%d N=%d K=%d", M, N, K);
   if (check_dt(dt)) return -1;
+  DropParams dp;
+  VITB_REQUIRE(make_drop_params(drop, &dp), "gemm_dgrad: dropout p = %f outside [0, 1)", (double)drop->p);
+  VITB_REQUIRE(dp.thr == 0 || K % 8 == 0, "gemm_dgrad: dropout needs K %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int dy_f32 = (flags & VITB_GEMM_DY_F32) ? 1 : 0;
+  if (dp.thr != 0 && !(dt == VITB_BF16 && !dy_f32 && tc_shape_ok(M, K, N))) {
+    int rc = vitb_gemm_dgrad(dy, w, z, dx, M, N, K, flags, dt, stream);
+    if (rc) return rc;
+    return vitb_dropout(dx, nullptr, dx, (int64_t)M * K, drop->p, drop->seed, drop->site, drop->step, drop->step_dev, dt, stream);
+  }
   EpiParams e = {};
   e.mode = EPI_DGRAD; e.out = dx; e.aux = z; e.ldc = K;
   // GEMM view: C[M, K] = dY[M, N] (K-major, reduction N) x W[N, K] (MN-major: reduction over rows)
@@ -1220,7 +1268,8 @@ int vitb_gemm_dgrad(const void* dy, const void* w, const void* z, void* dx, int 
     t.M = M; t.N = K; t.num_m_blocks = ceil_div(M, BM); t.num_n_blocks = K / kBN; t.splits = 1;
     t.kblocks_total = ceil_div(N, BK); t.kblocks_per_split = t.kblocks_total; t.e = e; t.valid_n = K;
     t.has_in = z != nullptr;
-    if (use_bn192(M, K, N)) {  // (the MN-major weight boxes are 64 columns wide: the same map serves both tile widths)
+    t.drop = dp;
+    if (dp.thr == 0 && use_bn192(M, K, N)) {  // (the MN-major weight boxes are 64 columns wide: the same map serves both tile widths)
       t.num_n_blocks = K / 192;
       return launch_tc<192, false, true>(m, t, st);
     }

@@ -291,13 +291,23 @@ class TrainEngine:
                          self._alloc("headb"), dx_prezeroed=True)
         self._allreduce(self.buckets[-1])
         done = {}
+        # (bf16 only: the fp32 check mode keeps the module path's kernel chain, with which it is compared bit for bit)
+        fuse_below = (Fn.ln_gelu_fused() and dm.use_mlp and self.act == torch.bfloat16 and (not self.drops or Fn._drop_fused()))
+        dz2_in = None
         for i in reversed(range(m.num_layers)):
             # backward scratch ping-pongs between two sets; with weight gradients on the side stream a set may only be rewritten
             # once the side-stream kernels of the layer that used it last (i + 2) have read it
             if side is not None and (i + 2) in done:
                 torch.cuda.current_stream().wait_event(done[i + 2])
+            # block i's last kernel (LayerNorm-1 backward) also writes block i - 1's dz2 and b2 gradient; that buffer rotates over
+            # three, not two: block i + 1's side-stream wgrad may still be reading its dz2 (the wait above covers i + 2 only)
+            below = None
+            if fuse_below and i > 0:
+                dz2_b = self._alloc(f"bwd_dz2_{(i - 1) % 3}")("dz2", (dm.rows, dm.H), self.act)
+                below = (saved[i - 1][4][6], dz2_b, self.lg[i - 1].b2, self.drops[i - 1] if self.drops else None)
             dx = Fn.encoder_bwd(dx, saved[i], self.lc[i], self.lp[i], self.lg[i], dm, self._bwd_alloc(i),
-                                drop=self.drops[i] if self.drops else None, side=side)
+                                drop=self.drops[i] if self.drops else None, side=side, dz2_in=dz2_in, below=below)
+            dz2_in = below[1] if below is not None else None
             if side is not None:
                 if self._defer and self._flush_per_layer:
                     # this layer's second passes on the side stream (ordered after everything issued so far on both streams),

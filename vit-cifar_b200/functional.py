@@ -9,6 +9,7 @@ the engine.  Activations are (rows, H) row-major with rows = B*T.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -86,7 +87,6 @@ def _bwd_fused_ok(rows: int, N: int, K: int, t: torch.Tensor) -> bool:
     (VITB_BWD_FUSED=1): measured on B200 it only equals dgrad + wgrad (66.5 vs 67.4 us at 66560 x 384 x 384) — with the
     weight slice resident, 131 KB of shared memory are left to stream 128 KB of operands per row block, too little to cover the
     load latency — and it is slower at 8,320 rows, where its 29 MB of per-CTA dW partials dominate."""
-    import os
     if os.environ.get("VITB_BWD_FUSED", "0") == "0":
         return False
     return ops.bwd_fused_ws_bytes(rows, N, K, ops.dt_of(t)) > 0
@@ -112,6 +112,25 @@ class Drop:
     def __call__(self, x: torch.Tensor, residual: Optional[torch.Tensor], out: torch.Tensor, site: int) -> None:
         ops.dropout(x, residual, out, self.p, self.seed, site, self.step, self.step_dev)
 
+    def desc(self, site: int):
+        """The site's descriptor for the kernels that apply the mask themselves (GEMM epilogues, GELU / LayerNorm backward)."""
+        return ops.drop_desc(self.p, self.seed, site, self.step, self.step_dev)
+
+
+def _drop_fused() -> bool:
+    """Dropout masks inside the producing / consuming kernels (default) or as separate elementwise passes (VITB_DROP_FUSED=0:
+    the round-1 path, kept as the A/B and as the reference the fused path is tested against bit for bit)."""
+    return os.environ.get("VITB_DROP_FUSED", "1") != "0"
+
+
+def ln_gelu_fused() -> bool:
+    """LayerNorm-1 backward of block i + 1 also writes dz2 of block i (the GELU backward of its second MLP Linear and that Linear's
+    bias gradient): one launch and one read of the block-output gradient less per block.  Opt-in (VITB_LN_GELU_FUSED=1): measured
+    on B200 the fused kernel is faster than its two parts in isolation (76 vs 46 + 41 us at 66,560 rows) but the step is not
+    (6.19 vs 6.17 ms at B = 1024, 1.391 vs 1.375 ms at B = 128, 2.211 vs 2.225 ms at T = 17): the GELU arithmetic moves from a
+    78-register kernel that shares SMs with the side-stream weight-gradient GEMMs into a 128-register one that does not."""
+    return os.environ.get("VITB_LN_GELU_FUSED", "0") != "0"
+
 
 # ---------------------------------------------------------------------------------------------
 # attention block: layers.py:90-103  (x -> out_project(attn(QKV(x))))
@@ -126,20 +145,23 @@ def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: All
     lse = alloc("lse", (dm.B, dm.heads, dm.T), torch.float32)
     ops.attn_fwd(qkv, o, lse, attn_map, dm.B, dm.T, dm.heads, dm.d, dm.scale)
     y = alloc("x1", (rows, H), act)
-    if drop is None:
-        ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H)
+    if drop is None or _drop_fused():                                               # layers.py:102, then "+ x" of layers.py:45
+        ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H, drop=drop.desc(0) if drop is not None else None)
     else:
         ops.gemm_fwd(o, c.wo, p.bo, None, y, None, rows, H, H)
-        drop(y, residual, y, 0)                                                    # layers.py:102, then "+ x" of layers.py:45
+        drop(y, residual, y, 0)
     return y, (x, qkv, o, lse)
 
 
 def mhsa_bwd(dy: torch.Tensor, saved, c: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc, bo_done: bool = False,
-             drop: Optional[Drop] = None, side: Optional[SideStream] = None):
-    """dy (rows,H) = grad of the block's attention branch output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x."""
+             drop: Optional[Drop] = None, side: Optional[SideStream] = None, dy_masked: Optional[torch.Tensor] = None):
+    """dy (rows,H) = grad of the block's attention branch output.  Fills g.wqkv,g.bqkv,g.wo,(g.bo); returns grad of x.
+    `dy_masked`: dy already taken through the out_project Dropout's mask (by the LayerNorm backward that produced dy)."""
     x, qkv, o, lse = saved
     rows, H, act = dm.rows, dm.H, dy.dtype
-    if drop is not None:  # gradient of the out_project output = dy through the same mask (dy itself is still needed by the caller)
+    if dy_masked is not None:
+        dy = dy_masked
+    elif drop is not None:  # gradient of the out_project output = dy through the same mask (dy itself is still needed by the caller)
         dya = alloc("dao", (rows, H), act)
         drop(dy, None, dya, 0)
         dy = dya
@@ -176,9 +198,13 @@ def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: 
     ops.layernorm_fwd(x1, H, p.ln2_w, p.ln2_b, x1n, mean2, rstd2, rows, H)
     z1 = alloc("z1", (rows, M), act)
     a1 = alloc("a1", (rows, M), act)
-    ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True)            # mlp[0], mlp[1]
     z2 = alloc("z2", (rows, H), act)
     x2 = alloc("x2", (rows, H), act)
+    if drop is not None and _drop_fused():                                         # mlp[0..2]: the mask in the epilogue, after the GELU
+        ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True, drop=drop.desc(1))
+        ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True, drop=drop.desc(2))   # mlp[3..5], + out
+        return x2, (x, mean1, rstd1, att_saved, (x1, x1n, mean2, rstd2, z1, a1, z2))
+    ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True)            # mlp[0], mlp[1]
     if drop is None:
         ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True)            # mlp[3], mlp[4], + out
     else:
@@ -189,19 +215,31 @@ def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: 
 
 
 def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: LayerViews, dm: Dims, alloc: Alloc,
-                drop: Optional[Drop] = None, side: Optional[SideStream] = None):
+                drop: Optional[Drop] = None, side: Optional[SideStream] = None, dz2_in: Optional[torch.Tensor] = None,
+                below: Optional[tuple] = None):
     """dout = grad of the block output; fills every field of g; returns grad of the block input.  `drop`: the same Drop the
-    forward ran with (masks are regenerated, not stored)."""
+    forward ran with (masks are regenerated, not stored).
+
+    Cross-block fusion (both optional, bf16 or fp32): `dz2_in` = this block's dz2 (gradient entering its second MLP Linear) and
+    g.b2, already produced by the block above; `below` = (z2, dz2, g_b2, drop) of the block BELOW: this block's last kernel, the
+    LayerNorm-1 backward that forms the block-input gradient, then also writes that block's dz2 = dropout(dx) * gelu'(z2) and its
+    column sums g_b2 (ops.layernorm_bwd_fused), which replaces that block's GELU-backward launch."""
     x, mean1, rstd1, att_saved, mlp_saved = saved
     rows, H, M, act = dm.rows, dm.H, dm.M, dout.dtype
+    fused_drop = drop is not None and _drop_fused()
+    dya = None
     if dm.use_mlp:
         x1, x1n, mean2, rstd2, z1, a1, z2 = mlp_saved
-        dz2 = alloc("dz2", (rows, H), act)
-        dg2 = dout
-        if drop is not None:
-            dg2 = alloc("dg2", (rows, H), act)
-            drop(dout, None, dg2, 2)                                     # mlp[5] backward
-        ops.gelu_bwd_colsum(dg2, z2, dz2, g.b2, rows, H)                 # second GELU (layers.py:37) + db2
+        if dz2_in is not None:
+            dz2 = dz2_in
+        else:
+            dz2 = alloc("dz2", (rows, H), act)
+            if drop is None or fused_drop:                               # second GELU (layers.py:37) + db2, mlp[5]'s mask on the way in
+                ops.gelu_bwd_colsum(dout, z2, dz2, g.b2, rows, H, drop=drop.desc(2) if drop is not None else None)
+            else:
+                dg2 = alloc("dg2", (rows, H), act)
+                drop(dout, None, dg2, 2)                                 # mlp[5] backward
+                ops.gelu_bwd_colsum(dg2, z2, dz2, g.b2, rows, H)
         dz1 = alloc("dz1", (rows, M), act)
         b1_done = False
         if drop is None and _bwd_fused_ok(rows, H, M, dz2):
@@ -210,9 +248,10 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
             b1_done = True
         else:
             _wgrad(side, dz2, a1, g.w2, None, rows, H, M)
-            ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M)               # first GELU's backward fused in the epilogue
-        if drop is not None:
-            drop(dz1, None, dz1, 1)                                      # mlp[2] backward (mask and gelu' commute)
+            # first GELU's backward — and mlp[2]'s mask: the two commute — fused in the epilogue
+            ops.gemm_dgrad(dz2, c.w2, z1, dz1, rows, H, M, drop=drop.desc(1) if fused_drop else None)
+            if drop is not None and not fused_drop:
+                drop(dz1, None, dz1, 1)
         dx1n = alloc("dx1n", (rows, H), act)
         if b1_done and _bwd_fused_ok(rows, M, H, dz1):
             ops.gemm_bwd_fused(dz1, x1n, c.w1, None, dx1n, g.w1, None, rows, M, H)   # mlp[0]
@@ -220,16 +259,28 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
             _wgrad(side, dz1, x1n, g.w1, None if b1_done else g.b1, rows, M, H)
             ops.gemm_dgrad(dz1, c.w1, None, dx1n, rows, M, H)
         dx1 = alloc("dx1", (rows, H), act)
-        # grad of x1 = residual branch (dout) + LN2 backward; its column sums are out_project's bias grad
-        # (with dropout the out_project output gradient is the MASKED dx1: its bias gradient then comes from the wgrad instead)
-        bo_done = drop is None
-        ops.layernorm_bwd(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, g.bo if bo_done else None, rows, H)
+        # grad of x1 = residual branch (dout) + LN2 backward; its column sums are out_project's bias grad.  With dropout the
+        # out_project output gradient is the MASKED dx1: the fused kernel writes it as a second output and sums THAT; the
+        # unfused path masks it in mhsa_bwd and takes the bias gradient from the wgrad instead
+        if fused_drop:
+            dya = alloc("dao", (rows, H), act)
+            ops.layernorm_bwd_fused(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, None, dya, g.bo, rows, H,
+                                    drop=drop.desc(0))
+            bo_done = True
+        else:
+            bo_done = drop is None
+            ops.layernorm_bwd(dx1n, x1, H, p.ln2_w, mean2, rstd2, dout, dx1, H, g.ln2_w, g.ln2_b, g.bo if bo_done else None, rows, H)
     else:
         dx1 = dout
         bo_done = False
-    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done, drop=drop, side=side)
+    dxn = mhsa_bwd(dx1, att_saved, c, g, dm, alloc, bo_done=bo_done, drop=drop, side=side, dy_masked=dya)
     dx = alloc("dx", (rows, H), act)
-    ops.layernorm_bwd(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, None, rows, H)
+    if below is not None:
+        z2_b, dz2_b, g_b2_b, drop_b = below
+        ops.layernorm_bwd_fused(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, z2_b, dz2_b, g_b2_b, rows, H,
+                                drop=drop_b.desc(2) if drop_b is not None else None)
+    else:
+        ops.layernorm_bwd(dxn, x, H, p.ln1_w, mean1, rstd1, dx1, dx, H, g.ln1_w, g.ln1_b, None, rows, H)
     return dx
 
 

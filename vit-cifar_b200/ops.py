@@ -125,15 +125,40 @@ def layernorm_bwd(dy, x, x_row_stride: int, gamma, mean, rstd, dres, dx, dx_row_
                                  dt_of(dy), _stream()), "layernorm_bwd")
 
 
-def gemm_fwd(a, w_act, bias, residual, out, preact, M: int, N: int, K: int, gelu: bool = False, out_f32: bool = False) -> None:
+def drop_desc(p: float, seed: int, site: int, step: int = 0, step_dev=None):
+    """A vitb_dropout_t for the fused dropout sites (None when p == 0).  Keep the returned object alive across the call."""
+    if not p:
+        return None
+    return _lib.DropoutDesc(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site), int(step) & 0xFFFFFFFF, _ptr(step_dev))
+
+
+def _dref(d):
+    return C.byref(d) if d is not None else None
+
+
+def layernorm_bwd_fused(dy, x, x_row_stride: int, gamma, mean, rstd, dres, dx, dx_row_stride: int, dgamma, dbeta, z, dx2, dx2_colsum,
+                        rows: int, H: int, drop=None) -> None:
+    """layernorm_bwd plus a second output dx2 = dropout(dx) [* gelu'(z)] and its column sums (vitb_layernorm_bwd_fused)."""
+    lib = _lib.load()
+    nb = lib.vitb_layernorm_bwd_ws_bytes(rows, H)
+    ws = workspace(nb, dy.device)
+    check(lib.vitb_layernorm_bwd_fused(_ptr(dy), _ptr(x), x_row_stride, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                       dx_row_stride, _ptr(dgamma), _ptr(dbeta), _ptr(z), _ptr(dx2), _ptr(dx2_colsum), _dref(drop),
+                                       _ptr(ws), ws.numel(), rows, H, dt_of(dy), _stream()), "layernorm_bwd_fused")
+
+
+def gemm_fwd(a, w_act, bias, residual, out, preact, M: int, N: int, K: int, gelu: bool = False, out_f32: bool = False, drop=None) -> None:
+    """out = dropout(act(a w^T + bias)) + residual; `drop`: a drop_desc (mask in the GEMM epilogue) or None."""
     flags = (GEMM_GELU if gelu else 0) | (GEMM_OUT_F32 if out_f32 else 0)
-    check(_lib.load().vitb_gemm_bias_act_fwd(_ptr(a), _ptr(w_act), _ptr(bias), _ptr(residual), _ptr(out), _ptr(preact),
-                                             M, N, K, flags, dt_of(a), _stream()), "gemm_bias_act_fwd")
+    check(_lib.load().vitb_gemm_bias_act_fwd_drop(_ptr(a), _ptr(w_act), _ptr(bias), _ptr(residual), _ptr(out), _ptr(preact),
+                                                  M, N, K, flags, dt_of(a), _dref(drop), _stream()), "gemm_bias_act_fwd")
 
 
-def gemm_dgrad(dy, w_act, z, dx, M: int, N: int, K: int, dy_f32: bool = False) -> None:
+def gemm_dgrad(dy, w_act, z, dx, M: int, N: int, K: int, dy_f32: bool = False, drop=None) -> None:
+    """dx = dropout(dy w * gelu'(z)); `drop`: a drop_desc or None."""
     flags = GEMM_DY_F32 if dy_f32 else 0
-    check(_lib.load().vitb_gemm_dgrad(_ptr(dy), _ptr(w_act), _ptr(z), _ptr(dx), M, N, K, flags, dt_of(dx), _stream()), "gemm_dgrad")
+    check(_lib.load().vitb_gemm_dgrad_drop(_ptr(dy), _ptr(w_act), _ptr(z), _ptr(dx), M, N, K, flags, dt_of(dx), _dref(drop), _stream()),
+          "gemm_dgrad")
 
 
 def gemm_wgrad(dy, x, dw, dbias, M: int, N: int, K: int, dy_f32: bool = False) -> None:
@@ -170,11 +195,12 @@ def attn_bwd(qkv, o, d_o, lse, dqkv, B: int, T: int, heads: int, d: int, scale: 
           "attn_bwd")
 
 
-def gelu_bwd_colsum(dy, z, dz, colsum, rows: int, cols: int) -> None:
+def gelu_bwd_colsum(dy, z, dz, colsum, rows: int, cols: int, drop=None) -> None:
+    """dz = dropout(dy) * gelu'(z), colsum = column sums of dz; `drop`: a drop_desc or None."""
     lib = _lib.load()
     ws = workspace(lib.vitb_colsum_ws_bytes(rows, cols), dy.device)
-    check(lib.vitb_gelu_bwd_colsum(_ptr(dy), _ptr(z), _ptr(dz), _ptr(colsum), _ptr(ws), ws.numel(), rows, cols, dt_of(dy), _stream()),
-          "gelu_bwd_colsum")
+    check(lib.vitb_gelu_bwd_colsum_drop(_ptr(dy), _ptr(z), _ptr(dz), _ptr(colsum), _ptr(ws), ws.numel(), rows, cols, dt_of(dy), _dref(drop),
+                                        _stream()), "gelu_bwd_colsum")
 
 
 def colsum(x, out, rows: int, cols: int) -> None:
