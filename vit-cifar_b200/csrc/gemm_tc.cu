@@ -120,6 +120,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#ifndef VITB_TC_TAIL_WAIT_READ
+#define VITB_TC_TAIL_WAIT_READ 1
+#endif
+constexpr bool kTailWaitRead = VITB_TC_TAIL_WAIT_READ != 0;
+#ifndef VITB_TC_BIAS_PREFETCH
+#define VITB_TC_BIAS_PREFETCH 1
+#endif
+constexpr bool kBiasPrefetch = VITB_TC_BIAS_PREFETCH != 0;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -625,6 +634,9 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
           tma_load_2d(slab_in, &tma_in, in_bar(ew), n0, in_row);
         }
       }
+      // the 64 bias values of this warp's columns (two 128-byte lines): on their way while the tile's MMAs run, so that a
+      // single-tile kernel does not add an L2 round trip after its accumulator is ready
+      if (kBiasPrefetch && NSLAB > 0 && e.mode == EPI_FWD && e.bias != nullptr && lane < 2) prefetch_l1(e.bias + n0 + lane * 32);
       const long long e0 = (p.dbg && ew == 0 && lane == 0) ? clock64() : 0;
       mbar_wait(tfull_bar(st_, acc), acc_phase);
       tc_fence_after();
@@ -788,7 +800,12 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
       }
       stores_pending = true;
     }
-    if (stores_pending && lane == 0) tma_store_wait_all();
+    // the shared-memory source must have been read before the CTA exits; the global writes themselves complete with the grid
+    // (what dependents wait for), so the kernel's tail does not sit out their round trip
+    if (stores_pending && lane == 0) {
+      if (kTailWaitRead) tma_store_wait_read();
+      else tma_store_wait_all();
+    }
   }
 
   // teardown: everyone (of both CTAs of a pair) done with TMEM and with remote barriers before the owning warp frees it

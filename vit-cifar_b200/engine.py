@@ -292,7 +292,7 @@ class TrainEngine:
         self._allreduce(self.buckets[-1])
         done = {}
         # (bf16 only: the fp32 check mode keeps the module path's kernel chain, with which it is compared bit for bit)
-        fuse_below = (Fn.ln_gelu_fused() and dm.use_mlp and self.act == torch.bfloat16 and (not self.drops or Fn._drop_fused()))
+        fuse_below = (Fn.ln_gelu_fused() and dm.use_mlp and self.act == torch.bfloat16 and (not self.drops or Fn._drop_fused(dm.rows)))
         dz2_in = None
         for i in reversed(range(m.num_layers)):
             # backward scratch ping-pongs between two sets; with weight gradients on the side stream a set may only be rewritten

@@ -117,10 +117,20 @@ class Drop:
         return ops.drop_desc(self.p, self.seed, site, self.step, self.step_dev)
 
 
-def _drop_fused() -> bool:
-    """Dropout masks inside the producing / consuming kernels (default) or as separate elementwise passes (VITB_DROP_FUSED=0:
-    the round-1 path, kept as the A/B and as the reference the fused path is tested against bit for bit)."""
-    return os.environ.get("VITB_DROP_FUSED", "1") != "0"
+# rows from which the in-kernel masks win: measured on B200 with dropout 0.1, 66,560 rows 6.644 vs 6.736 ms per step (+1.4 %),
+# 8,320 rows 1.585 vs 1.520 ms (-4 %): ten Philox rounds per eight elements cost the eight epilogue warps of a GEMM tile about as much
+# as the GELU does, which a large problem hides behind the other stream's MMAs and a single-wave problem does not, and the
+# stand-alone pass over a small tensor is a 4 us launch
+DROP_FUSED_MIN_ROWS = 16384
+
+
+def _drop_fused(rows: int = 1 << 30) -> bool:
+    """Dropout masks inside the producing / consuming kernels, or as separate elementwise passes (the round-1 path, kept as the
+    A/B and as what the fused path is tested against).  VITB_DROP_FUSED=1 / 0 forces one of them; default: by problem size."""
+    v = os.environ.get("VITB_DROP_FUSED", "auto")
+    if v in ("0", "1"):
+        return v == "1"
+    return rows >= DROP_FUSED_MIN_ROWS
 
 
 def ln_gelu_fused() -> bool:
@@ -145,7 +155,7 @@ def mhsa_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: All
     lse = alloc("lse", (dm.B, dm.heads, dm.T), torch.float32)
     ops.attn_fwd(qkv, o, lse, attn_map, dm.B, dm.T, dm.heads, dm.d, dm.scale)
     y = alloc("x1", (rows, H), act)
-    if drop is None or _drop_fused():                                               # layers.py:102, then "+ x" of layers.py:45
+    if drop is None or _drop_fused(rows):                                           # layers.py:102, then "+ x" of layers.py:45
         ops.gemm_fwd(o, c.wo, p.bo, residual, y, None, rows, H, H, drop=drop.desc(0) if drop is not None else None)
     else:
         ops.gemm_fwd(o, c.wo, p.bo, None, y, None, rows, H, H)
@@ -200,7 +210,7 @@ def encoder_fwd(x: torch.Tensor, c: LayerViews, p: LayerViews, dm: Dims, alloc: 
     a1 = alloc("a1", (rows, M), act)
     z2 = alloc("z2", (rows, H), act)
     x2 = alloc("x2", (rows, H), act)
-    if drop is not None and _drop_fused():                                         # mlp[0..2]: the mask in the epilogue, after the GELU
+    if drop is not None and _drop_fused(rows):                                     # mlp[0..2]: the mask in the epilogue, after the GELU
         ops.gemm_fwd(x1n, c.w1, p.b1, None, a1, z1, rows, M, H, gelu=True, drop=drop.desc(1))
         ops.gemm_fwd(a1, c.w2, p.b2, x1, x2, z2, rows, H, M, gelu=True, drop=drop.desc(2))   # mlp[3..5], + out
         return x2, (x, mean1, rstd1, att_saved, (x1, x1n, mean2, rstd2, z1, a1, z2))
@@ -226,7 +236,7 @@ def encoder_bwd(dout: torch.Tensor, saved, c: LayerViews, p: LayerViews, g: Laye
     column sums g_b2 (ops.layernorm_bwd_fused), which replaces that block's GELU-backward launch."""
     x, mean1, rstd1, att_saved, mlp_saved = saved
     rows, H, M, act = dm.rows, dm.H, dm.M, dout.dtype
-    fused_drop = drop is not None and _drop_fused()
+    fused_drop = drop is not None and _drop_fused(rows)
     dya = None
     if dm.use_mlp:
         x1, x1n, mean2, rstd2, z1, a1, z2 = mlp_saved
