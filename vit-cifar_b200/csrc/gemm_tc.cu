@@ -50,6 +50,7 @@ struct TcArgs {
   int pair;          // resident fwd/dgrad launched as cta_group::2 pairs (num_m_blocks then counts 256-row blocks, tma_b boxes are half tiles)
   int pf_tiles;      // fwd/dgrad: prefetch the A tile this many tiles (per stream) ahead into L2; 0 = off
   int pf_kblocks;    // wgrad: prefetch operands this many k-blocks ahead into L2; 0 = off
+  int pf_in;         // resident fwd/dgrad: also prefetch the epilogue's input operand (residual / z) of the tile pf_tiles ahead
   int dbg_flags;     // tools only: 1 = epilogue skips its work (accumulator handed straight back), 2 = producer loads nothing
   DropParams drop;   // thr != 0: nn.Dropout on the output, after GELU / gelu' and before the residual (mask over the flattened [M, N] output)
   int out3;          // EPI_FWD: tma_out is a 3-D (columns, tokens, images) map of a (B, T, H) tensor — the patch embedding writes GEMM
@@ -437,8 +438,15 @@ __global__ void __launch_bounds__(tc_threads(NS, epi_warps_for(BN, NSLAB)), 1)
         // the row block (one per column block, same pace); streaming mode lets the CTA at column block 0 do it.
         if (W_RES) {
           int pm0, pn0, pnblk, psplit;
-          if (get_tile(it + p.pf_tiles * NS, pm0, pn0, pnblk, psplit))
+          if (get_tile(it + p.pf_tiles * NS, pm0, pn0, pnblk, psplit)) {
             for (int kb = res_group; kb < p.kblocks_total; kb += res_groups) tma_prefetch_2d(&tma_a, kb * BK, pm0);
+            if (p.pf_in && p.has_in) {  // the epilogue's input operand (residual / z) of that tile: 64 x 32 boxes
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_prefetch_2d(&tma_in, pn0 + c * 64, pm0 + q * 32);
+            }
+          }
         } else if (nblk == 0) {
           const int pm0 = m0 + ceil_div_dev(p.pf_tiles * NS * (int)gridDim.x, p.num_n_blocks) * BM;
           if (pm0 < p.num_m_blocks * BM)
@@ -941,7 +949,10 @@ constexpr int kBN = 128;
 static long long* g_tc_dbg = nullptr;  // set through vitb_debug_gemm_timeline (tools only)
 static int g_tc_force_mode = 0;        // 0 auto, 1 never resident, 2 always resident (when legal)
 static int g_tc_dbg_flags = 0;
-static int g_tc_pf_tiles = 2, g_tc_pf_kblocks = 8;  // L2 prefetch distances (tools can change them)
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+// L2 prefetch distances (tools / VITB_GEMM_PF_* can change them)
+static int g_tc_pf_tiles = env_int("VITB_GEMM_PF_TILES", 2), g_tc_pf_kblocks = env_int("VITB_GEMM_PF_KBLOCKS", 8);
+static int g_tc_pf_in = env_int("VITB_GEMM_PF_IN", 0);
 
 static bool use_resident_weights(const TcArgs& a) {
   if (a.e.mode == EPI_RAW_F32 || a.splits != 1 || a.kblocks_total > kMaxResKB || a.num_n_blocks > kNumSMs) return false;
@@ -971,6 +982,7 @@ static int launch_tc(const TcMaps& m, const TcArgs& args_in, cudaStream_t st) {
   args.dbg_flags = g_tc_dbg_flags;
   args.pf_tiles = g_tc_pf_tiles;
   args.pf_kblocks = g_tc_pf_kblocks;
+  args.pf_in = g_tc_pf_in;
   if constexpr (BN != 128) {
     // wide tiles (BN = 192): a 128x192x16 MMA holds the pipe for 96 cycles, which one issuing thread can sustain, and the
     // operand bytes per FLOP drop by a sixth; single stream.  wgrad: 5 stages x 40 KB, fp32 direct-store epilogue;
