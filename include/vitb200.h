@@ -217,6 +217,15 @@ int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const
                              const float* lam_dev, const int* n_valid_dev, float* loss, float* dlogits, int B, int C,
                              float smoothing, float grad_scale, void* stream);
 
+/* The same loss over many thread blocks (the single-block form above takes 57 us for 100 classes at B = 1024): per-block partial
+ * sums and the arrival counter live in `ws` (vitb_ls_ce_ws_bytes() bytes of device memory, 4-byte aligned, ZERO before the first
+ * call; the kernel leaves the counter at zero, so the buffer is reusable by the next call on the same stream — not by concurrent
+ * calls).  The partials are added in block order: deterministic.  ws == NULL or C > 256: falls back to the single-block kernel. */
+size_t vitb_ls_ce_ws_bytes(void);
+int vitb_ls_ce_blocks_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam,
+                              const float* lam_dev, const int* n_valid_dev, float* loss, float* dlogits, int B, int C,
+                              float smoothing, float grad_scale, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- backward of one nn.Linear y = x W^T (W: [N, K] bf16) in a single pass over dY — what autograd runs as two GEMMs
  * (layers.py:33-37, 85, 102):  dx [M, K] = dy [M, N] W  (times gelu'(z) when z [M, K] != NULL: the Linear's input was GELU(z),
  * layers.py:34);  dw [N, K] fp32 = dy^T x;  dx_colsum [K] fp32 (may be NULL) = column sums of dx as stored, i.e. the bias gradient

@@ -138,7 +138,7 @@ def test_gemm_wgrad_dbias(ops, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("B,C,H", [(1024, 10, 384), (130, 100, 384), (9, 128, 768)])
+@pytest.mark.parametrize("B,C,H", [(1024, 10, 384), (130, 100, 384), (9, 128, 768), (1023, 100, 384), (17, 10, 128), (64, 7, 200)])
 def test_classifier_head_kernels(ops, dtype, B, C, H):
     """fc[1] (vit.py:63,76) forward / dgrad / wgrad+dbias through the small-N kernels (head.cu), at CIFAR-10 and -100 widths."""
     hn = rnd((B, H), dtype, 1); w = rnd((C, H), dtype, 2, 0.05); bias = rnd((C,), torch.float32, 3)
@@ -286,14 +286,22 @@ def test_pool(ops, dtype, mode):
         assert torch.equal(dx2[:, 0], dx[:, 0]) and bool((dx2[:, 1:] == 3.0).all())  # really writes nothing else
 
 
-@pytest.mark.parametrize("B,C", [(4, 10), (128, 100), (1000, 10), (3, 1000)])
+@pytest.mark.parametrize("B,C", [(4, 10), (128, 100), (1000, 10), (3, 1000), (1024, 100), (1023, 17), (5, 16), (33, 256), (2, 257)])
 def test_ls_ce(ops, B, C):
     import oracle
     z = rnd((B, C), torch.float32, 1, 3.0); y = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(2))
     loss = torch.empty((), device="cuda"); dl = torch.empty((B, C), device="cuda")
-    ops.ls_ce(cu(z), cu(y), loss, dl, 0.1, 1.0)
-    assert abs(loss.item() - oracle.ls_ce_loss(z, y, C, 0.1).item()) < 1e-5 * max(1.0, abs(loss.item()))
-    assert rel(dl, oracle.ls_ce_dlogits(z, y, C, 0.1)) < 1e-5
+    for fn in (ops.ls_ce, ops.ls_ce_single_block):  # many blocks + workspace, and the workspace-free single block
+        loss.fill_(-1.0); dl.fill_(7.0)
+        fn(cu(z), cu(y), loss, dl, 0.1, 1.0)
+        assert abs(loss.item() - oracle.ls_ce_loss(z, y, C, 0.1).item()) < 1e-5 * max(1.0, abs(loss.item()))
+        assert rel(dl, oracle.ls_ce_dlogits(z, y, C, 0.1)) < 1e-5
+    # deterministic (block partials are added in block order) and reusable: the arrival counter is back at zero
+    l2 = torch.empty((), device="cuda"); d2 = torch.empty_like(dl)
+    for _ in range(3):
+        ops.ls_ce(cu(z), cu(y), l2, d2, 0.1, 1.0)
+        ops.ls_ce(cu(z), cu(y), loss, dl, 0.1, 1.0)
+        assert l2.item() == loss.item() and torch.equal(d2, dl)
 
 
 def test_adam_matches_oracle(ops):

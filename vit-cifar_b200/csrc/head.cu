@@ -36,6 +36,63 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
   }
 }
 
+// K = 128 KV: a warp takes TWO rows, keeps them in registers and walks the classes four at a time — eight independent dot
+// products and eight interleaved warp reductions in flight instead of one (the one-row, one-class-at-a-time kernel above is a chain
+// of N dependent load -> FMA -> shuffle rounds: 104 us for the 100-class head at B = 1024, 4.7 % of that configuration's step).
+// Per (row, class) the summation order is the one of head_fwd_kernel (lane-strided k, then the xor tree): bit-identical results.
+constexpr int kHeadFwdClasses = 20;  // classes per CTA (a multiple of 4)
+template <typename T, int KV>
+__global__ void __launch_bounds__(256) head_fwd_rows_kernel(const T* __restrict__ a, const T* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int M, int N) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int K = 128 * KV;
+  const int lane = threadIdx.x & 31;
+  const int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (r0 >= M) return;
+  const bool two = r0 + 1 < M;
+  float4 x0[KV], x1[KV];
+#pragma unroll
+  for (int j = 0; j < KV; ++j) {
+    x0[j] = ld4(a + (size_t)r0 * K + (j * 32 + lane) * 4);
+    x1[j] = ld4(a + (size_t)(two ? r0 + 1 : r0) * K + (j * 32 + lane) * 4);
+  }
+  // blockIdx.y owns kHeadFwdClasses classes: the class loop is a chain of load -> FMA -> shuffle rounds (about a microsecond per
+  // four classes), so a 100-class head is spread over five times as many warps instead of walked by one
+  const int c_end = min(N, ((int)blockIdx.y + 1) * kHeadFwdClasses);
+  for (int c = (int)blockIdx.y * kHeadFwdClasses; c < c_end; c += 4) {
+    float s0[4], s1[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const T* wr = w + (size_t)min(c + cc, N - 1) * K;  // (classes beyond N: computed on the last row, not stored)
+      float u = 0.f, v = 0.f;
+#pragma unroll
+      for (int j = 0; j < KV; ++j) {
+        const float4 y = ld4(wr + (j * 32 + lane) * 4);
+        u = fmaf(x0[j].x, y.x, u); u = fmaf(x0[j].y, y.y, u); u = fmaf(x0[j].z, y.z, u); u = fmaf(x0[j].w, y.w, u);
+        v = fmaf(x1[j].x, y.x, v); v = fmaf(x1[j].y, y.y, v); v = fmaf(x1[j].z, y.z, v); v = fmaf(x1[j].w, y.w, v);
+      }
+      s0[cc] = u;
+      s1[cc] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        s0[cc] += __shfl_xor_sync(0xffffffffu, s0[cc], o);
+        s1[cc] += __shfl_xor_sync(0xffffffffu, s1[cc], o);
+      }
+    }
+    if (lane < 4 && c + lane < c_end) {
+      const float b = bias ? bias[c + lane] : 0.f;
+      const float t0 = lane == 0 ? s0[0] : lane == 1 ? s0[1] : lane == 2 ? s0[2] : s0[3];
+      const float t1 = lane == 0 ? s1[0] : lane == 1 ? s1[1] : lane == 2 ? s1[2] : s1[3];
+      out[(size_t)r0 * N + c + lane] = t0 + b;
+      if (two) out[(size_t)(r0 + 1) * N + c + lane] = t1 + b;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx, int M, int N,
                                                          int K) {
@@ -122,12 +179,27 @@ __global__ void __launch_bounds__(32 * kHeadSlices) head_wgrad_kernel(const floa
 
 bool head_shape_ok(int M, int N, int K) { return N <= 128 && K % 4 == 0 && M > 0; }
 
-int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st) {
+template <typename T>
+static int head_fwd_launch_t(const T* a, const T* w, const float* bias, float* out, int M, int N, int K, cudaStream_t st) {
   const int wpb = 8;
-  if (dt == VITB_BF16) VITB_LAUNCH((head_fwd_kernel<bf16>), ceil_div(M, wpb), 32 * wpb, 0, st, (const bf16*)a, (const bf16*)w, bias, out, M, N, K);
-  else VITB_LAUNCH((head_fwd_kernel<float>), ceil_div(M, wpb), 32 * wpb, 0, st, (const float*)a, (const float*)w, bias, out, M, N, K);
+#define VITB_HEAD_ROWS(KV)                                                                                             \
+  case KV: VITB_LAUNCH((head_fwd_rows_kernel<T, KV>), dim3(ceil_div(M, 2 * wpb), ceil_div(N, kHeadFwdClasses)), 32 * wpb, 0, st, a, w, bias, out, M, N); break;
+  if (K % 128 == 0 && ((uintptr_t)a | (uintptr_t)w) % 16 == 0) {
+    switch (K / 128) {
+      VITB_HEAD_ROWS(1) VITB_HEAD_ROWS(2) VITB_HEAD_ROWS(3) VITB_HEAD_ROWS(4) VITB_HEAD_ROWS(6) VITB_HEAD_ROWS(8)
+      default: VITB_LAUNCH((head_fwd_kernel<T>), ceil_div(M, wpb), 32 * wpb, 0, st, a, w, bias, out, M, N, K); break;
+    }
+  } else {
+    VITB_LAUNCH((head_fwd_kernel<T>), ceil_div(M, wpb), 32 * wpb, 0, st, a, w, bias, out, M, N, K);
+  }
+#undef VITB_HEAD_ROWS
   VITB_LAUNCH_OK();
   return 0;
+}
+
+int head_fwd_launch(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, int dt, cudaStream_t st) {
+  if (dt == VITB_BF16) return head_fwd_launch_t<bf16>((const bf16*)a, (const bf16*)w, bias, out, M, N, K, st);
+  return head_fwd_launch_t<float>((const float*)a, (const float*)w, bias, out, M, N, K, st);
 }
 
 int head_dgrad_launch(const float* dy, const void* w, void* dx, int M, int N, int K, int dt, cudaStream_t st) {

@@ -10,6 +10,104 @@ namespace vitb {
 // Two-target form (CutMix / MixUp, network.py:149-167): loss = lam * L(z, a) + (1 - lam) * L(z, b), i.e. the smoothed target
 // distribution is q = lam * q_a + (1 - lam) * q_b.  labels_b == nullptr is the plain loss.  lam comes from device memory when
 // lam_dev != nullptr (so a captured CUDA graph sees a new value every step).
+// One block of 1024 threads (the loss is ONE number: a single block sums it in a fixed order without scratch memory).  A row is
+// owned by a group of G lanes (G = 16 for C <= 16, else 32) that keeps its C <= 256 logits in registers: coalesced loads, one pass
+// over memory, xor-tree reductions inside the group.  (Round 1's one-thread-per-row loop took 141 us at B = 1024, C = 100: three
+// uncoalesced passes over the row per thread.)  C > 8 G falls back to the serial row loop.
+constexpr int kLsMaxV = 8;  // logits per lane, at most
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// kLsR rows per group and iteration, all their loads (logits, labels) issued before the first reduction: a row is a chain of
+// load -> reduce -> exp -> reduce -> log -> gather z[y] of about two thousand cycles, and a group walks B / (1024 / G) rows
+// (V = logits per lane, R = rows per iteration: 1024 threads leave 64 registers per thread)
+template <int G, int kLsV, int kLsR>
+__device__ __forceinline__ float ls_ce_rows(const float* __restrict__ logits, const int64_t* __restrict__ labels, const int64_t* __restrict__ labels_b,
+                                            float lam, float* __restrict__ dlogits, int B, int C, int nv, float conf, float off, float gs) {
+  // groups of the whole grid (one block in ls_ce_kernel, many in ls_ce_blocks_kernel)
+  const int gl = threadIdx.x % G, gid = (int)blockIdx.x * (blockDim.x / G) + threadIdx.x / G, ngroups = (int)gridDim.x * (blockDim.x / G);
+  float acc = 0.f;
+  for (int base = 0; base < B; base += ngroups * kLsR) {  // (uniform trip count: the shuffles below need every lane of the warp)
+    float v[kLsR][kLsV], mx[kLsR], sz[kLsR], se[kLsR];
+    int y[kLsR], yb[kLsR];
+    bool live[kLsR];
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) {
+      const int r = base + q * ngroups + gid;
+      live[q] = r < nv;
+      mx[q] = -INFINITY;
+      sz[q] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLsV; ++i) {
+        const int j = gl + i * G;
+        v[q][i] = (live[q] && j < C) ? logits[(size_t)r * C + j] : -INFINITY;
+      }
+      y[q] = live[q] ? (int)labels[r] : 0;
+      yb[q] = (live[q] && labels_b != nullptr) ? (int)labels_b[r] : y[q];
+    }
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) {
+#pragma unroll
+      for (int i = 0; i < kLsV; ++i)
+        if (live[q] && gl + i * G < C) {
+          mx[q] = fmaxf(mx[q], v[q][i]);
+          sz[q] += v[q][i];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) {
+      mx[q] = group_max<G>(mx[q]);
+      sz[q] = group_sum<G>(sz[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) {
+      se[q] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLsV; ++i)
+        if (live[q] && gl + i * G < C) se[q] += expf(v[q][i] - mx[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) se[q] = group_sum<G>(se[q]);
+#pragma unroll
+    for (int q = 0; q < kLsR; ++q) {
+      const int r = base + q * ngroups + gid;
+      if (r < B && !live[q] && dlogits != nullptr) {
+        for (int j = gl; j < C; j += G) dlogits[(size_t)r * C + j] = 0.f;
+      }
+      if (!live[q]) continue;
+      const float lse = mx[q] + logf(se[q]);
+      const float zy = logits[(size_t)r * C + y[q]], zb = logits[(size_t)r * C + yb[q]];
+      // sum_j -q_j (z_j - lse) for each target, then the lam mix (criterions.py:13-19 applied twice, network.py:163-165)
+      const float la = -(conf * (zy - lse) + off * ((sz[q] - zy) - (float)(C - 1) * lse));
+      const float lb = -(conf * (zb - lse) + off * ((sz[q] - zb) - (float)(C - 1) * lse));
+      if (gl == 0) acc += lam * la + (1.0f - lam) * lb;
+      if (dlogits != nullptr) {
+#pragma unroll
+        for (int i = 0; i < kLsV; ++i) {
+          const int j = gl + i * G;
+          if (j < C) {
+            const float p = expf(v[q][i] - lse);
+            const float t = lam * (j == y[q] ? conf : off) + (1.0f - lam) * (j == yb[q] ? conf : off);
+            dlogits[(size_t)r * C + j] = (p - t) * gs;
+          }
+        }
+      }
+    }
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(1024)
     ls_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const int64_t* __restrict__ labels_b, float lam_host,
                  const float* __restrict__ lam_dev, const int* __restrict__ n_valid_dev, float* __restrict__ loss, float* __restrict__ dlogits, int B,
@@ -27,6 +125,13 @@ __global__ void __launch_bounds__(1024)
   const float gs = grad_scale / (float)nv;
   const float lam = labels_b == nullptr ? 1.0f : (lam_dev != nullptr ? *lam_dev : lam_host);
   float acc = 0.f;
+  if (C <= 16) {
+    acc = ls_ce_rows<16, 1, 4>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  } else if (C <= 32 * 4) {
+    acc = ls_ce_rows<32, 4, 4>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  } else if (C <= 32 * kLsMaxV) {
+    acc = ls_ce_rows<32, kLsMaxV, 2>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  } else {
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
     if (r >= nv) {
       if (dlogits != nullptr)
@@ -46,7 +151,6 @@ __global__ void __launch_bounds__(1024)
     for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
     const float lse = mx + logf(se);
     const float zy = z[y], zb = z[yb];
-    // sum_j -q_j (z_j - lse) for each target, then the lam mix (criterions.py:13-19 applied twice, network.py:163-165)
     const float la = -(conf * (zy - lse) + off * ((sz - zy) - (float)(C - 1) * lse));
     const float lb = -(conf * (zb - lse) + off * ((sz - zb) - (float)(C - 1) * lse));
     acc += lam * la + (1.0f - lam) * lb;
@@ -59,6 +163,7 @@ __global__ void __launch_bounds__(1024)
       }
     }
   }
+  }
   acc = warp_sum(acc);
   if (lane == 0) part[warp] = acc;
   __syncthreads();
@@ -66,6 +171,49 @@ __global__ void __launch_bounds__(1024)
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += part[w];
     *loss = s / (float)nv;
+  }
+}
+
+// The same rows over MANY blocks (a 100-class loss at B = 1024 is 4 M instructions: 57 us on one SM): every block leaves the fixed-order
+// sum of its rows in ws[1 + block], the last block to arrive (counter in ws[0], which atomicInc wraps back to zero) adds the partials in
+// block order — deterministic, and no second launch.  C <= 256.
+constexpr int kLsBlockThreads = 256;
+constexpr int kLsMaxBlocks = 256;
+__global__ void __launch_bounds__(kLsBlockThreads)
+    ls_ce_blocks_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const int64_t* __restrict__ labels_b, float lam_host,
+                        const float* __restrict__ lam_dev, const int* __restrict__ n_valid_dev, float* __restrict__ loss, float* __restrict__ dlogits,
+                        int B, int C, float smoothing, float grad_scale, float* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float part[kLsBlockThreads / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float off = smoothing / (float)(C - 1);
+  const float conf = 1.0f - smoothing;
+  const int nv = n_valid_dev != nullptr ? min(max(*n_valid_dev, 1), B) : B;
+  const float gs = grad_scale / (float)nv;
+  const float lam = labels_b == nullptr ? 1.0f : (lam_dev != nullptr ? *lam_dev : lam_host);
+  float acc;
+  if (C <= 16) acc = ls_ce_rows<16, 1, 2>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  else if (C <= 32 * 4) acc = ls_ce_rows<32, 4, 2>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  else acc = ls_ce_rows<32, kLsMaxV, 2>(logits, labels, labels_b, lam, dlogits, B, C, nv, conf, off, gs);
+  acc = warp_sum(acc);
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kLsBlockThreads / 32; ++w) s += part[w];
+    volatile float* vp = ws + 1;
+    vp[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int done = atomicInc(reinterpret_cast<unsigned int*>(ws), gridDim.x - 1);  // wraps to 0 with the last arrival
+    last = done == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      float t = 0.f;
+      for (unsigned int b = 0; b < gridDim.x; ++b) t += vp[b];
+      *loss = t / (float)nv;
+    }
   }
 }
 
@@ -167,6 +315,26 @@ int vitb_ls_ce_batch_fwd_bwd(const float* logits, const int64_t* labels_a, const
   VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
   VITB_REQUIRE(lam_dev != nullptr || (lam >= 0.0f && lam <= 1.0f), "ls_ce: lam=%f outside [0, 1]", lam);
   VITB_LAUNCH((ls_ce_kernel), 1, 1024, 0, (cudaStream_t)stream, logits, labels_a, labels_b, lam, lam_dev, n_valid_dev, loss, dlogits, B, C, smoothing, grad_scale);
+  VITB_LAUNCH_OK();
+  return 0;
+}
+
+size_t vitb_ls_ce_ws_bytes(void) { return (size_t)(1 + kLsMaxBlocks) * sizeof(float); }
+
+int vitb_ls_ce_blocks_fwd_bwd(const float* logits, const int64_t* labels_a, const int64_t* labels_b, float lam, const float* lam_dev,
+                              const int* n_valid_dev, float* loss, float* dlogits, int B, int C, float smoothing, float grad_scale, void* ws,
+                              size_t ws_bytes, void* stream) {
+  VITB_REQUIRE(logits && labels_a && loss, "ls_ce: null pointer");
+  VITB_REQUIRE(B > 0 && C > 1, "ls_ce: bad shape B=%d C=%d", B, C);
+  VITB_REQUIRE(lam_dev != nullptr || (lam >= 0.0f && lam <= 1.0f), "ls_ce: lam=%f outside [0, 1]", lam);
+  if (ws == nullptr || C > 32 * kLsMaxV)  // no workspace / very wide rows: the single-block kernel
+    return vitb_ls_ce_batch_fwd_bwd(logits, labels_a, labels_b, lam, lam_dev, n_valid_dev, loss, dlogits, B, C, smoothing, grad_scale, stream);
+  VITB_REQUIRE(ws_bytes >= vitb_ls_ce_ws_bytes() && (uintptr_t)ws % 4 == 0, "ls_ce: workspace too small (%zu < %zu)", ws_bytes, vitb_ls_ce_ws_bytes());
+  const int groups_per_block = kLsBlockThreads / (C <= 16 ? 16 : 32);
+  int blocks = ceil_div(B, groups_per_block * 2);  // two rows per group and iteration
+  if (blocks > kLsMaxBlocks) blocks = kLsMaxBlocks;
+  VITB_LAUNCH((ls_ce_blocks_kernel), blocks, kLsBlockThreads, 0, (cudaStream_t)stream, logits, labels_a, labels_b, lam, lam_dev, n_valid_dev, loss, dlogits,
+              B, C, smoothing, grad_scale, (float*)ws);
   VITB_LAUNCH_OK();
   return 0;
 }

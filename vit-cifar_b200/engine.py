@@ -134,6 +134,8 @@ class TrainEngine:
         self.labels_b = torch.zeros_like(self.labels)
         self._labels_b_stage = torch.zeros_like(self.labels)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        from . import _lib
+        self._ls_ws = torch.zeros(int(_lib.load().vitb_ls_ce_ws_bytes()) // 4, dtype=torch.float32, device=self.dev)  # loss kernel: partials + counter
         # input staging for `prefetch`: the next batch crosses PCIe on a copy stream while the current step computes
         self._img_stage = torch.zeros_like(self.img)
         self._labels_stage = torch.zeros_like(self.labels)
@@ -245,9 +247,9 @@ class TrainEngine:
         n_valid_dev = self.hyper_dev.view(torch.int32)[11:12]
         if self.mixed_targets:
             ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, labels_b=self.labels_b, lam_dev=self.hyper_dev[9:10],
-                      n_valid_dev=n_valid_dev)
+                      n_valid_dev=n_valid_dev, ws=self._ls_ws)
         else:
-            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, n_valid_dev=n_valid_dev)
+            ops.ls_ce(self.logits, self.labels, self.loss, self.dlogits, self.smoothing, 1.0, n_valid_dev=n_valid_dev, ws=self._ls_ws)
 
         self._opt_done_from = self.n  # elements [_opt_done_from, n) have had their optimiser step on the side stream
         self._backward(hsaved, saved, words)

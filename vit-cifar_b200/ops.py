@@ -262,11 +262,41 @@ def dropout(x, residual, out, p: float, seed: int, site: int, step: int = 0, ste
                                    int(step) & 0xFFFFFFFF, _ptr(step_dev), dt_of(x), _stream()), "dropout")
 
 
+_ls_ws = {}
+
+
+def _ls_workspace(device) -> torch.Tensor:
+    """Zero-initialised partial-sum / counter buffer of the multi-block loss kernel, one per (device, stream): the kernel leaves the
+    counter at zero, so consecutive calls on a stream share it; calls on different streams must not."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ls_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().vitb_ls_ce_ws_bytes()) // 4, dtype=torch.float32, device=device)
+        _ls_ws[key] = ws
+    return ws
+
+
 def ls_ce(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0, lam_dev=None,
-          n_valid_dev=None) -> None:
+          n_valid_dev=None, ws=None) -> None:
     """LS-CE forward + dlogits.  With `labels_b`: the two-target CutMix / MixUp loss lam*L(a) + (1-lam)*L(b) (network.py:149-167);
     `lam_dev` (1-element fp32 device tensor) overrides `lam` so that a captured graph reads a fresh value every step.
-    `n_valid_dev` (1-element int32 device tensor): only rows [0, n_valid) are images (partial last batch of an epoch)."""
+    `n_valid_dev` (1-element int32 device tensor): only rows [0, n_valid) are images (partial last batch of an epoch).
+    `ws`: zeroed fp32 workspace of vitb_ls_ce_ws_bytes() for the multi-block kernel (default: one per device and stream)."""
+    B, Cn = logits.shape
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    assert labels_b is None or (labels_b.dtype == torch.int64 and labels_b.shape == labels.shape)
+    assert n_valid_dev is None or n_valid_dev.dtype == torch.int32
+    _contig(logits, labels, dlogits, labels_b)
+    _ptr(logits)  # (CPU tensors: raise before touching the device for a workspace)
+    if ws is None:
+        ws = _ls_workspace(logits.device)
+    check(_lib.load().vitb_ls_ce_blocks_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(labels_b), float(lam), _ptr(lam_dev), _ptr(n_valid_dev), _ptr(loss),
+                                                _ptr(dlogits), B, Cn, smoothing, grad_scale, _ptr(ws), ws.numel() * 4, _stream()), "ls_ce_blocks_fwd_bwd")
+
+
+def ls_ce_single_block(logits, labels, loss, dlogits, smoothing: float, grad_scale: float = 1.0, labels_b=None, lam: float = 1.0,
+                       lam_dev=None, n_valid_dev=None) -> None:
+    """The workspace-free single-block form of ls_ce (vitb_ls_ce_fwd_bwd / _mix_ / _batch_)."""
     B, Cn = logits.shape
     assert logits.dtype == torch.float32 and labels.dtype == torch.int64
     _contig(logits, labels, dlogits)
