@@ -945,11 +945,11 @@ static int launch_tc_impl(const TcMaps& m, const TcArgs& args, cudaStream_t st) 
 }
 
 constexpr int kBN = 128;
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
 static long long* g_tc_dbg = nullptr;  // set through vitb_debug_gemm_timeline (tools only)
 static int g_tc_force_mode = 0;        // 0 auto, 1 never resident, 2 always resident (when legal)
 static int g_tc_dbg_flags = 0;
-static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 // L2 prefetch distances (tools / VITB_GEMM_PF_* can change them)
 static int g_tc_pf_tiles = env_int("VITB_GEMM_PF_TILES", 2), g_tc_pf_kblocks = env_int("VITB_GEMM_PF_KBLOCKS", 8);
 static int g_tc_pf_in = env_int("VITB_GEMM_PF_IN", 0);
@@ -1327,6 +1327,18 @@ static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* 
   // wide (QKV: 27 tiles); narrow outputs (9 tiles) keep one item per CTA, where twice the fp32 partials cost more than the second
   // stream gains
   int s = (kNumSMs * ((bn == 128 && tiles >= 18) ? g_tc_streams : 1)) / (tiles > 0 ? tiles : 1);
+  // tuning hook: at least this many 64-row k-blocks per work item (fewer, longer items and fewer fp32 partials for small batches)
+  static const int min_kb = env_int("VITB_WGRAD_MIN_KBLOCKS", 1);
+  if (min_kb > 1 && s > total / min_kb) s = total / min_kb;
+  // Short reductions (small batch / few tokens): fewer, longer work items.  A weight gradient runs on the side stream next to the
+  // critical path; with 130-272 k-blocks to reduce, 22-24 splits per tile put 6 x 24 CTAs of a few k-blocks each on the machine and
+  // write 24 fp32 partial tiles, 8-11 splits finish as soon in wall-clock terms, leave two thirds of the SMs to the critical path and
+  // cut the partials (and the flush that re-reads them) to a third.  Measured (profiles/r2_wgrad_splits_ab.md): B=128 1.376 -> 1.272 ms
+  // at 8 splits (6: 1.347), T=17 at B=1024 1.997 -> 1.888 ms at 11 (8: 1.913, 16: 1.947), T=17 at B=128 0.910 -> 0.844 ms at 8;
+  // B=1024 (1040 k-blocks) is flat from 8 to 24.  VITB_WGRAD_MAX_SPLITS = n caps at n, -1 removes the cap.
+  static const int max_splits = env_int("VITB_WGRAD_MAX_SPLITS", 0);
+  const int cap = max_splits > 0 ? max_splits : (max_splits < 0 ? s : (total / 24 > 8 ? total / 24 : 8));
+  if (s > cap) s = cap;
   if (s < 1) s = 1;
   if (s > total) s = total;
   const int per = ceil_div(total, s);
