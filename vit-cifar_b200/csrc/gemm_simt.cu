@@ -249,14 +249,20 @@ __global__ void batch_sum_kernel(const T* __restrict__ x, float* __restrict__ pa
 
 static int batch_sum_slices(int B) { return B >= 256 ? 16 : (B >= 32 ? 4 : 1); }
 
-// words[m][f..f+7] (bf16) for the tensor-core path: 8 consecutive features per thread (vit.py:79-89)
-__global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restrict__ words, int B, int S, int P) {
+// words[m][f..f+7] (bf16) for the tensor-core path: 8 consecutive features per thread (vit.py:79-89).  The same launch also does
+// the two small jobs of the stem that depend on nothing else: the bf16 copy of pos_emb the GEMM epilogue reads through TMA
+// (pos_bf16 != nullptr) and the B cls rows out[b, 0, :] = cls + pos[0] (cls_out != nullptr; rows the GEMM does not write) —
+// 4 launches -> 2 for the patch embedding.
+__global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restrict__ words, int B, int S, int P, const float* __restrict__ pos,
+                                  bf16* __restrict__ pos_bf16, int64_t n_pos, const float* __restrict__ cls, bf16* __restrict__ cls_out, int Tn,
+                                  int H) {
   pdl_trigger();
   pdl_wait();
   const int ps = S / P;
   const int K = ps * ps * 3, K8 = K / 8;
   const int64_t total = (int64_t)B * P * P * K8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < total; i += nthreads) {
     const int f0 = (int)(i % K8) * 8;
     const int m = (int)(i / K8);
     float v[8];
@@ -265,6 +271,15 @@ __global__ void words_bf16_kernel(const float* __restrict__ img, bf16* __restric
     uint4 u;
     u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(words + (int64_t)m * K + f0) = u;
+  }
+  if (pos_bf16 != nullptr) {
+    for (int64_t i = tid; i < n_pos; i += nthreads) pos_bf16[i] = __float2bfloat16_rn(pos[i]);
+  }
+  if (cls_out != nullptr) {
+    for (int64_t i = tid; i < (int64_t)B * H; i += nthreads) {
+      const int b = (int)(i / H), c = (int)(i % H);
+      cls_out[(size_t)b * Tn * H + c] = __float2bfloat16_rn(cls[c] + pos[c]);
+    }
   }
 }
 
@@ -298,21 +313,12 @@ int vitb_patch_embed_fwd(const float* img, const float* w, const void* w_act, co
     // pos_emb[token] and stores into the token rows of (B, T, H) -> the B cls rows
     int blocks = (int)ceil_div64((int64_t)B * PP * (K / 8), 256);
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-    VITB_LAUNCH((words_bf16_kernel), blocks, 256, 0, st, img, (bf16*)words, B, S, P);
-    VITB_LAUNCH_OK();
     const void* pos_bf16 = nullptr;
-    if (PP % 32 == 0 && ws != nullptr && ws_bytes >= vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)) {
-      int rc0 = vitb_cast_f32_to_bf16(pos, ws, (int64_t)Tn * H, stream);
-      if (rc0) return rc0;
-      pos_bf16 = ws;
-    }
-    int rc = tc_patch_fwd(words, w_act, bias, pos, pos_bf16, out, B, PP, Tn, has_cls ? 1 : 0, H, K, st);
-    if (rc) return rc;
-    if (has_cls) {
-      VITB_LAUNCH((cls_rows_kernel<bf16>), B, 128, 0, st, cls, pos, (bf16*)out, B, Tn, H);
-      VITB_LAUNCH_OK();
-    }
-    return 0;
+    if (PP % 32 == 0 && ws != nullptr && ws_bytes >= vitb_patch_embed_fwd_ws_bytes(B, S, P, H, dt)) pos_bf16 = ws;
+    VITB_LAUNCH((words_bf16_kernel), blocks, 256, 0, st, img, (bf16*)words, B, S, P, pos, (bf16*)const_cast<void*>(pos_bf16), (int64_t)Tn * H,
+                has_cls ? cls : nullptr, has_cls ? (bf16*)out : nullptr, Tn, H);
+    VITB_LAUNCH_OK();
+    return tc_patch_fwd(words, w_act, bias, pos, pos_bf16, out, B, PP, Tn, has_cls ? 1 : 0, H, K, st);
   }
   SimtGemmArgs g = {};
   g.a = img; g.b = w;

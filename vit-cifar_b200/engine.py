@@ -290,7 +290,7 @@ class TrainEngine:
             ops.defer_begin(self._arena)
         g_ln_w, g_ln_b, g_fc_w, g_fc_b = self.head_g
         dx = Fn.head_bwd(self.dlogits, hsaved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B, T, H, Cn, m.is_cls_token, self.act,
-                         self._alloc("headb"), dx_prezeroed=True)
+                         self._alloc("headb"), dx_prezeroed=True, side=side)
         self._allreduce(self.buckets[-1])
         done = {}
         # (bf16 only: the fp32 check mode keeps the module path's kernel chain, with which it is compared bit for bit)

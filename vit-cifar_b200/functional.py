@@ -332,15 +332,20 @@ def head_fwd(x: torch.Tensor, ln_w, ln_b, fc_w_c, fc_b, B: int, T: int, H: int, 
 
 
 def head_bwd(dlogits: torch.Tensor, saved, ln_w, fc_w_c, g_ln_w, g_ln_b, g_fc_w, g_fc_b, B: int, T: int, H: int, C: int,
-             is_cls: bool, act: torch.dtype, alloc: Alloc, dx_prezeroed: bool = False) -> torch.Tensor:
-    """dlogits (B,C) fp32 -> grad of the encoder output (B*T,H) act (zeros where nothing flows)."""
+             is_cls: bool, act: torch.dtype, alloc: Alloc, dx_prezeroed: bool = False, side: Optional[SideStream] = None) -> torch.Tensor:
+    """dlogits (B,C) fp32 -> grad of the encoder output (B*T,H) act (zeros where nothing flows).  `side`: stream for the weight
+    gradient (off the critical path, like the encoder's)."""
     src, stride, hn, mean, rstd = saved
-    ops.gemm_wgrad(dlogits, hn, g_fc_w, g_fc_b, B, C, H, dy_f32=True)
+    _wgrad(side, dlogits, hn, g_fc_w, g_fc_b, B, C, H, dy_f32=True)
     dhn = alloc("dhn", (B, H), act)
     ops.gemm_dgrad(dlogits, fc_w_c, None, dhn, B, C, H, dy_f32=True)
+    dx = alloc("dxL", (B * T, H), act)
+    if is_cls and dx_prezeroed:
+        # `alloc` hands out a static buffer whose non-cls rows are zero and stay zero (TrainEngine): the LayerNorm backward writes
+        # its B rows straight into the cls rows of dx (row stride T * H) — no pooled gradient, no scatter launch
+        ops.layernorm_bwd(dhn, src, stride, ln_w, mean, rstd, None, dx, T * H, g_ln_w, g_ln_b, None, B, H)
+        return dx
     dpool = alloc("dpool", (B, H), act)
     ops.layernorm_bwd(dhn, src, stride, ln_w, mean, rstd, None, dpool, H, g_ln_w, g_ln_b, None, B, H)
-    dx = alloc("dxL", (B * T, H), act)
-    # dx_prezeroed: `alloc` hands out a static buffer whose non-cls rows are zero and stay zero (TrainEngine): write B rows, not B*T
-    ops.pool_bwd(dpool, dx, B, T, H, (2 if dx_prezeroed else 0) if is_cls else 1)
+    ops.pool_bwd(dpool, dx, B, T, H, 0 if is_cls else 1)
     return dx
