@@ -1335,9 +1335,12 @@ static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* 
   // write 24 fp32 partial tiles, 8-11 splits finish as soon in wall-clock terms, leave two thirds of the SMs to the critical path and
   // cut the partials (and the flush that re-reads them) to a third.  Measured (profiles/r2_wgrad_splits_ab.md): B=128 1.376 -> 1.272 ms
   // at 8 splits (6: 1.347), T=17 at B=1024 1.997 -> 1.888 ms at 11 (8: 1.913, 16: 1.947), T=17 at B=128 0.910 -> 0.844 ms at 8;
-  // B=1024 (1040 k-blocks) is flat from 8 to 24.  VITB_WGRAD_MAX_SPLITS = n caps at n, -1 removes the cap.
+  // B=1024 (1040 k-blocks) is flat from 8 to 24 (12: 6.047 vs 6.071 ms).  VITB_WGRAD_MAX_SPLITS = n caps at n, -1 removes the cap.
   static const int max_splits = env_int("VITB_WGRAD_MAX_SPLITS", 0);
-  const int cap = max_splits > 0 ? max_splits : (max_splits < 0 ? s : (total / 24 > 8 ? total / 24 : 8));
+  // 8 splits up to 130 k-blocks, 10-11 at 260-272, 12 from 310 (B = 256: 1.944 -> 1.819 ms at 10, 1.837 at 8; B = 512: 3.184 -> 3.101 ms at 12)
+  int rule = 8 + (total - 130) / 45;
+  rule = rule < 8 ? 8 : (rule > 12 ? 12 : rule);
+  const int cap = max_splits > 0 ? max_splits : (max_splits < 0 ? s : rule);
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   if (s > total) s = total;
