@@ -1338,8 +1338,11 @@ static void wgrad_tc_plan(int M, int N, int K, int* splits, int* kb_total, int* 
   // B=1024 (1040 k-blocks) is flat from 8 to 24 (12: 6.047 vs 6.071 ms).  VITB_WGRAD_MAX_SPLITS = n caps at n, -1 removes the cap.
   static const int max_splits = env_int("VITB_WGRAD_MAX_SPLITS", 0);
   // 8 splits up to 130 k-blocks, 10-11 at 260-272, 12 from 310 (B = 256: 1.944 -> 1.819 ms at 10, 1.837 at 8; B = 512: 3.184 -> 3.101 ms at 12)
+  // From 1000 k-blocks (B = 1024 at T = 65) the old plan stays: the step is the same within the run-to-run band (6.047 vs 6.071 ms,
+  // 6.044 vs 6.210 ms) but a 12-split kernel takes twice as long by itself (0.30 instead of 0.39 of the tensor peak in isolation).
   int rule = 8 + (total - 130) / 45;
   rule = rule < 8 ? 8 : (rule > 12 ? 12 : rule);
+  if (total >= 1000) rule = s;
   const int cap = max_splits > 0 ? max_splits : (max_splits < 0 ? s : rule);
   if (s > cap) s = cap;
   if (s < 1) s = 1;
