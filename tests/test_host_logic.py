@@ -349,3 +349,25 @@ def test_fused_dp_slices_partition_the_flat_buffer():
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
             assert all(lo % 4 == 0 and hi % 4 == 0 and lo <= hi for lo, hi in edges)
             assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges[:-1] or edges) <= 4 * world or world == 1 or n < 64
+
+
+def test_weight_gradient_split_plan_follows_the_measured_rule():
+    """Host-side plan of the tensor-core weight gradients (csrc/gemm_tc.cu: wgrad_tc_plan): short reductions get 8-12 splits per
+    output tile (profiles/r2_wgrad_splits_ab.md), the benchmark size keeps one work item per SM."""
+    import ctypes
+    import vit_cifar_b200  # noqa: F401
+    from vit_cifar_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    f = lib.vitb_debug_wgrad_splits
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] * 3
+    rows = lambda B, T: B * T  # noqa: E731
+    assert f(rows(128, 65), 384, 384) == 8          # 130 k-blocks of 64 rows
+    assert f(rows(256, 65), 384, 384) == 10         # 260
+    assert f(rows(1024, 17), 384, 384) == 11        # 272
+    assert f(rows(512, 65), 384, 384) == 12         # 520
+    assert f(rows(1024, 65), 384, 384) == 24        # 1040: 148 SMs / 6 tiles
+    assert f(rows(128, 17), 384, 384) == 7          # 34 k-blocks: 8 asked for, 5 k-blocks each -> 7 items
+    assert f(100, 384, 384) == 2                    # never more splits than k-blocks
+    assert 1 <= f(rows(1024, 65), 1152, 384) <= 12  # wide output (27 tiles of 128 x 128, two streams): 148 * 2 / 27
+    assert f(rows(128, 65), 100, 384) == 0          # not a tensor-core shape (N % 128 != 0)

@@ -1360,6 +1360,14 @@ static bool wgrad_tc_ok(int N, int K, int flags, int dt) {
 static int wgrad_simt_splits(int M, int N, int K) { return simt_pick_splits(ceil_div(N, 64) * ceil_div(K, 64), M); }
 
 // workspace: [dW partials: splits*N*K][dbias partials: splits*N][colsum scratch (SIMT path)]
+/* tools / tests only (not in vitb200.h): splits of the reduction a bf16 tensor-core weight gradient of this shape would use */
+int vitb_debug_wgrad_splits(int M, int N, int K) {
+  if (!wgrad_tc_ok(N, K, 0, VITB_BF16) || M <= 0) return 0;
+  int splits, a, b;
+  wgrad_tc_plan(M, N, K, &splits, &a, &b);
+  return splits;
+}
+
 size_t vitb_gemm_wgrad_ws_bytes(int M, int N, int K, int dt) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int splits;
