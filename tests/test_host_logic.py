@@ -371,3 +371,31 @@ def test_weight_gradient_split_plan_follows_the_measured_rule():
     assert f(100, 384, 384) == 2                    # never more splits than k-blocks
     assert 1 <= f(rows(1024, 65), 1152, 384) <= 12  # wide output (27 tiles of 128 x 128, two streams): 148 * 2 / 27
     assert f(rows(128, 65), 100, 384) == 0          # not a tensor-core shape (N % 128 != 0)
+
+
+def test_committed_evidence_lines_carry_the_bench_contract():
+    """The bench lines committed under profiles/ (what DESIGN.md quotes) have every key of the bench.py contract, with sane values:
+    a kernel-only number, an end-to-end number below it with real host<->device bytes, a measured roofline and clean clocks."""
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r2_evidence_bench*.json")))
+    assert len(files) >= 6
+    for f in files:
+        d = json.load(open(f))
+        if d.get("impl") == "reference":
+            assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+            continue
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                  "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "step_ms"):
+            assert k in d, (f, k)
+        assert d["unit"] == "img/s" and d["dtype"] == "bf16" and d["higher_is_better"] is True and d["data"] == "synthetic"
+        assert d["warmup"] >= 3 and "workload" in d["config"] and "model" not in d["config"]
+        e = d["e2e"]
+        assert 0 < e["value"] <= d["value"] * 1.02 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+        assert d["gpu_launches"] >= 100 * d["steps"]          # > 100 of our kernels per step, counted by the library
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert not bad & set(d["clocks"]["reasons"]), (f, d["clocks"])
+        assert d["step_ms"]["p10"] <= d["step_ms"]["p50"] <= d["step_ms"]["p90"]
